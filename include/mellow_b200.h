@@ -1,0 +1,86 @@
+/* mellow_b200 -- C ABI of the B200-native Mellow inference path.
+ *
+ * The reference (soham97/mellow) has no FFI / plugin interface: its boundary is the Python class
+ * `MellowWrapper` (mellow/wrapper.py:25-287).  This library replaces what sits *under* that class:
+ *
+ *   reference call site                                              replaced by
+ *   ---------------------------------------------------------------  ------------------------------
+ *   model.to(f"cuda:{device}")                 wrapper.py:87-88       mb_create + mb_bind_weights
+ *   htsat.spectrogram_extractor/logmel/bn0     htsat.py:864-870       mb_frontend
+ *   AudioEncoder.forward (x2 clips)            mellow.py:64-68,105-6  mb_encode
+ *   DecoderModel.generate_prefix_inference     decoder.py:36-55       mb_prefix
+ *   lm(inputs_embeds=prefix).logits[:, -1]     wrapper.py:217-218     mb_prefill
+ *   the decode loop                            wrapper.py:216-249     mb_decode
+ *   generate_prefix_inference + _generate_batch wrapper.py:285-286    mb_generate / mb_generate_host
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure (message via mb_last_error).  Pointers are
+ * DEVICE pointers unless the name ends in `_host`.  One handle per device; a handle is not thread-safe; no device
+ * allocation happens after mb_create.  `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ * There is no CPU fallback: without a CUDA device mb_create fails.
+ */
+#ifndef MELLOW_B200_H
+#define MELLOW_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB_POLICY_SPLIT 0 /* bf16 hi/lo operand split, 3 MMA passes, fp32 KV cache: greedy ids match the fp32 reference */
+#define MB_POLICY_FAST 1  /* single bf16 operand plane, 1 MMA pass, bf16 KV cache: logits within bf16 tolerance */
+
+int mb_version(void);
+
+/* ---- weights: the library owns the arena layout; the host packer asks for it by entry name ---- */
+int mb_weight_entry_count(void);
+const char* mb_weight_entry_name(int i);
+long long mb_weight_entry_offset(int i);
+long long mb_weight_entry_bytes(int i);
+long long mb_weights_size(void);
+
+/* ---- lifetime ---- */
+void* mb_create(int device, int max_batch, int max_new_tokens, int policy);
+void mb_destroy(void* h);
+const char* mb_last_error(void* h); /* h may be NULL for mb_create failures */
+/* binds a packed device arena of mb_weights_size() bytes (caller keeps it alive; it is what gets NCCL-broadcast) */
+int mb_bind_weights(void* h, const void* dev_arena, long long nbytes);
+long long mb_workspace_bytes(void* h);
+int mb_set_gemm_engine(void* h, int engine); /* 0 = mma.sync bring-up engine, 1 = tcgen05 engine where a tile fits */
+long long mb_kernel_launches(void* h);       /* kernels launched by this handle so far (counting graph replays) */
+
+/* ---- stages (each can be profiled / parity-checked in isolation) ---- */
+/* wave [n_clips,320000] f32 -> logmel_out [n_clips,1001,64] (pre-BN, may be NULL), bn_out (post-bn0, may be NULL) */
+int mb_frontend(void* h, const float* wave, int n_clips, float* logmel_out, float* bn_out, void* stream);
+/* wave1, wave2 [B,320000] -> rows_out [2][B][33][576] f32 (may be NULL; the handle keeps its own copy for mb_prefix) */
+int mb_encode(void* h, const float* wave1, const float* wave2, int B, float* rows_out, void* stream);
+/* debug tap: run the encoder on `wave` [n_clips,320000] and copy the residual stream after stage `stage`:
+ * 0 = patch embed [n,4096,96], 1..4 = after Swin stage (incl. merging) [n,1024,192] [n,256,384] [n,64,768] [n,64,768],
+ * 5 = latent [n,768] followed by c2l frame rows [n,32,768] */
+int mb_encode_tap(void* h, const float* wave, int n_clips, int stage, float* out, void* stream);
+/* input_ids [B,129] i32 -> prefix_out [B,389,576] f32 (may be NULL); uses the rows of the last mb_encode */
+int mb_prefix(void* h, const int* input_ids, int B, float* prefix_out, void* stream);
+/* alternative to mb_encode+mb_prefix for tests: load an externally built prefix [B,389,576] */
+int mb_set_prefix(void* h, const float* prefix, int B, void* stream);
+/* LM prefill over the 389-token prefix, fills the KV cache; logits_out [B,49152] f32 of the last position (may be NULL) */
+int mb_prefill(void* h, int B, float* logits_out, void* stream);
+/* decode loop.  tokens_out [B,max_len] i32 (row stride max_len); *steps_out_host = number of valid columns (the
+ * reference breaks once every row has emitted eos_id).  logits_dump [max_len][B][49152] f32 (NULL = off);
+ * forced_tokens [B,max_len] i32 (NULL = off): teacher forcing, tokens_out still records the model's own argmax. */
+int mb_decode(void* h, int B, int max_len, float temperature, float top_p, int eos_id, int* tokens_out,
+              int* steps_out_host, float* logits_dump, const int* forced_tokens, void* stream);
+/* whole path from device buffers */
+int mb_generate(void* h, const float* wave1, const float* wave2, const int* input_ids, int B, int max_len,
+                float temperature, float top_p, int eos_id, int* tokens_out, int* steps_out_host, void* stream);
+/* whole path from HOST buffers (pinned recommended): H2D of the inputs and D2H of the tokens are inside the call */
+int mb_generate_host(void* h, const float* wave1_host, const float* wave2_host, const int* input_ids_host, int B,
+                     int max_len, float temperature, float top_p, int eos_id, int* tokens_out_host,
+                     int* steps_out_host, void* stream);
+
+/* ---- op-level test hooks (parity tests of single kernels) ---- */
+/* C[M,N] = A[M,K] * W[N,K]^T (+bias) with the library's GEMM engine and operand policy; fp32 device in/out */
+int mb_op_gemm(void* h, const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int act,
+               void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MELLOW_B200_H */

@@ -1,0 +1,779 @@
+// C ABI + orchestration of the Mellow inference path (see include/mellow_b200.h for the reference call sites each
+// entry point replaces).  Host code here only sequences kernel launches; all arithmetic is in the .cu kernels.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mellow_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace mb {
+
+cudaError_t launch_gemm_umma(const GemmArgs& g, int epi, cudaStream_t st, bool* handled);   // gemm_umma.cu
+
+namespace {
+
+constexpr int kDepths[4] = {2, 2, 6, 2};
+constexpr int kHeadsPerStage[4] = {4, 8, 16, 32};
+inline int stage_dim(int i) { return kEmbed << i; }
+inline int stage_res(int i) { return kGrid0 >> i; }
+
+struct Plane { const bf16* hi; const bf16* lo; };
+
+struct SwinBlockW {
+    const float *ln1_w, *ln1_b, *qkv_b, *relbias, *proj_b, *ln2_w, *ln2_b, *fc1_b, *fc2_b;
+    Plane qkv, proj, fc1, fc2;
+};
+struct MergeW { const float *ln_w, *ln_b; Plane red; };
+struct LmLayerW { const float *ln1, *ln2; Plane qkv, o, gu, down; };
+
+struct Weights {
+    // front end
+    const float *window, *twiddle, *melW, *bn_scale, *bn_shift;
+    const int *mel_lo, *mel_hi;
+    const float *pe_w, *pe_b, *pe_ln_w, *pe_ln_b;
+    SwinBlockW blk[4][6];
+    MergeW merge[3];
+    const float *tail_ln_w, *tail_ln_b, *tscam_b, *c2l_b, *proj_ln_w, *proj_ln_b;
+    Plane tscam, c2l, proj1, proj2;
+    // LM
+    const float *embed, *lm_norm, *rope_cos, *rope_sin;
+    Plane head;
+    LmLayerW layer[kLayers];
+};
+
+struct Entry { std::string name; size_t bytes; size_t offset; const void** slot; };
+
+struct Table {
+    std::vector<Entry> entries;
+    size_t total = 0;
+    void add(const std::string& name, size_t bytes, const void** slot) {
+        entries.push_back({name, bytes, total, slot});
+        total += (bytes + 255) / 256 * 256;
+    }
+    void f32(const std::string& n, size_t count, const float** slot) { add(n, count * 4, (const void**)slot); }
+    void i32(const std::string& n, size_t count, const int** slot) { add(n, count * 4, (const void**)slot); }
+    void plane(const std::string& n, size_t count, Plane* p) {
+        add(n + ".hi", count * 2, (const void**)&p->hi);
+        add(n + ".lo", count * 2, (const void**)&p->lo);
+    }
+};
+
+// The arena layout: single source of truth for the host packer (mellow_b200/weights.py asks by name).
+void build_table(Table& t, Weights& w) {
+    t.f32("fe.window", kNfft, &w.window);
+    t.f32("fe.twiddle", 1024, &w.twiddle);
+    t.f32("fe.melW", (size_t)kBins * kMels, &w.melW);
+    t.i32("fe.mel_lo", kMels, &w.mel_lo);
+    t.i32("fe.mel_hi", kMels, &w.mel_hi);
+    t.f32("fe.bn_scale", kMels, &w.bn_scale);
+    t.f32("fe.bn_shift", kMels, &w.bn_shift);
+    t.f32("pe.w", kEmbed * 16, &w.pe_w);
+    t.f32("pe.b", kEmbed, &w.pe_b);
+    t.f32("pe.ln_w", kEmbed, &w.pe_ln_w);
+    t.f32("pe.ln_b", kEmbed, &w.pe_ln_b);
+    for (int i = 0; i < 4; ++i) {
+        const size_t C = stage_dim(i);
+        for (int b = 0; b < kDepths[i]; ++b) {
+            SwinBlockW& k = w.blk[i][b];
+            const std::string p = "s" + std::to_string(i) + ".b" + std::to_string(b) + ".";
+            t.f32(p + "ln1_w", C, &k.ln1_w);
+            t.f32(p + "ln1_b", C, &k.ln1_b);
+            t.plane(p + "qkv_w", 3 * C * C, &k.qkv);
+            t.f32(p + "qkv_b", 3 * C, &k.qkv_b);
+            t.f32(p + "relbias", (size_t)kHeadsPerStage[i] * 64 * 64, &k.relbias);
+            t.plane(p + "proj_w", C * C, &k.proj);
+            t.f32(p + "proj_b", C, &k.proj_b);
+            t.f32(p + "ln2_w", C, &k.ln2_w);
+            t.f32(p + "ln2_b", C, &k.ln2_b);
+            t.plane(p + "fc1_w", 4 * C * C, &k.fc1);
+            t.f32(p + "fc1_b", 4 * C, &k.fc1_b);
+            t.plane(p + "fc2_w", 4 * C * C, &k.fc2);
+            t.f32(p + "fc2_b", C, &k.fc2_b);
+        }
+        if (i < 3) {
+            const std::string p = "m" + std::to_string(i) + ".";
+            t.f32(p + "ln_w", 4 * C, &w.merge[i].ln_w);
+            t.f32(p + "ln_b", 4 * C, &w.merge[i].ln_b);
+            t.plane(p + "red_w", 8 * C * C, &w.merge[i].red);
+        }
+    }
+    t.f32("tail.ln_w", kEncOut, &w.tail_ln_w);
+    t.f32("tail.ln_b", kEncOut, &w.tail_ln_b);
+    t.plane("tail.tscam_w", (size_t)kClasses * 6 * kEncOut, &w.tscam);
+    t.f32("tail.tscam_b", kClasses, &w.tscam_b);
+    t.plane("tail.c2l_w", (size_t)kEncOut * kClassesPad, &w.c2l);
+    t.f32("tail.c2l_b", kEncOut, &w.c2l_b);
+    t.plane("proj.w1", (size_t)kProj * kEncOut, &w.proj1);
+    t.plane("proj.w2", (size_t)kProj * kProj, &w.proj2);
+    t.f32("proj.ln_w", kProj, &w.proj_ln_w);
+    t.f32("proj.ln_b", kProj, &w.proj_ln_b);
+    t.f32("lm.embed", (size_t)kVocab * kHidden, &w.embed);
+    t.plane("lm.head_w", (size_t)kVocab * kHidden, &w.head);
+    t.f32("lm.norm", kHidden, &w.lm_norm);
+    t.f32("lm.rope_cos", (size_t)kMaxPos * 32, &w.rope_cos);
+    t.f32("lm.rope_sin", (size_t)kMaxPos * 32, &w.rope_sin);
+    for (int l = 0; l < kLayers; ++l) {
+        LmLayerW& k = w.layer[l];
+        const std::string p = "lm.l" + std::to_string(l) + ".";
+        t.f32(p + "ln1", kHidden, &k.ln1);
+        t.plane(p + "qkv_w", (size_t)kQkvDim * kHidden, &k.qkv);
+        t.plane(p + "o_w", (size_t)kHidden * kHidden, &k.o);
+        t.f32(p + "ln2", kHidden, &k.ln2);
+        t.plane(p + "gu_w", (size_t)2 * kInter * kHidden, &k.gu);
+        t.plane(p + "down_w", (size_t)kHidden * kInter, &k.down);
+    }
+}
+
+struct Layout {
+    Weights w;
+    Table t;
+    Layout() { build_table(t, w); }
+};
+Layout& layout() {
+    static Layout L;
+    return L;
+}
+
+thread_local char g_create_error[512] = "";
+
+struct Handle {
+    int device = 0, max_batch = 0, max_new = 0, policy = 0, engine = 0;
+    int t_max = 0;
+    bool bound = false;
+    Weights w;
+    Table t;
+    char err[512] = "";
+    long long launches = 0;
+    size_t ws_bytes = 0;
+    std::vector<void*> allocs;
+    // encoder workspace (N = 2*max_batch clips)
+    float *bn = nullptr, *xa = nullptr, *xb = nullptr, *qkv = nullptr;
+    bf16 *a_hi = nullptr, *a_lo = nullptr, *h_hi = nullptr, *h_lo = nullptr;
+    float *ytail = nullptr, *latent = nullptr, *frames = nullptr, *e1 = nullptr, *s33 = nullptr, *rows33 = nullptr;
+    bf16 *col_hi = nullptr, *col_lo = nullptr, *cls_hi = nullptr, *cls_lo = nullptr;
+    bf16 *a33_hi = nullptr, *a33_lo = nullptr, *g33_hi = nullptr, *g33_lo = nullptr;
+    // LM workspace (M = max_batch*389 rows)
+    float *x = nullptr, *q = nullptr, *logits = nullptr;
+    bf16 *la_hi = nullptr, *la_lo = nullptr, *lh_hi = nullptr, *lh_lo = nullptr;
+    void *kcache = nullptr, *vcache = nullptr;
+    size_t kv_layer_elems = 0;
+    float *part_acc = nullptr, *part_ml = nullptr;
+    int *d_tokens = nullptr, *d_done = nullptr, *d_step = nullptr, *d_stop = nullptr, *d_ids = nullptr;
+    float *wave_stage = nullptr;
+    int prefix_B = 0;
+    // decode graph cache
+    cudaGraphExec_t graph = nullptr;
+    int g_B = 0, g_max_len = 0, g_eos = 0, g_launches = 0;
+    float g_temp = 0.f;
+    cudaStream_t g_stream = nullptr;
+    cudaStream_t own_stream = nullptr;   // used when the caller passes NULL (the legacy stream cannot be graph-captured)
+};
+
+inline cudaStream_t pick_stream(Handle* h, void* stream) { return stream ? (cudaStream_t)stream : h->own_stream; }
+
+#define MB_CK(h, expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (expr);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            snprintf((h)->err, sizeof((h)->err), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                     __FILE__, __LINE__);                                                                \
+            return 1;                                                                                    \
+        }                                                                                                \
+    } while (0)
+
+#define MB_TRY(expr)            \
+    do {                        \
+        int r__ = (expr);       \
+        if (r__ != 0) return r__; \
+    } while (0)
+
+int fail(Handle* h, const char* msg) {
+    snprintf(h->err, sizeof(h->err), "%s", msg);
+    return 1;
+}
+
+template <typename T>
+int dev_alloc(Handle* h, T** p, size_t count) {
+    void* q = nullptr;
+    const size_t bytes = (count * sizeof(T) + 255) / 256 * 256;
+    MB_CK(h, cudaMalloc(&q, bytes));
+    h->allocs.push_back(q);
+    h->ws_bytes += bytes;
+    *p = reinterpret_cast<T*>(q);
+    return 0;
+}
+
+inline const bf16* lo_of(const Handle* h, const bf16* lo) { return h->policy == kPolicySplit ? lo : nullptr; }
+inline bf16* lo_of(const Handle* h, bf16* lo) { return h->policy == kPolicySplit ? lo : nullptr; }
+
+GemmArgs gemm_base(const Handle* h, const bf16* a_hi, const bf16* a_lo, int lda, Plane wgt, int ldw, int M, int N, int K) {
+    GemmArgs g;
+    memset(&g, 0, sizeof(g));
+    g.A_hi = a_hi; g.A_lo = lo_of(h, a_lo); g.lda = lda;
+    g.W_hi = wgt.hi; g.W_lo = lo_of(h, wgt.lo); g.ldw = ldw;
+    g.M = M; g.N = N; g.K = K;
+    g.passes = h->policy == kPolicySplit ? 3 : 1;
+    return g;
+}
+
+int run_gemm(Handle* h, const GemmArgs& g, int epi, cudaStream_t st) {
+    if (h->engine == 1) {
+        bool handled = false;
+        MB_CK(h, launch_gemm_umma(g, epi, st, &handled));
+        if (handled) { h->launches++; return 0; }
+    }
+    MB_CK(h, launch_gemm_mma(g, epi, st));
+    h->launches++;
+    return 0;
+}
+
+int run_norm(Handle* h, int kind, const float* x, const float* w, const float* b, int rows, int C, bf16* hi, bf16* lo,
+             float* out_f32, int row_stride, int row_off, int res, cudaStream_t st) {
+    NormArgs a;
+    a.x = x; a.w = w; a.b = b;
+    a.out_hi = hi; a.out_lo = hi ? lo_of(h, lo) : nullptr; a.out_f32 = out_f32;
+    a.rows = rows; a.C = C; a.row_stride = row_stride; a.row_off = row_off; a.res = res;
+    MB_CK(h, launch_norm(a, kind, st));
+    h->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ encoder
+int swin_block(Handle* h, float* x, int n_clips, int stage, int b, cudaStream_t st) {
+    const int C = stage_dim(stage), R = stage_res(stage), nH = kHeadsPerStage[stage];
+    const int M = n_clips * R * R;
+    const int shift = (b % 2 == 1 && R > kWin) ? kWin / 2 : 0;      // htsat.py:539, 368-371
+    const SwinBlockW& k = h->w.blk[stage][b];
+    MB_TRY(run_norm(h, NORM_LN, x, k.ln1_w, k.ln1_b, M, C, h->a_hi, h->a_lo, nullptr, 1, 0, 0, st));
+    {
+        GemmArgs g = gemm_base(h, h->a_hi, h->a_lo, C, k.qkv, C, M, 3 * C, C);
+        g.bias = k.qkv_b; g.out_f32 = h->qkv; g.ldo = 3 * C;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    MB_CK(h, launch_window_attention(h->qkv, k.relbias, h->a_hi, lo_of(h, h->a_lo), n_clips, R, C, nH, shift, st));
+    h->launches++;
+    {
+        GemmArgs g = gemm_base(h, h->a_hi, h->a_lo, C, k.proj, C, M, C, C);
+        g.bias = k.proj_b; g.residual = x; g.ldr = C; g.out_f32 = x; g.ldo = C;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    MB_TRY(run_norm(h, NORM_LN, x, k.ln2_w, k.ln2_b, M, C, h->a_hi, h->a_lo, nullptr, 1, 0, 0, st));
+    {
+        GemmArgs g = gemm_base(h, h->a_hi, h->a_lo, C, k.fc1, C, M, 4 * C, C);
+        g.bias = k.fc1_b; g.act = ACT_GELU; g.out_hi = h->h_hi; g.out_lo = lo_of(h, h->h_lo); g.ldp = 4 * C;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    {
+        GemmArgs g = gemm_base(h, h->h_hi, h->h_lo, 4 * C, k.fc2, 4 * C, M, C, 4 * C);
+        g.bias = k.fc2_b; g.residual = x; g.ldr = C; g.out_f32 = x; g.ldo = C;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    return 0;
+}
+
+// bn [n,1001,64] -> rows33 (or a tap).  Returns the buffer holding the residual stream in *x_final.
+int encoder_body(Handle* h, int n_clips, int stop_stage, float* tap_out, float* rows_out, cudaStream_t st) {
+    PatchW pw{h->w.pe_w, h->w.pe_b, h->w.pe_ln_w, h->w.pe_ln_b};
+    MB_CK(h, launch_patch_embed(h->bn, n_clips, pw, h->xa, st));
+    h->launches++;
+    float* x = h->xa;
+    float* other = h->xb;
+    auto tap = [&](int stage_id, const float* src, size_t count) -> int {
+        if (tap_out && stop_stage == stage_id) {
+            MB_CK(h, cudaMemcpyAsync(tap_out, src, count * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            return 2;
+        }
+        return 0;
+    };
+    int r = tap(0, x, (size_t)n_clips * 4096 * kEmbed);
+    if (r) return r == 2 ? 0 : r;
+    for (int i = 0; i < 4; ++i) {
+        const int C = stage_dim(i), R = stage_res(i);
+        for (int b = 0; b < kDepths[i]; ++b) MB_TRY(swin_block(h, x, n_clips, i, b, st));
+        size_t count = (size_t)n_clips * R * R * C;
+        if (i < 3) {
+            const int M4 = n_clips * (R / 2) * (R / 2);
+            MB_TRY(run_norm(h, NORM_LN_MERGE, x, h->w.merge[i].ln_w, h->w.merge[i].ln_b, M4, 4 * C, h->a_hi, h->a_lo,
+                            nullptr, 1, 0, R, st));
+            GemmArgs g = gemm_base(h, h->a_hi, h->a_lo, 4 * C, h->w.merge[i].red, 4 * C, M4, 2 * C, 4 * C);
+            g.out_f32 = other; g.ldo = 2 * C;
+            MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+            float* tmp = x; x = other; other = tmp;
+            count = (size_t)M4 * 2 * C;
+        }
+        r = tap(i + 1, x, count);
+        if (r) return r == 2 ? 0 : r;
+    }
+    // tail: final LN, latent mean, TSCAM conv as GEMM (+sigmoid), c2l, projection -- on the 33 unique rows per clip
+    const int Mt = n_clips * 64;
+    MB_TRY(run_norm(h, NORM_LN, x, h->w.tail_ln_w, h->w.tail_ln_b, Mt, kEncOut, nullptr, nullptr, h->ytail, 1, 0, 0, st));
+    MB_CK(h, launch_tail_gather(h->ytail, n_clips, h->latent, h->col_hi, lo_of(h, h->col_lo), st));
+    h->launches++;
+    {
+        GemmArgs g = gemm_base(h, h->col_hi, h->col_lo, 6 * kEncOut, h->w.tscam, 6 * kEncOut, n_clips * 32, kClasses, 6 * kEncOut);
+        g.bias = h->w.tscam_b; g.act = ACT_SIGMOID; g.out_hi = h->cls_hi; g.out_lo = lo_of(h, h->cls_lo); g.ldp = kClassesPad;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    {
+        GemmArgs g = gemm_base(h, h->cls_hi, h->cls_lo, kClassesPad, h->w.c2l, kClassesPad, n_clips * 32, kEncOut, kClassesPad);
+        g.bias = h->w.c2l_b; g.out_f32 = h->frames; g.ldo = kEncOut;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    if (tap_out && stop_stage == 5) {
+        MB_CK(h, cudaMemcpyAsync(tap_out, h->latent, (size_t)n_clips * kEncOut * 4, cudaMemcpyDeviceToDevice, st));
+        MB_CK(h, cudaMemcpyAsync(tap_out + (size_t)n_clips * kEncOut, h->frames, (size_t)n_clips * 32 * kEncOut * 4,
+                                 cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    MB_CK(h, launch_assemble33(h->latent, h->frames, n_clips, h->a33_hi, lo_of(h, h->a33_lo), st));
+    h->launches++;
+    const int M33 = n_clips * kAudioRows;
+    {
+        GemmArgs g = gemm_base(h, h->a33_hi, h->a33_lo, kEncOut, h->w.proj1, kEncOut, M33, kProj, kEncOut);
+        g.out_f32 = h->e1; g.ldo = kProj;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    MB_CK(h, launch_gelu_planes(h->e1, (size_t)M33 * kProj, h->g33_hi, lo_of(h, h->g33_lo), st));
+    h->launches++;
+    {
+        GemmArgs g = gemm_base(h, h->g33_hi, h->g33_lo, kProj, h->w.proj2, kProj, M33, kProj, kProj);
+        g.residual = h->e1; g.ldr = kProj; g.out_f32 = h->s33; g.ldo = kProj;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    MB_TRY(run_norm(h, NORM_LN, h->s33, h->w.proj_ln_w, h->w.proj_ln_b, M33, kProj, nullptr, nullptr, h->rows33, 1, 0, 0, st));
+    if (rows_out)
+        MB_CK(h, cudaMemcpyAsync(rows_out, h->rows33, (size_t)M33 * kProj * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int frontend(Handle* h, const float* wave, int n_clips, float* logmel_out, float* bn_out, cudaStream_t st) {
+    FrontendW fw{h->w.window, h->w.twiddle, h->w.melW, h->w.mel_lo, h->w.mel_hi, h->w.bn_scale, h->w.bn_shift};
+    MB_CK(h, launch_logmel(wave, n_clips, fw, logmel_out, bn_out, st));
+    h->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ LM
+inline void* kv_layer(const Handle* h, void* base, int l) {
+    const size_t esz = h->policy == kPolicyFast ? 2 : 4;
+    return reinterpret_cast<char*>(base) + (size_t)l * h->kv_layer_elems * esz;
+}
+
+// one transformer layer over M rows of h->x.  prefill: rows_per_seq = 389; decode: rows_per_seq = 1.
+int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_t st) {
+    const LmLayerW& k = h->w.layer[l];
+    const int M = B * rows_per_seq;
+    MB_TRY(run_norm(h, NORM_RMS, h->x, k.ln1, nullptr, M, kHidden, h->la_hi, h->la_lo, nullptr, 1, 0, 0, st));
+    {
+        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.qkv, kHidden, M, kQkvDim, kHidden);
+        g.q_out = h->q;
+        g.k_cache = kv_layer(h, h->kcache, l); g.v_cache = kv_layer(h, h->vcache, l);
+        g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
+        g.rows_per_seq = rows_per_seq;
+        g.pos_base = decode ? kPrefix - 1 : 0;
+        g.d_pos = decode ? h->d_step : nullptr;
+        g.t_max = h->t_max; g.kv_bf16 = h->policy == kPolicyFast;
+        MB_TRY(run_gemm(h, g, EPI_QKV_ROPE, st));
+    }
+    if (decode) {
+        DecodeAttnArgs a;
+        a.q = h->q; a.kc = kv_layer(h, h->kcache, l); a.vc = kv_layer(h, h->vcache, l);
+        a.kv_bf16 = h->policy == kPolicyFast; a.B = B; a.t_max = h->t_max;
+        int ns = (888 + 3 * B - 1) / (3 * B);
+        a.nsplit = ns < 1 ? 1 : (ns > 8 ? 8 : ns);
+        a.ctx_base = kPrefix; a.d_step = h->d_step;
+        a.part_acc = h->part_acc; a.part_ml = h->part_ml;
+        a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
+        MB_CK(h, launch_decode_attention(a, st));
+        h->launches += 2;
+    } else {
+        MB_CK(h, launch_prefill_attention(h->q, kv_layer(h, h->kcache, l), kv_layer(h, h->vcache, l),
+                                          h->policy == kPolicyFast, B, rows_per_seq, h->t_max, h->la_hi,
+                                          lo_of(h, h->la_lo), st));
+        h->launches++;
+    }
+    {
+        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.o, kHidden, M, kHidden, kHidden);
+        g.residual = h->x; g.ldr = kHidden; g.out_f32 = h->x; g.ldo = kHidden;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    MB_TRY(run_norm(h, NORM_RMS, h->x, k.ln2, nullptr, M, kHidden, h->la_hi, h->la_lo, nullptr, 1, 0, 0, st));
+    {
+        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.gu, kHidden, M, 2 * kInter, kHidden);
+        g.out_hi = h->lh_hi; g.out_lo = lo_of(h, h->lh_lo); g.ldp = kInter;
+        MB_TRY(run_gemm(h, g, EPI_SWIGLU, st));
+    }
+    {
+        GemmArgs g = gemm_base(h, h->lh_hi, h->lh_lo, kInter, k.down, kInter, M, kHidden, kInter);
+        g.residual = h->x; g.ldr = kHidden; g.out_f32 = h->x; g.ldo = kHidden;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    return 0;
+}
+
+// final RMSNorm of one row per sequence + lm_head -> h->logits [B,V]
+int lm_head(Handle* h, int B, int row_stride, int row_off, cudaStream_t st) {
+    MB_TRY(run_norm(h, NORM_RMS, h->x, h->w.lm_norm, nullptr, B, kHidden, h->la_hi, h->la_lo, nullptr, row_stride,
+                    row_off, 0, st));
+    GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, h->w.head, kHidden, B, kVocab, kHidden);
+    g.out_f32 = h->logits; g.ldo = kVocab;
+    return run_gemm(h, g, EPI_GENERIC, st);
+}
+
+int decode_step(Handle* h, int B, cudaStream_t st) {
+    for (int l = 0; l < kLayers; ++l) MB_TRY(lm_layer(h, l, B, 1, true, st));
+    return lm_head(h, B, 1, 0, st);
+}
+
+int sample_and_advance(Handle* h, int B, int max_len, float temperature, float top_p, int eos_id, float* logits_dump,
+                       const int* forced, cudaStream_t st) {
+    SampleArgs a;
+    a.logits = h->logits; a.embed = h->w.embed; a.B = B; a.max_len = max_len; a.eos_id = eos_id;
+    a.temperature = temperature; a.top_p = top_p; a.d_step = h->d_step; a.tokens_out = h->d_tokens;
+    a.forced = forced; a.x_next = h->x; a.done = h->d_done; a.logits_dump = logits_dump;
+    MB_CK(h, launch_sample(a, st));
+    MB_CK(h, launch_step_advance(h->d_step, h->d_done, B, h->d_stop, st));
+    h->launches += 2;
+    return 0;
+}
+
+int check_ready(Handle* h, int B) {
+    if (!h->bound) return fail(h, "weights not bound (call mb_bind_weights first)");
+    if (B < 1 || B > h->max_batch) return fail(h, "batch size out of range for this handle");
+    return 0;
+}
+
+int do_prefill(Handle* h, int B, float* logits_out, cudaStream_t st) {
+    for (int l = 0; l < kLayers; ++l) MB_TRY(lm_layer(h, l, B, kPrefix, false, st));
+    MB_TRY(lm_head(h, B, kPrefix, kPrefix - 1, st));
+    if (logits_out)
+        MB_CK(h, cudaMemcpyAsync(logits_out, h->logits, (size_t)B * kVocab * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int do_decode(Handle* h, int B, int max_len, float temperature, float top_p, int eos_id, int* tokens_out,
+              int tokens_on_host, int* steps_out_host, float* logits_dump, const int* forced, cudaStream_t st) {
+    if (max_len < 1 || max_len > h->max_new) return fail(h, "max_len out of range for this handle");
+    MB_CK(h, cudaMemsetAsync(h->d_step, 0, sizeof(int), st));
+    MB_CK(h, cudaMemsetAsync(h->d_done, 0, sizeof(int) * B, st));
+    MB_CK(h, cudaMemsetAsync(h->d_stop, 0xff, sizeof(int), st));
+    MB_CK(h, cudaMemsetAsync(h->d_tokens, 0, sizeof(int) * (size_t)B * max_len, st));
+    // step 0: logits come from the prefill
+    MB_TRY(sample_and_advance(h, B, max_len, temperature, top_p, eos_id, logits_dump, forced, st));
+    const bool use_graph = !logits_dump && !forced && getenv("MB_NO_GRAPH") == nullptr;
+    int stop = -1;
+    if (use_graph && max_len > 1) {
+        const bool hit = h->graph && h->g_B == B && h->g_max_len == max_len && h->g_eos == eos_id &&
+                         h->g_temp == temperature && h->g_stream == st;
+        if (!hit) {
+            if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+            cudaGraph_t graph = nullptr;
+            const long long before = h->launches;
+            MB_CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            int rc = decode_step(h, B, st);
+            if (rc == 0) rc = sample_and_advance(h, B, max_len, temperature, top_p, eos_id, nullptr, nullptr, st);
+            cudaError_t ce = cudaStreamEndCapture(st, &graph);
+            if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+            MB_CK(h, ce);
+            h->g_launches = (int)(h->launches - before);
+            h->launches = before;
+            MB_CK(h, cudaGraphInstantiate(&h->graph, graph, 0));
+            cudaGraphDestroy(graph);
+            h->g_B = B; h->g_max_len = max_len; h->g_eos = eos_id; h->g_temp = temperature; h->g_stream = st;
+        }
+    }
+    for (int s = 1; s < max_len; ++s) {
+        if (use_graph) {
+            MB_CK(h, cudaGraphLaunch(h->graph, st));
+            h->launches += h->g_launches;
+        } else {
+            MB_TRY(decode_step(h, B, st));
+            MB_TRY(sample_and_advance(h, B, max_len, temperature, top_p, eos_id, logits_dump, forced, st));
+        }
+        if ((s & 15) == 0) {          // the reference syncs every step (wrapper.py:248); poll the stop flag sparsely
+            MB_CK(h, cudaMemcpyAsync(&stop, h->d_stop, sizeof(int), cudaMemcpyDeviceToHost, st));
+            MB_CK(h, cudaStreamSynchronize(st));
+            if (stop >= 0) break;
+        }
+    }
+    MB_CK(h, cudaMemcpyAsync(&stop, h->d_stop, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (tokens_out)
+        MB_CK(h, cudaMemcpyAsync(tokens_out, h->d_tokens, sizeof(int) * (size_t)B * max_len,
+                                 tokens_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
+    MB_CK(h, cudaStreamSynchronize(st));
+    if (steps_out_host) *steps_out_host = stop >= 0 ? stop : max_len;
+    return 0;
+}
+
+int do_generate(Handle* h, const float* w1, const float* w2, const int* ids, int B, int max_len, float temperature,
+                float top_p, int eos_id, int* tokens_out, int tokens_on_host, int* steps_out_host, cudaStream_t st) {
+    MB_TRY(frontend(h, w1, B, nullptr, h->bn, st));
+    MB_TRY(frontend(h, w2, B, nullptr, h->bn + (size_t)B * kFrames * kMels, st));
+    MB_TRY(encoder_body(h, 2 * B, -1, nullptr, nullptr, st));
+    MB_CK(h, launch_prefix(h->rows33, ids, h->w.embed, B, h->x, st));
+    h->launches++;
+    h->prefix_B = B;
+    MB_TRY(do_prefill(h, B, nullptr, st));
+    return do_decode(h, B, max_len, temperature, top_p, eos_id, tokens_out, tokens_on_host, steps_out_host, nullptr,
+                     nullptr, st);
+}
+
+}  // namespace
+}  // namespace mb
+
+using namespace mb;
+
+extern "C" {
+
+int mb_version(void) { return 1; }
+int mb_weight_entry_count(void) { return (int)layout().t.entries.size(); }
+const char* mb_weight_entry_name(int i) { return layout().t.entries[i].name.c_str(); }
+long long mb_weight_entry_offset(int i) { return (long long)layout().t.entries[i].offset; }
+long long mb_weight_entry_bytes(int i) { return (long long)layout().t.entries[i].bytes; }
+long long mb_weights_size(void) { return (long long)layout().t.total; }
+
+const char* mb_last_error(void* hv) { return hv ? reinterpret_cast<Handle*>(hv)->err : g_create_error; }
+
+void mb_destroy(void* hv) {
+    if (!hv) return;
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    cudaSetDevice(h->device);
+    if (h->graph) cudaGraphExecDestroy(h->graph);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (void* p : h->allocs) cudaFree(p);
+    delete h;
+}
+
+static int create_body(Handle* h) {
+    const size_t N = 2 * (size_t)h->max_batch;           // clips
+    const size_t M0 = N * 4096;                          // stage-0 tokens
+    MB_TRY(dev_alloc(h, &h->bn, N * kFrames * kMels));
+    MB_TRY(dev_alloc(h, &h->xa, M0 * kEmbed));
+    MB_TRY(dev_alloc(h, &h->xb, M0 * kEmbed / 2));
+    MB_TRY(dev_alloc(h, &h->qkv, M0 * 3 * kEmbed));
+    MB_TRY(dev_alloc(h, &h->a_hi, M0 * kEmbed));
+    MB_TRY(dev_alloc(h, &h->a_lo, M0 * kEmbed));
+    MB_TRY(dev_alloc(h, &h->h_hi, M0 * 4 * kEmbed));
+    MB_TRY(dev_alloc(h, &h->h_lo, M0 * 4 * kEmbed));
+    MB_TRY(dev_alloc(h, &h->ytail, N * 64 * kEncOut));
+    MB_TRY(dev_alloc(h, &h->latent, N * kEncOut));
+    MB_TRY(dev_alloc(h, &h->frames, N * 32 * kEncOut));
+    MB_TRY(dev_alloc(h, &h->col_hi, N * 32 * 6 * kEncOut));
+    MB_TRY(dev_alloc(h, &h->col_lo, N * 32 * 6 * kEncOut));
+    MB_TRY(dev_alloc(h, &h->cls_hi, N * 32 * kClassesPad));
+    MB_TRY(dev_alloc(h, &h->cls_lo, N * 32 * kClassesPad));
+    MB_CK(h, cudaMemset(h->cls_hi, 0, N * 32 * kClassesPad * 2));
+    MB_CK(h, cudaMemset(h->cls_lo, 0, N * 32 * kClassesPad * 2));
+    MB_TRY(dev_alloc(h, &h->a33_hi, N * kAudioRows * kEncOut));
+    MB_TRY(dev_alloc(h, &h->a33_lo, N * kAudioRows * kEncOut));
+    MB_TRY(dev_alloc(h, &h->g33_hi, N * kAudioRows * kProj));
+    MB_TRY(dev_alloc(h, &h->g33_lo, N * kAudioRows * kProj));
+    MB_TRY(dev_alloc(h, &h->e1, N * kAudioRows * kProj));
+    MB_TRY(dev_alloc(h, &h->s33, N * kAudioRows * kProj));
+    MB_TRY(dev_alloc(h, &h->rows33, N * kAudioRows * kProj));
+    const size_t B = h->max_batch, M = B * kPrefix;
+    MB_TRY(dev_alloc(h, &h->x, M * kHidden));
+    MB_TRY(dev_alloc(h, &h->q, M * kHidden));
+    MB_TRY(dev_alloc(h, &h->la_hi, M * kHidden));
+    MB_TRY(dev_alloc(h, &h->la_lo, M * kHidden));
+    MB_TRY(dev_alloc(h, &h->lh_hi, M * kInter));
+    MB_TRY(dev_alloc(h, &h->lh_lo, M * kInter));
+    MB_TRY(dev_alloc(h, &h->logits, B * kVocab));
+    h->t_max = kPrefix + h->max_new;
+    h->kv_layer_elems = B * kKvHeads * h->t_max * kHeadDim;
+    const size_t esz = h->policy == kPolicyFast ? 2 : 4;
+    char* kc = nullptr; char* vc = nullptr;
+    MB_TRY(dev_alloc(h, &kc, h->kv_layer_elems * kLayers * esz));
+    MB_TRY(dev_alloc(h, &vc, h->kv_layer_elems * kLayers * esz));
+    h->kcache = kc; h->vcache = vc;
+    MB_TRY(dev_alloc(h, &h->part_acc, B * kHeads * 8 * kHeadDim));
+    MB_TRY(dev_alloc(h, &h->part_ml, B * kHeads * 8 * 2));
+    MB_TRY(dev_alloc(h, &h->d_tokens, B * h->max_new));
+    MB_TRY(dev_alloc(h, &h->d_done, B));
+    MB_TRY(dev_alloc(h, &h->d_step, 4));
+    MB_TRY(dev_alloc(h, &h->d_stop, 4));
+    MB_TRY(dev_alloc(h, &h->d_ids, B * kTextLen));
+    MB_TRY(dev_alloc(h, &h->wave_stage, N * kClipSamples));
+    return 0;
+}
+
+void* mb_create(int device, int max_batch, int max_new_tokens, int policy) {
+    g_create_error[0] = 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        snprintf(g_create_error, sizeof(g_create_error), "no CUDA device available (%s); mellow_b200 has no CPU fallback",
+                 cudaGetErrorString(e));
+        return nullptr;
+    }
+    if (device < 0 || device >= count || max_batch < 1 || max_new_tokens < 1 || kPrefix + max_new_tokens > kMaxPos ||
+        (policy != kPolicySplit && policy != kPolicyFast)) {
+        snprintf(g_create_error, sizeof(g_create_error), "mb_create: invalid argument");
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major != 10) {
+        snprintf(g_create_error, sizeof(g_create_error), "device %d is sm_%d%d; this library is built for sm_100a only",
+                 device, prop.major, prop.minor);
+        return nullptr;
+    }
+    cudaSetDevice(device);
+    Handle* h = new Handle();
+    h->device = device; h->max_batch = max_batch; h->max_new = max_new_tokens; h->policy = policy;
+    build_table(h->t, h->w);
+    // a blocking stream: implicitly ordered with work the caller issued on the legacy default stream
+    if (cudaStreamCreate(&h->own_stream) != cudaSuccess || create_body(h) != 0) {
+        snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
+        mb_destroy(h);
+        return nullptr;
+    }
+    return h;
+}
+
+int mb_bind_weights(void* hv, const void* dev_arena, long long nbytes) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    if (nbytes != (long long)h->t.total) return fail(h, "weight arena size mismatch");
+    if (((uintptr_t)dev_arena & 255) != 0) return fail(h, "weight arena must be 256-byte aligned");
+    for (auto& e : h->t.entries) *e.slot = reinterpret_cast<const char*>(dev_arena) + e.offset;
+    h->bound = true;
+    return 0;
+}
+
+long long mb_workspace_bytes(void* hv) { return (long long)reinterpret_cast<Handle*>(hv)->ws_bytes; }
+int mb_set_gemm_engine(void* hv, int engine) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    if (engine != 0 && engine != 1) return fail(h, "unknown GEMM engine");
+    h->engine = engine;
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    return 0;
+}
+long long mb_kernel_launches(void* hv) { return reinterpret_cast<Handle*>(hv)->launches; }
+
+int mb_frontend(void* hv, const float* wave, int n_clips, float* logmel_out, float* bn_out, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    if (!h->bound) return fail(h, "weights not bound");
+    if (n_clips < 1) return fail(h, "n_clips < 1");
+    cudaSetDevice(h->device);
+    return frontend(h, wave, n_clips, logmel_out, bn_out, pick_stream(h, stream));
+}
+
+int mb_encode(void* hv, const float* wave1, const float* wave2, int B, float* rows_out, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    MB_TRY(check_ready(h, B));
+    cudaSetDevice(h->device);
+    cudaStream_t st = pick_stream(h, stream);
+    MB_TRY(frontend(h, wave1, B, nullptr, h->bn, st));
+    MB_TRY(frontend(h, wave2, B, nullptr, h->bn + (size_t)B * kFrames * kMels, st));
+    return encoder_body(h, 2 * B, -1, nullptr, rows_out, st);
+}
+
+int mb_encode_tap(void* hv, const float* wave, int n_clips, int stage, float* out, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    if (!h->bound) return fail(h, "weights not bound");
+    if (n_clips < 1 || n_clips > 2 * h->max_batch || stage < 0 || stage > 5) return fail(h, "bad tap arguments");
+    cudaSetDevice(h->device);
+    cudaStream_t st = pick_stream(h, stream);
+    MB_TRY(frontend(h, wave, n_clips, nullptr, h->bn, st));
+    return encoder_body(h, n_clips, stage, out, nullptr, st);
+}
+
+int mb_prefix(void* hv, const int* input_ids, int B, float* prefix_out, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    MB_TRY(check_ready(h, B));
+    cudaSetDevice(h->device);
+    cudaStream_t st = pick_stream(h, stream);
+    MB_CK(h, launch_prefix(h->rows33, input_ids, h->w.embed, B, h->x, st));
+    h->launches++;
+    h->prefix_B = B;
+    if (prefix_out)
+        MB_CK(h, cudaMemcpyAsync(prefix_out, h->x, (size_t)B * kPrefix * kHidden * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+int mb_set_prefix(void* hv, const float* prefix, int B, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    MB_TRY(check_ready(h, B));
+    cudaSetDevice(h->device);
+    MB_CK(h, cudaMemcpyAsync(h->x, prefix, (size_t)B * kPrefix * kHidden * 4, cudaMemcpyDeviceToDevice, pick_stream(h, stream)));
+    h->prefix_B = B;
+    return 0;
+}
+
+int mb_prefill(void* hv, int B, float* logits_out, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    MB_TRY(check_ready(h, B));
+    if (h->prefix_B != B) return fail(h, "mb_prefill: no prefix of this batch size (call mb_prefix / mb_set_prefix)");
+    cudaSetDevice(h->device);
+    return do_prefill(h, B, logits_out, pick_stream(h, stream));
+}
+
+int mb_decode(void* hv, int B, int max_len, float temperature, float top_p, int eos_id, int* tokens_out,
+              int* steps_out_host, float* logits_dump, const int* forced_tokens, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    MB_TRY(check_ready(h, B));
+    cudaSetDevice(h->device);
+    return do_decode(h, B, max_len, temperature, top_p, eos_id, tokens_out, 0, steps_out_host, logits_dump,
+                     forced_tokens, pick_stream(h, stream));
+}
+
+int mb_generate(void* hv, const float* wave1, const float* wave2, const int* input_ids, int B, int max_len,
+                float temperature, float top_p, int eos_id, int* tokens_out, int* steps_out_host, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    MB_TRY(check_ready(h, B));
+    cudaSetDevice(h->device);
+    return do_generate(h, wave1, wave2, input_ids, B, max_len, temperature, top_p, eos_id, tokens_out, 0,
+                       steps_out_host, pick_stream(h, stream));
+}
+
+int mb_generate_host(void* hv, const float* wave1_host, const float* wave2_host, const int* input_ids_host, int B,
+                     int max_len, float temperature, float top_p, int eos_id, int* tokens_out_host,
+                     int* steps_out_host, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    MB_TRY(check_ready(h, B));
+    cudaSetDevice(h->device);
+    cudaStream_t st = pick_stream(h, stream);
+    const size_t wbytes = (size_t)B * kClipSamples * sizeof(float);
+    float* w1 = h->wave_stage;
+    float* w2 = h->wave_stage + (size_t)B * kClipSamples;
+    MB_CK(h, cudaMemcpyAsync(w1, wave1_host, wbytes, cudaMemcpyHostToDevice, st));
+    MB_CK(h, cudaMemcpyAsync(w2, wave2_host, wbytes, cudaMemcpyHostToDevice, st));
+    MB_CK(h, cudaMemcpyAsync(h->d_ids, input_ids_host, (size_t)B * kTextLen * sizeof(int), cudaMemcpyHostToDevice, st));
+    return do_generate(h, w1, w2, h->d_ids, B, max_len, temperature, top_p, eos_id, tokens_out_host, 1,
+                       steps_out_host, st);
+}
+
+int mb_op_gemm(void* hv, const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int act,
+               void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    cudaSetDevice(h->device);
+    cudaStream_t st = pick_stream(h, stream);
+    if (K % 32 != 0) return fail(h, "mb_op_gemm: K must be a multiple of 32");
+    bf16 *ah = nullptr, *al = nullptr, *wh = nullptr, *wl = nullptr;
+    const size_t na = (size_t)M * K, nw = (size_t)N * K;
+    MB_CK(h, cudaMalloc((void**)&ah, na * 2));
+    MB_CK(h, cudaMalloc((void**)&al, na * 2));
+    MB_CK(h, cudaMalloc((void**)&wh, nw * 2));
+    MB_CK(h, cudaMalloc((void**)&wl, nw * 2));
+    int rc = 0;
+    do {
+        if (launch_split_planes(A, na, ah, al, st) != cudaSuccess || launch_split_planes(W, nw, wh, wl, st) != cudaSuccess) {
+            rc = fail(h, "split_planes launch failed");
+            break;
+        }
+        Plane wp{wh, wl};
+        GemmArgs g = gemm_base(h, ah, al, K, wp, K, M, N, K);
+        g.bias = bias; g.act = act; g.out_f32 = C; g.ldo = N;
+        rc = run_gemm(h, g, EPI_GENERIC, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (rc == 0 && e != cudaSuccess) { snprintf(h->err, sizeof(h->err), "mb_op_gemm: %s", cudaGetErrorString(e)); rc = 1; }
+    } while (0);
+    cudaFree(ah); cudaFree(al); cudaFree(wh); cudaFree(wl);
+    return rc;
+}
+
+}  // extern "C"

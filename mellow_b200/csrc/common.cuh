@@ -1,0 +1,112 @@
+// Shared device helpers for the mellow_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mb {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------- model constants
+// reference mellow/config/v0.yaml, mellow/model/config.py:4-9, mellow/model/htsat.py:599-606,
+// SmolLM2-135M
+constexpr int kClipSamples = 320000;
+constexpr int kNfft = 1024;
+constexpr int kHop = 320;
+constexpr int kBins = 513;
+constexpr int kMels = 64;
+constexpr int kFrames = 1001;
+constexpr int kStretch = 1024;
+constexpr int kImg = 256;
+constexpr int kGrid0 = 64;          // 64x64 patches
+constexpr int kEmbed = 96;
+constexpr int kWin = 8;
+constexpr int kWinTok = 64;
+constexpr int kClasses = 527;
+constexpr int kClassesPad = 544;    // K of the c2l GEMM padded to a multiple of 32
+constexpr int kEncOut = 768;
+constexpr int kProj = 576;
+constexpr int kAudioRows = 33;      // 1 latent + 32 unique frame rows per clip
+constexpr int kAudioSlots = 129;
+constexpr int kTextLen = 129;
+constexpr int kPrefix = 389;
+constexpr int kVocab = 49152;
+constexpr int kHidden = 576;
+constexpr int kLayers = 30;
+constexpr int kHeads = 9;
+constexpr int kKvHeads = 3;
+constexpr int kHeadDim = 64;
+constexpr int kQkvDim = 960;        // 576 q + 192 k + 192 v
+constexpr int kInter = 1536;
+constexpr int kMaxPos = 1024;       // rope table rows (389 + max_new <= 1024)
+
+// Precision policy (mb_create): how the tensor-core GEMM operands are represented.
+//   kPolicySplit: every fp32 operand x is carried as two bf16 planes hi=bf16(x), lo=bf16(x-hi) and each GEMM
+//                 issues hi*hi + hi*lo + lo*hi with fp32 accumulation (error ~2^-16 relative; greedy ids match the
+//                 fp32 reference); KV cache fp32.
+//   kPolicyFast:  single bf16 plane, one MMA pass, KV cache bf16 (logits within the stated bf16 tolerance).
+constexpr int kPolicySplit = 0;
+constexpr int kPolicyFast = 1;
+
+// ---------------------------------------------------------------- small device helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// hi/lo bf16 split of an fp32 value
+__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ void store_planes2(bf16* hi, bf16* lo, size_t idx, float a, float b) {
+    bf16 ah, al, bh, bl;
+    split_bf16(a, ah, al);
+    split_bf16(b, bh, bl);
+    __nv_bfloat162 h2, l2;
+    h2.x = ah; h2.y = bh;
+    l2.x = al; l2.y = bl;
+    *reinterpret_cast<__nv_bfloat162*>(hi + idx) = h2;
+    if (lo) *reinterpret_cast<__nv_bfloat162*>(lo + idx) = l2;
+}
+__device__ __forceinline__ void store_planes1(bf16* hi, bf16* lo, size_t idx, float a) {
+    bf16 ah, al;
+    split_bf16(a, ah, al);
+    hi[idx] = ah;
+    if (lo) lo[idx] = al;
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// KV-cache element types
+__device__ __forceinline__ float kv_load(const float* p) { return *p; }
+__device__ __forceinline__ float kv_load(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void kv_store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void kv_store2(bf16* p, float a, float b) {
+    __nv_bfloat162 v;
+    v.x = __float2bfloat16_rn(a);
+    v.y = __float2bfloat16_rn(b);
+    *reinterpret_cast<__nv_bfloat162*>(p) = v;
+}
+
+}  // namespace mb

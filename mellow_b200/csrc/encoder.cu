@@ -1,0 +1,250 @@
+// HTSAT (Swin) encoder glue kernels: row normalisation feeding the GEMM operand planes, shifted-window attention,
+// and the TSCAM tail gathers.  Reference: mellow/model/htsat.py:414-455 (block), :301-332 (window attention),
+// :478-499 (patch merging), :742-796 (tail), mellow/model/mellow.py:48-52 (projection).
+#include "kernels.cuh"
+
+namespace mb {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// One warp per row: LayerNorm / RMSNorm (fp32 statistics) -> bf16 hi/lo planes (GEMM A operand) and/or fp32.
+// NORM_LN_MERGE gathers the 2x2 neighbourhood of PatchMerging (htsat.py:489-493) on the fly.
+template <int C, int KIND>
+__global__ void __launch_bounds__(256) norm_kernel(const NormArgs a) {
+    constexpr int PER = C / 32;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= a.rows) return;
+    float v[PER];
+    if (KIND == NORM_LN_MERGE) {
+        constexpr int CI = C / 4;
+        const int r2 = a.res >> 1;
+        const int n = row / (r2 * r2);
+        const int rem = row - n * r2 * r2;
+        const int y2 = rem / r2, x2 = rem - y2 * r2;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int i = lane + 32 * j;
+            const int qd = i / CI, ci = i - qd * CI;
+            const int dy = qd & 1, dx = qd >> 1;          // x0:(0,0) x1:(1,0) x2:(0,1) x3:(1,1)
+            const size_t tok = (size_t)n * a.res * a.res + (size_t)(2 * y2 + dy) * a.res + (2 * x2 + dx);
+            v[j] = a.x[tok * CI + ci];
+        }
+    } else {
+        const float* src = a.x + ((size_t)row * a.row_stride + a.row_off) * C;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) v[j] = src[lane + 32 * j];
+    }
+    float mean = 0.f, rstd;
+    if (KIND == NORM_RMS) {
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) sq += v[j] * v[j];
+        rstd = rsqrtf(warp_sum(sq) * (1.0f / C) + 1e-5f);
+    } else {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) s += v[j];
+        mean = warp_sum(s) * (1.0f / C);
+        float sq = 0.f;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) { const float d = v[j] - mean; sq += d * d; }
+        rstd = rsqrtf(warp_sum(sq) * (1.0f / C) + 1e-5f);
+    }
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int i = lane + 32 * j;
+        float y;
+        if (KIND == NORM_RMS) y = a.w[i] * (v[j] * rstd);          // LlamaRMSNorm: weight * (x * rsqrt(ms + eps))
+        else y = (v[j] - mean) * rstd * a.w[i] + a.b[i];
+        const size_t o = (size_t)row * C + i;
+        if (a.out_f32) a.out_f32[o] = y;
+        if (a.out_hi) store_planes1(a.out_hi, a.out_lo, o, y);
+    }
+}
+
+template <int KIND>
+cudaError_t launch_norm_kind(const NormArgs& a, cudaStream_t st) {
+    const int grid = (a.rows + 7) / 8;
+    switch (a.C) {
+        case 96: norm_kernel<96, KIND><<<grid, 256, 0, st>>>(a); break;
+        case 192: norm_kernel<192, KIND><<<grid, 256, 0, st>>>(a); break;
+        case 384: norm_kernel<384, KIND><<<grid, 256, 0, st>>>(a); break;
+        case 576: norm_kernel<576, KIND><<<grid, 256, 0, st>>>(a); break;
+        case 768: norm_kernel<768, KIND><<<grid, 256, 0, st>>>(a); break;
+        case 1536: norm_kernel<1536, KIND><<<grid, 256, 0, st>>>(a); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// (Shifted-)window attention, one CTA per (clip, window, head), one thread per query token.  The cyclic shift and
+// the window partition / reverse of the reference (htsat.py:428-449) are pure index arithmetic here: local token
+// (iy,ix) of window (wy,wx) lives at source token ((wy*8+iy+shift)%R, (wx*8+ix+shift)%R), which is also where its
+// output row goes.  The q rows of the qkv weight are pre-scaled by head_dim^-0.5 at pack time (htsat.py:311).
+constexpr int kHd = 24;
+
+__device__ __forceinline__ int shift_band(int v, int R) { return v < R - kWin ? 0 : (v < R - kWin / 2 ? 1 : 2); }
+
+__global__ void __launch_bounds__(64) window_attention_kernel(const float* __restrict__ qkv,
+                                                              const float* __restrict__ relbias,
+                                                              bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
+                                                              int R, int C, int n_heads, int shift) {
+    __shared__ __align__(16) float sk[kWinTok][kHd];
+    __shared__ __align__(16) float sv[kWinTok][kHd];
+    __shared__ float sbias[kWinTok][kWinTok + 1];
+    __shared__ int slab[kWinTok];
+    const int i = threadIdx.x;
+    const int head = blockIdx.x, win = blockIdx.y, clip = blockIdx.z;
+    const int nwx = R / kWin;
+    const int wy = win / nwx, wx = win - wy * nwx;
+    const int y = wy * kWin + (i >> 3), x = wx * kWin + (i & 7);          // coordinates in the shifted frame
+    const int sy = (y + shift) % R, sx = (x + shift) % R;
+    const size_t tok = (size_t)clip * R * R + (size_t)sy * R + sx;
+    const float* row = qkv + tok * 3 * C + head * kHd;
+    float q[kHd];
+#pragma unroll
+    for (int d = 0; d < kHd; d += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(row + d);
+        q[d] = a.x; q[d + 1] = a.y; q[d + 2] = a.z; q[d + 3] = a.w;
+        *reinterpret_cast<float4*>(&sk[i][d]) = *reinterpret_cast<const float4*>(row + C + d);
+        *reinterpret_cast<float4*>(&sv[i][d]) = *reinterpret_cast<const float4*>(row + 2 * C + d);
+    }
+    slab[i] = shift > 0 ? shift_band(y, R) * 3 + shift_band(x, R) : 0;
+    const float* bsrc = relbias + (size_t)head * kWinTok * kWinTok;
+    for (int e = i; e < kWinTok * kWinTok; e += 64) sbias[e >> 6][e & 63] = bsrc[e];
+    __syncthreads();
+
+    float s[kWinTok];
+    const int mylab = slab[i];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < kWinTok; ++j) {
+        float acc = 0.f;
+#pragma unroll
+        for (int d = 0; d < kHd; d += 4) {
+            const float4 k4 = *reinterpret_cast<const float4*>(&sk[j][d]);
+            acc += q[d] * k4.x; acc += q[d + 1] * k4.y; acc += q[d + 2] * k4.z; acc += q[d + 3] * k4.w;
+        }
+        acc += sbias[i][j];
+        if (slab[j] != mylab) acc += -100.0f;                              // attn_mask, htsat.py:408
+        s[j] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < kWinTok; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
+    const float inv = 1.0f / sum;
+    float o[kHd];
+#pragma unroll
+    for (int d = 0; d < kHd; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kWinTok; ++j) {
+        const float p = s[j] * inv;
+#pragma unroll
+        for (int d = 0; d < kHd; d += 4) {
+            const float4 v4 = *reinterpret_cast<const float4*>(&sv[j][d]);
+            o[d] += p * v4.x; o[d + 1] += p * v4.y; o[d + 2] += p * v4.z; o[d + 3] += p * v4.w;
+        }
+    }
+    const size_t ob = tok * C + head * kHd;
+#pragma unroll
+    for (int d = 0; d < kHd; d += 2) store_planes2(out_hi, out_lo, ob + d, o[d], o[d + 1]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Tail (htsat.py:744-757,774): y = LN(final tokens) [N,64,768], token = (cq*2+fb)*8 + tt, time = cq*8+tt.
+//   latent[n,c]  = mean over the 64 tokens (order fb-major then time, like avgpool over flatten(x,2))
+//   col[(n,t), (dt*2+fb)*768 + c] = y[n, token(fb, t+dt-1), c]  (zero outside 0..31): im2col of the (2,3) TSCAM conv
+__global__ void __launch_bounds__(256) tail_gather_kernel(const float* __restrict__ y, float* __restrict__ latent,
+                                                          bf16* __restrict__ col_hi, bf16* __restrict__ col_lo) {
+    const int n = blockIdx.y, t = blockIdx.x;                               // t in 0..32 ; t == 32 -> latent
+    const float* yn = y + (size_t)n * 64 * kEncOut;
+    if (t == 32) {
+        for (int c = threadIdx.x; c < kEncOut; c += 256) {
+            float s = 0.f;
+            for (int fb = 0; fb < 2; ++fb)
+                for (int tm = 0; tm < 32; ++tm) s += yn[(size_t)(((tm >> 3) * 2 + fb) * 8 + (tm & 7)) * kEncOut + c];
+            latent[(size_t)n * kEncOut + c] = s * (1.0f / 64.0f);
+        }
+        return;
+    }
+    const size_t rowo = ((size_t)n * 32 + t) * (6 * kEncOut);
+    for (int e = threadIdx.x; e < 6 * kEncOut; e += 256) {
+        const int seg = e / kEncOut, c = e - seg * kEncOut;
+        const int dt = seg >> 1, fb = seg & 1;
+        const int tm = t + dt - 1;
+        float v = 0.f;
+        if (tm >= 0 && tm < 32) v = yn[(size_t)(((tm >> 3) * 2 + fb) * 8 + (tm & 7)) * kEncOut + c];
+        store_planes1(col_hi, col_lo, rowo + e, v);
+    }
+}
+
+// rows of the projection input: [latent ; 32 c2l frame rows] per clip (htsat.py:952-954 without the 32x repeat)
+__global__ void __launch_bounds__(256) assemble33_kernel(const float* __restrict__ latent,
+                                                         const float* __restrict__ frames, bf16* __restrict__ a_hi,
+                                                         bf16* __restrict__ a_lo) {
+    const int n = blockIdx.y, r = blockIdx.x;
+    const float* src = (r == 0) ? latent + (size_t)n * kEncOut : frames + ((size_t)n * 32 + (r - 1)) * kEncOut;
+    const size_t o = ((size_t)n * kAudioRows + r) * kEncOut;
+    for (int c = threadIdx.x; c < kEncOut; c += 256) store_planes1(a_hi, a_lo, o + c, src[c]);
+}
+
+__global__ void __launch_bounds__(256) gelu_planes_kernel(const float* __restrict__ x, size_t n, bf16* __restrict__ hi,
+                                                          bf16* __restrict__ lo) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) store_planes1(hi, lo, i, gelu_erf(x[i]));
+}
+
+__global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, size_t n, bf16* __restrict__ hi,
+                                                           bf16* __restrict__ lo) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) store_planes1(hi, lo, i, x[i]);
+}
+
+}  // namespace
+
+cudaError_t launch_norm(const NormArgs& a, int kind, cudaStream_t st) {
+    switch (kind) {
+        case NORM_LN: return launch_norm_kind<NORM_LN>(a, st);
+        case NORM_RMS: return launch_norm_kind<NORM_RMS>(a, st);
+        case NORM_LN_MERGE: return launch_norm_kind<NORM_LN_MERGE>(a, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_window_attention(const float* qkv, const float* relbias, bf16* out_hi, bf16* out_lo, int n_clips,
+                                    int res, int C, int n_heads, int shift, cudaStream_t st) {
+    if (C != n_heads * kHd || res % kWin != 0) return cudaErrorInvalidValue;
+    dim3 grid(n_heads, (res / kWin) * (res / kWin), n_clips);
+    window_attention_kernel<<<grid, 64, 0, st>>>(qkv, relbias, out_hi, out_lo, res, C, n_heads, shift);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_tail_gather(const float* y, int n_clips, float* latent, bf16* col_hi, bf16* col_lo,
+                               cudaStream_t st) {
+    dim3 grid(33, n_clips);
+    tail_gather_kernel<<<grid, 256, 0, st>>>(y, latent, col_hi, col_lo);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble33(const float* latent, const float* frames, int n_clips, bf16* a_hi, bf16* a_lo,
+                              cudaStream_t st) {
+    dim3 grid(kAudioRows, n_clips);
+    assemble33_kernel<<<grid, 256, 0, st>>>(latent, frames, a_hi, a_lo);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gelu_planes(const float* x, size_t n, bf16* hi, bf16* lo, cudaStream_t st) {
+    gelu_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, hi, lo);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_split_planes(const float* x, size_t n, bf16* hi, bf16* lo, cudaStream_t st) {
+    split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, hi, lo);
+    return cudaGetLastError();
+}
+
+}  // namespace mb

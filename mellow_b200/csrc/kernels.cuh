@@ -1,0 +1,68 @@
+// Launchers of the non-GEMM kernels (frontend.cu, encoder.cu, lm.cu).
+#pragma once
+#include "common.cuh"
+
+namespace mb {
+
+// ---- frontend.cu
+struct FrontendW {
+    const float* window;    // [1024] analysis window (row k=0 of the checkpoint's conv_real basis)
+    const float* twiddle;   // [512][2] exp(-2 pi i k / 1024)
+    const float* melW;      // [513][64]
+    const int* mel_lo;      // [64] first non-zero bin of each mel filter
+    const int* mel_hi;      // [64] one past the last non-zero bin
+    const float* bn_scale;  // [64] gamma / sqrt(var + eps)
+    const float* bn_shift;  // [64] beta - mean * scale
+};
+cudaError_t launch_logmel(const float* wave, int n_clips, const FrontendW& w, float* logmel_out, float* bn_out,
+                          cudaStream_t st);
+struct PatchW { const float* w; const float* b; const float* ln_w; const float* ln_b; };
+cudaError_t launch_patch_embed(const float* bn, int n_clips, const PatchW& w, float* x_out, cudaStream_t st);
+
+// ---- encoder.cu
+enum { NORM_LN = 0, NORM_RMS = 1, NORM_LN_MERGE = 2 };
+struct NormArgs {
+    const float* x; const float* w; const float* b;
+    bf16* out_hi; bf16* out_lo; float* out_f32;     // any subset
+    int rows, C;
+    int row_stride, row_off;                         // source row = r * row_stride + row_off (LN / RMS)
+    int res;                                         // NORM_LN_MERGE: input grid side (tokens are res x res, C/4 wide)
+};
+cudaError_t launch_norm(const NormArgs& a, int kind, cudaStream_t st);
+cudaError_t launch_window_attention(const float* qkv, const float* relbias, bf16* out_hi, bf16* out_lo, int n_clips,
+                                    int res, int C, int n_heads, int shift, cudaStream_t st);
+cudaError_t launch_tail_gather(const float* y, int n_clips, float* latent, bf16* col_hi, bf16* col_lo, cudaStream_t st);
+cudaError_t launch_assemble33(const float* latent, const float* frames, int n_clips, bf16* a_hi, bf16* a_lo,
+                              cudaStream_t st);
+cudaError_t launch_gelu_planes(const float* x, size_t n, bf16* hi, bf16* lo, cudaStream_t st);
+cudaError_t launch_split_planes(const float* x, size_t n, bf16* hi, bf16* lo, cudaStream_t st);
+
+// ---- lm.cu
+cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embed, int B, float* prefix, cudaStream_t st);
+cudaError_t launch_prefill_attention(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S, int t_max,
+                                     bf16* out_hi, bf16* out_lo, cudaStream_t st);
+struct DecodeAttnArgs {
+    const float* q;                 // [B,576]
+    const void* kc; const void* vc; // layer caches [B][3][t_max][64]
+    int kv_bf16, B, t_max, nsplit;
+    int ctx_base; const int* d_step;   // ctx = ctx_base + *d_step  (keys 0..ctx-1)
+    float* part_acc; float* part_ml;   // [B][9][nsplit][64], [B][9][nsplit][2]
+    bf16* out_hi; bf16* out_lo;        // [B,576]
+};
+cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st);
+struct SampleArgs {
+    const float* logits;            // [B,V]
+    const float* embed;             // [V,576] fp32 table (next-token embedding gather)
+    int B, max_len, eos_id;
+    float temperature, top_p;
+    const int* d_step;              // current step (column of tokens_out)
+    int* tokens_out;                // [B,max_len]
+    const int* forced;              // optional teacher-forced tokens [B,max_len]: fed back instead of the argmax
+    float* x_next;                  // [B,576] embedding of the token fed to the next step
+    int* done;                      // [B] row has emitted eos
+    float* logits_dump;             // optional [max_len][B][V] temperature-scaled logits
+};
+cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st);
+cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st);
+
+}  // namespace mb

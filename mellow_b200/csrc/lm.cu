@@ -1,0 +1,379 @@
+// SmolLM2 decoder-side kernels that are not GEMMs: prefix assembly (reference mellow/model/decoder.py:14-55),
+// causal prefill attention and split-KV decode attention (transformers modeling_llama.py:276-285; the reference has
+// no KV cache, wrapper.py:216-217), and the sampling step (wrapper.py:218-249).
+#include "kernels.cuh"
+
+namespace mb {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// prefix[b] = [lat1, 128 pooled a1, sep, lat2, 128 pooled a2, sep, 129 text embeddings]   (B,389,576)
+// The 128 pooled slots are avg_pool(kernel 8) over 32 copies of each of the 32 frame rows, i.e. each unique row 4
+// times; the 8-term fp32 running sum and the divide are kept so the value is bit-identical to the reference's pool.
+__global__ void __launch_bounds__(144) prefix_kernel(const float* __restrict__ rows33, const int* __restrict__ ids,
+                                                     const float* __restrict__ embed, int B, float* __restrict__ prefix) {
+    const int p = blockIdx.x, b = blockIdx.y;
+    const int c4 = threadIdx.x;                                   // 144 float4 = 576 floats
+    float4 v;
+    if (p < 2 * (kAudioSlots + 1)) {
+        const int which = p / (kAudioSlots + 1);                  // 0: audio1, 1: audio2
+        const int slot = p - which * (kAudioSlots + 1);
+        if (slot == kAudioSlots) {
+            v = reinterpret_cast<const float4*>(embed)[c4];       // separator = embed_tokens[0], decoder.py:49-50
+        } else {
+            const int row = slot == 0 ? 0 : 1 + (slot - 1) / 4;
+            const float4 r = reinterpret_cast<const float4*>(rows33 + (((size_t)which * B + b) * kAudioRows + row) * kProj)[c4];
+            if (slot == 0) {
+                v = r;
+            } else {
+                float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { s.x += r.x; s.y += r.y; s.z += r.z; s.w += r.w; }
+                v = make_float4(s.x / 8.0f, s.y / 8.0f, s.z / 8.0f, s.w / 8.0f);
+            }
+        }
+    } else {
+        const int id = ids[b * kTextLen + (p - 2 * (kAudioSlots + 1))];
+        v = reinterpret_cast<const float4*>(embed + (size_t)id * kHidden)[c4];
+    }
+    reinterpret_cast<float4*>(prefix + ((size_t)b * kPrefix + p) * kHidden)[c4] = v;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Causal prefill attention, fp32 on CUDA cores: one CTA = 64 query rows of one (batch, head); one thread per query.
+// K/V tiles of 32 keys are staged in shared memory (converted to fp32) and read as warp-wide broadcasts.
+template <typename T>
+__global__ void __launch_bounds__(64) prefill_attention_kernel(const float* __restrict__ q, const T* __restrict__ kc,
+                                                               const T* __restrict__ vc, int S, int t_max,
+                                                               bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+    constexpr int TK = 32;
+    __shared__ __align__(16) float sk[TK][kHeadDim];
+    __shared__ __align__(16) float sv[TK][kHeadDim];
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x;
+    const int r = qt * 64 + tid;
+    const bool active = r < S;
+    const int kvh = h / (kHeads / kKvHeads);
+    const T* kb = kc + ((size_t)b * kKvHeads + kvh) * t_max * kHeadDim;
+    const T* vb = vc + ((size_t)b * kKvHeads + kvh) * t_max * kHeadDim;
+    float qr[kHeadDim], acc[kHeadDim];
+    const float* qp = q + ((size_t)b * S + (active ? r : 0)) * kHidden + h * kHeadDim;
+#pragma unroll
+    for (int d = 0; d < kHeadDim; d += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(qp + d);
+        qr[d] = a.x; qr[d + 1] = a.y; qr[d + 2] = a.z; qr[d + 3] = a.w;
+        acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
+    }
+    float m_run = -INFINITY, l_run = 0.f;
+    const int kend = min(S, qt * 64 + 64);
+    for (int k0 = 0; k0 < kend; k0 += TK) {
+        __syncthreads();
+        for (int e = tid; e < TK * kHeadDim; e += 64) {
+            const int j = e >> 6, d = e & 63;
+            const int key = k0 + j;
+            sk[j][d] = key < S ? kv_load(kb + (size_t)key * kHeadDim + d) : 0.f;
+            sv[j][d] = key < S ? kv_load(vb + (size_t)key * kHeadDim + d) : 0.f;
+        }
+        __syncthreads();
+        float s[TK];
+        float mt = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < TK; ++j) {
+            float a = 0.f;
+#pragma unroll
+            for (int d = 0; d < kHeadDim; d += 4) {
+                const float4 k4 = *reinterpret_cast<const float4*>(&sk[j][d]);
+                a += qr[d] * k4.x; a += qr[d + 1] * k4.y; a += qr[d + 2] * k4.z; a += qr[d + 3] * k4.w;
+            }
+            a *= 0.125f;                                            // head_dim^-0.5
+            if (k0 + j > r) a = -INFINITY;                          // causal mask
+            s[j] = a;
+            mt = fmaxf(mt, a);
+        }
+        if (mt == -INFINITY) continue;                              // whole tile is in this row's future (uniform bar count kept above)
+        const float m_new = fmaxf(m_run, mt);
+        const float alpha = expf(m_run - m_new);
+        float lsum = 0.f;
+#pragma unroll
+        for (int j = 0; j < TK; ++j) { s[j] = expf(s[j] - m_new); lsum += s[j]; }
+        l_run = l_run * alpha + lsum;
+        m_run = m_new;
+#pragma unroll
+        for (int d = 0; d < kHeadDim; ++d) acc[d] *= alpha;
+#pragma unroll
+        for (int j = 0; j < TK; ++j) {
+            const float p = s[j];
+#pragma unroll
+            for (int d = 0; d < kHeadDim; d += 4) {
+                const float4 v4 = *reinterpret_cast<const float4*>(&sv[j][d]);
+                acc[d] += p * v4.x; acc[d + 1] += p * v4.y; acc[d + 2] += p * v4.z; acc[d + 3] += p * v4.w;
+            }
+        }
+    }
+    if (!active) return;
+    const float inv = 1.0f / l_run;
+    const size_t ob = ((size_t)b * S + r) * kHidden + h * kHeadDim;
+#pragma unroll
+    for (int d = 0; d < kHeadDim; d += 2) store_planes2(out_hi, out_lo, ob + d, acc[d] * inv, acc[d + 1] * inv);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Decode attention: one new query per row, ctx keys.  CTA = (split, kv head, row): the 3 query heads that share the
+// kv head (GQA, modeling_llama.py:187-196) are processed together so K/V are read once.  128 threads, 64-key tiles,
+// cp.async double buffering; partial (m, l, acc) per split are merged by decode_combine_kernel.
+template <typename T>
+struct DecodeSmem {
+    static constexpr int KLD = kHeadDim + 16 / sizeof(T);         // +16 B: conflict-free 16 B row reads
+    T k[2][64][KLD];
+    T v[2][64][kHeadDim];
+    float q[3][kHeadDim];
+    float sc[3][64];
+    float alpha[3], m[3], l[3];
+    float red[3][64];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DecodeSmem<T>& sm = *reinterpret_cast<DecodeSmem<T>*>(smem_raw);
+    constexpr int E = 16 / sizeof(T);             // elements per 16 B chunk
+    constexpr int NCH = kHeadDim / E;             // chunks per row
+    const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ctx = a.ctx_base + (a.d_step ? *a.d_step : 0);
+    const int ntiles = (ctx + 63) >> 6;
+    const int tps = (ntiles + a.nsplit - 1) / a.nsplit;
+    const int t_begin = split * tps, t_end = min(ntiles, t_begin + tps);
+    const T* kb = reinterpret_cast<const T*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * kHeadDim;
+    const T* vb = reinterpret_cast<const T*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * kHeadDim;
+
+    for (int e = tid; e < 3 * kHeadDim; e += 128)
+        sm.q[e >> 6][e & 63] = a.q[(size_t)b * kHidden + (kvh * 3 + (e >> 6)) * kHeadDim + (e & 63)];
+    if (tid < 3) { sm.m[tid] = -INFINITY; sm.l[tid] = 0.f; }
+
+    auto load_tile = [&](int buf, int tile) {
+        const int key0 = tile << 6;
+        for (int c = tid; c < 64 * NCH; c += 128) {
+            const int j = c / NCH, ch = c - j * NCH;
+            const int key = key0 + j;
+            const bool ok = key < ctx;
+            const size_t off = (size_t)(ok ? key : 0) * kHeadDim + ch * E;
+            cp_async16(&sm.k[buf][j][ch * E], kb + off, ok);
+            cp_async16(&sm.v[buf][j][ch * E], vb + off, ok);
+        }
+    };
+
+    float acc[3] = {0.f, 0.f, 0.f};
+    const int d_own = tid & 63, khalf = tid >> 6;
+    if (t_begin < t_end) load_tile(0, t_begin);
+    cp_async_commit();
+    for (int t = t_begin; t < t_end; ++t) {
+        const int buf = (t - t_begin) & 1;
+        if (t + 1 < t_end) load_tile(buf ^ 1, t + 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        // scores: thread = (key j, half); each half takes every other 16 B chunk of the key row
+        {
+            const int j = tid >> 1, half = tid & 1;
+            float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < NCH / 2; ++i) {
+                const int ch = 2 * i + half;
+                const T* kp = &sm.k[buf][j][ch * E];
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const float kvv = kv_load(kp + e);
+                    const int d = ch * E + e;
+                    p0 += sm.q[0][d] * kvv; p1 += sm.q[1][d] * kvv; p2 += sm.q[2][d] * kvv;
+                }
+            }
+            p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
+            p2 += __shfl_xor_sync(0xffffffffu, p2, 1);
+            if (half == 0) {
+                const bool ok = ((t << 6) + j) < ctx;
+                sm.sc[0][j] = ok ? p0 * 0.125f : -INFINITY;
+                sm.sc[1][j] = ok ? p1 * 0.125f : -INFINITY;
+                sm.sc[2][j] = ok ? p2 * 0.125f : -INFINITY;
+            }
+        }
+        __syncthreads();
+        if (warp < 3) {                                              // online softmax bookkeeping, one warp per head
+            const float s0 = sm.sc[warp][lane], s1 = sm.sc[warp][lane + 32];
+            const float mt = warp_max(fmaxf(s0, s1));                // finite: every tile in range has >= 1 valid key
+            const float m_old = sm.m[warp];
+            const float m_new = fmaxf(m_old, mt);
+            const float e0 = expf(s0 - m_new), e1 = expf(s1 - m_new);
+            const float ls = warp_sum(e0 + e1);
+            sm.sc[warp][lane] = e0;
+            sm.sc[warp][lane + 32] = e1;
+            __syncwarp();
+            if (lane == 0) {
+                const float al = expf(m_old - m_new);
+                sm.alpha[warp] = al;
+                sm.l[warp] = sm.l[warp] * al + ls;
+                sm.m[warp] = m_new;
+            }
+        }
+        __syncthreads();
+        {
+            const float a0 = sm.alpha[0], a1 = sm.alpha[1], a2 = sm.alpha[2];
+            float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+#pragma unroll 8
+            for (int jj = 0; jj < 32; ++jj) {
+                const int j = khalf * 32 + jj;
+                const float vv = kv_load(&sm.v[buf][j][d_own]);
+                x0 += sm.sc[0][j] * vv; x1 += sm.sc[1][j] * vv; x2 += sm.sc[2][j] * vv;
+            }
+            acc[0] = acc[0] * a0 + x0; acc[1] = acc[1] * a1 + x1; acc[2] = acc[2] * a2 + x2;
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    if (khalf == 1) { sm.red[0][d_own] = acc[0]; sm.red[1][d_own] = acc[1]; sm.red[2][d_own] = acc[2]; }
+    __syncthreads();
+    if (khalf == 0) {
+#pragma unroll
+        for (int hh = 0; hh < 3; ++hh) {
+            const size_t o = (((size_t)b * kHeads + kvh * 3 + hh) * a.nsplit + split);
+            a.part_acc[o * kHeadDim + d_own] = acc[hh] + sm.red[hh][d_own];
+            if (d_own == 0) { a.part_ml[o * 2] = sm.m[hh]; a.part_ml[o * 2 + 1] = sm.l[hh]; }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64) decode_combine_kernel(const DecodeAttnArgs a) {
+    const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
+    const size_t base = ((size_t)b * kHeads + h) * a.nsplit;
+    float m = -INFINITY;
+    for (int s = 0; s < a.nsplit; ++s) m = fmaxf(m, a.part_ml[(base + s) * 2]);
+    float num = 0.f, den = 0.f;
+    for (int s = 0; s < a.nsplit; ++s) {
+        const float ms = a.part_ml[(base + s) * 2];
+        if (ms == -INFINITY) continue;                             // empty split
+        const float w = expf(ms - m);
+        num += w * a.part_acc[(base + s) * kHeadDim + d];
+        den += w * a.part_ml[(base + s) * 2 + 1];
+    }
+    store_planes1(a.out_hi, a.out_lo, (size_t)b * kHidden + h * kHeadDim + d, num / den);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sampling step of the reference (wrapper.py:218-249): logits / temperature, top-p filter, ARGMAX, next embedding,
+// stop bookkeeping.  The reference's filter never removes the top-1 entry (the shifted mask clears index 0,
+// wrapper.py:224-226) and the decision is an argmax over what is kept, so the kept-set argmax equals the global
+// argmax for every top_p and every temperature > 0; the kernel therefore scans once for (max, first index).
+// One CTA per row.
+__global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
+    __shared__ float smax[32];
+    __shared__ int sidx[32];
+    __shared__ int stoken;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int step = *a.d_step;
+    const float* lg = a.logits + (size_t)b * kVocab;
+    const float tdiv = a.temperature > 0.f ? a.temperature : 1.0f;
+    float* dump = a.logits_dump ? a.logits_dump + ((size_t)step * a.B + b) * kVocab : nullptr;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < kVocab; i += 1024) {
+        const float v = lg[i] / tdiv;
+        if (dump) dump[i] = v;
+        if (v > best) { best = v; bi = i; }                        // strided scan keeps the smallest index per thread
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (lane == 0) { smax[warp] = best; sidx[warp] = bi; }
+    __syncthreads();
+    if (warp == 0) {
+        best = smax[lane]; bi = sidx[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) {
+            a.tokens_out[(size_t)b * a.max_len + step] = bi;
+            if (bi == a.eos_id) a.done[b] = 1;
+            stoken = a.forced ? a.forced[(size_t)b * a.max_len + step] : bi;
+        }
+    }
+    __syncthreads();
+    const int tok = stoken;
+    if (tid < kHidden / 4)
+        reinterpret_cast<float4*>(a.x_next + (size_t)b * kHidden)[tid] =
+            reinterpret_cast<const float4*>(a.embed + (size_t)tok * kHidden)[tid];
+}
+
+// step += 1; records the first step count at which every row has emitted eos (wrapper.py:247-249)
+__global__ void step_advance_kernel(int* d_step, const int* done, int B, int* d_stop_step) {
+    __shared__ int all;
+    if (threadIdx.x == 0) all = 1;
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x)
+        if (!done[b]) all = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int s = *d_step + 1;
+        *d_step = s;
+        if (all && *d_stop_step < 0) *d_stop_step = s;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embed, int B, float* prefix,
+                          cudaStream_t st) {
+    dim3 grid(kPrefix, B);
+    prefix_kernel<<<grid, 144, 0, st>>>(rows33, ids, embed, B, prefix);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_prefill_attention(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S,
+                                     int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st) {
+    dim3 grid((S + 63) / 64, kHeads, B);
+    if (kv_bf16)
+        prefill_attention_kernel<bf16><<<grid, 64, 0, st>>>(q, (const bf16*)kc, (const bf16*)vc, S, t_max, out_hi, out_lo);
+    else
+        prefill_attention_kernel<float><<<grid, 64, 0, st>>>(q, (const float*)kc, (const float*)vc, S, t_max, out_hi, out_lo);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
+    dim3 grid(a.nsplit, kKvHeads, a.B);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(decode_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)sizeof(DecodeSmem<float>));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(decode_attention_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(DecodeSmem<bf16>));
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (a.kv_bf16) decode_attention_kernel<bf16><<<grid, 128, sizeof(DecodeSmem<bf16>), st>>>(a);
+    else decode_attention_kernel<float><<<grid, 128, sizeof(DecodeSmem<float>), st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dim3 g2(kHeads, a.B);
+    decode_combine_kernel<<<g2, 64, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st) {
+    sample_kernel<<<a.B, 1024, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st) {
+    step_advance_kernel<<<1, 128, 0, st>>>(d_step, done, B, d_stop_step);
+    return cudaGetLastError();
+}
+
+}  // namespace mb

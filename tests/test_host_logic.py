@@ -1,0 +1,144 @@
+"""CPU: host-side logic of the product package and the C-ABI surface (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from mellow_b200 import dsp, native, schema as S, synth, weights
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return native.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "mellow_b200.h")).read()
+    declared = set(re.findall(r"\b(mb_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    bound = {name for name, _, _ in native.SYMBOLS}
+    assert declared == bound, f"header/ctypes mismatch: {declared ^ bound}"
+    for name in declared:
+        assert hasattr(lib, name)
+    assert lib.mb_version() >= 1
+
+
+def test_arena_layout_is_consistent(lib):
+    entries = native.weight_entries(lib)
+    assert len({n for n, _, _ in entries}) == len(entries)
+    end = 0
+    for name, off, nbytes in entries:
+        assert off % 256 == 0 and off >= end and nbytes > 0, name
+        end = off + nbytes
+    assert end <= lib.mb_weights_size()
+
+
+def test_pack_roundtrip(sd, lib):
+    entries = native.weight_entries(lib)
+    arena = weights.pack(sd, entries, lib.mb_weights_size())
+    table = {n: (o, b) for n, o, b in entries}
+
+    def f32(name):
+        o, b = table[name]
+        return arena[o:o + b].view(torch.float32)
+
+    def planes(name):
+        o, b = table[name + ".hi"]
+        hi = arena[o:o + b].view(torch.bfloat16).float()
+        o, b = table[name + ".lo"]
+        return hi + arena[o:o + b].view(torch.bfloat16).float()
+
+    # hi + lo reproduces fp32 weights to ~2^-16 relative
+    w = sd["caption_decoder.lm.model.layers.3.self_attn.o_proj.weight"]
+    assert (planes("lm.l3.o_w").view_as(w) - w).abs().max() <= w.abs().max() * 2.0 ** -15
+    # q rows of the Swin qkv are pre-scaled by head_dim^-0.5 = 24^-0.5
+    qkv = sd["audio_encoder.base.htsat.layers.0.blocks.0.attn.qkv.weight"].clone()
+    qkv[:96] *= 24 ** -0.5
+    assert (planes("s0.b0.qkv_w").view_as(qkv) - qkv).abs().max() < 1e-5
+    # rotate-half partners are adjacent after the q/k row permutation; v rows untouched
+    q = sd["caption_decoder.lm.model.layers.0.self_attn.q_proj.weight"]
+    packed = planes("lm.l0.qkv_w").view(960, 576)
+    assert torch.allclose(packed[0], q[0], atol=1e-5) and torch.allclose(packed[1], q[32], atol=1e-5)
+    assert torch.allclose(packed[64 + 3], q[64 + 33], atol=1e-5)
+    v = sd["caption_decoder.lm.model.layers.0.self_attn.v_proj.weight"]
+    assert torch.allclose(packed[768:], v, atol=1e-5)
+    gate = sd["caption_decoder.lm.model.layers.0.mlp.gate_proj.weight"]
+    up = sd["caption_decoder.lm.model.layers.0.mlp.up_proj.weight"]
+    gu = planes("lm.l0.gu_w").view(3072, 576)
+    assert torch.allclose(gu[10], gate[5], atol=1e-5) and torch.allclose(gu[11], up[5], atol=1e-5)
+    # folded BatchNorm
+    p = "audio_encoder.base.htsat.bn0."
+    x = torch.linspace(-60, 10, 64)
+    want = (x - sd[p + "running_mean"]) / torch.sqrt(sd[p + "running_var"] + 1e-5) * sd[p + "weight"] + sd[p + "bias"]
+    assert torch.allclose(x * f32("fe.bn_scale") + f32("fe.bn_shift"), want, atol=1e-5)
+    # mel filter extents cover every non-zero weight
+    melW = sd["audio_encoder.base.htsat.logmel_extractor.melW"]
+    o, b = table["fe.mel_lo"]; lo = arena[o:o + b].view(torch.int32)
+    o, b = table["fe.mel_hi"]; hi = arena[o:o + b].view(torch.int32)
+    for m in range(64):
+        nz = torch.nonzero(melW[:, m]).flatten()
+        assert lo[m] <= nz.min() and hi[m] > nz.max()
+    # rope table equals the oracle's
+    from oracle import restated as R
+    cos, sin = R.rope_tables(1024)
+    assert torch.equal(f32("lm.rope_cos").view(1024, 32), cos[:, :32]) and torch.equal(f32("lm.rope_sin").view(1024, 32), sin[:, :32])
+
+
+def test_packer_rejects_bad_checkpoints(sd, lib):
+    entries = native.weight_entries(lib)
+    bad = dict(sd)
+    k = "audio_encoder.base.htsat.spectrogram_extractor.stft.conv_imag.weight"
+    bad[k] = sd[k] * 1.01
+    with pytest.raises(RuntimeError, match="windowed DFT"):
+        weights.pack(bad, entries, lib.mb_weights_size())
+    bad = dict(sd)
+    del bad["audio_encoder.base.c2l.bias"]
+    with pytest.raises(RuntimeError, match="schema"):
+        weights.pack(bad, entries, lib.mb_weights_size())
+    wrapped = {"module." + k: v for k, v in sd.items()}
+    assert set(weights.strip_module_prefix(wrapped)) == set(sd)          # wrapper.py:77-82
+
+
+def test_synthetic_checkpoint_is_reproducible(sd):
+    again = synth.synthetic_state_dict()
+    for k in ("audio_encoder.projection.linear1.weight", "caption_decoder.lm.model.layers.29.mlp.down_proj.weight"):
+        assert torch.equal(sd[k], again[k])
+    import hashlib
+    h = hashlib.sha256(sd["caption_decoder.lm.model.norm.weight"].numpy().tobytes()).hexdigest()
+    assert h == hashlib.sha256(again["caption_decoder.lm.model.norm.weight"].numpy().tobytes()).hexdigest()
+    assert S.count_parameters() == S.TOTAL_PARAMS
+    assert S.PREFIX_LEN == 3 * 129 + 2 and S.N_FRAMES == 1001
+
+
+def test_shift_mask_closed_form():
+    m = dsp.shifted_window_mask(16)
+    assert m.shape == (4, 64, 64) and set(np.unique(m)) == {-100.0, 0.0}
+    assert (m[0] == 0).all()                                           # top-left window is not cut by the shift
+
+
+def test_tokenizer_stand_in_and_wrapper_errors():
+    from mellow_b200.tokenizer import ByteStandInTokenizer, tokenize_prompts
+    tok = ByteStandInTokenizer()
+    ids = tokenize_prompts(tok, ["hi!", "what?"], 129)
+    assert ids.shape == (2, 129) and ids.dtype == torch.int64
+    assert ids[0, 3:].eq(17).all() and tok.encode("<|endoftext|>")[0] == 0
+    assert tok.decode([256 + ord("o"), 256 + ord("k"), 0, 300]).split("<|endoftext|>")[0] == "ok"
+    from mellow_b200 import MellowWrapper, MellowNativeError
+    with pytest.raises(ValueError):
+        MellowWrapper(config="v0", model="v9", device=0)
+    if not torch.cuda.is_available():
+        with pytest.raises(MellowNativeError):
+            MellowWrapper(config="v0", model="v0", device="cpu", use_cuda=False, checkpoint="synthetic")
+
+
+def test_create_fails_loudly_without_gpu(lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = lib.mb_create(0, 1, 8, 0)
+    assert not h
+    assert b"no CUDA device" in lib.mb_last_error(None)

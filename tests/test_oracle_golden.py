@@ -1,0 +1,81 @@
+"""CPU: the standalone oracle restatement (oracle/restated.py) against the golden vectors produced by the
+reference's own model classes (tests/golden/make_golden.py)."""
+import numpy as np
+import torch
+
+from oracle import restated as R
+
+TOK_ROWS = {"patch": [0, 2047, 4095], "stage0": [0, 511, 1023], "stage1": [0, 100, 255], "stage2": [0, 31, 63],
+            "stage3": [0, 31, 63]}
+FRAME_ROWS = [0, 1, 2, 500, 998, 999, 1000]
+PREFIX_ROWS = [0, 1, 4, 5, 128, 129, 130, 131, 258, 259, 260, 323, 324, 388]
+
+
+def _close(a, b, atol):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    err = np.abs(a - b).max()
+    assert err <= atol, f"max abs err {err} > {atol}"
+
+
+def test_encoder_stages_match_reference(sd, golden, inputs):
+    taps = {}
+    with torch.no_grad():
+        rows = R.encode_clips(sd, inputs["wave1"], taps)
+    _close(taps["logmel"][:, FRAME_ROWS], golden["logmel_rows"], 1e-4)      # dB
+    _close(taps["bn"][:, FRAME_ROWS], golden["bn_rows"], 1e-4)
+    for name, idx in TOK_ROWS.items():
+        _close(taps[name][:, idx], golden[name], 5e-5)
+    _close(taps["latent"], golden["latent"], 2e-5)
+    _close(taps["oframe"], golden["frames"], 2e-5)
+    _close(rows, golden["rows33"], 5e-5)
+
+
+def test_prefix_and_greedy_tokens_match_reference(sd, golden, inputs):
+    with torch.no_grad():
+        ra, rb = R.encode_clips(sd, inputs["wave1"]), R.encode_clips(sd, inputs["wave2"])
+        prefix = R.build_prefix(sd, ra, rb, inputs["ids"])
+        assert prefix.shape == (2, 389, 576)
+        _close(prefix[:, PREFIX_ROWS], golden["prefix_rows"], 5e-5)
+        steps = 4                                                       # full 12-step run is exercised on the GPU box
+        toks, logits = R.generate_ids(sd, prefix, steps, top_p=0.8, temperature=1.0, dump_logits=True)
+    assert toks.tolist() == golden["tokens"][:, :steps].tolist()
+    logits = torch.stack(logits, 0)
+    probe = torch.from_numpy(golden["probe_ids"])
+    _close(logits[:, :, probe], golden["probe_logits"][:steps], 2e-4)
+    top = logits.topk(8, dim=-1)
+    assert top.indices[..., 0].tolist() == golden["top8_ids"][:steps, :, 0].tolist()
+    _close(top.values, golden["top8_vals"][:steps], 2e-4)
+
+
+def test_pooled_rows_are_exact_copies(sd):
+    """decoder.py:14-18 on 32x-repeated rows: the 128 pooled slots are 32 unique rows x 4 copies."""
+    g = torch.Generator().manual_seed(3)
+    rows = torch.randn(2, 33, 576, generator=g)
+    slots = R.expand_audio_rows(rows)
+    assert slots.shape == (2, 129, 576)
+    assert torch.equal(slots[:, 0], rows[:, 0])
+    body = slots[:, 1:].reshape(2, 32, 4, 576)
+    assert torch.equal(body[:, :, 0], body[:, :, 3])
+    assert (body[:, :, 0] - rows[:, 1:]).abs().max() < 1e-6
+
+
+def test_top_p_filter_never_changes_the_argmax():
+    """wrapper.py:219-232: the shifted mask keeps the top-1 entry, so the result is the plain argmax."""
+    g = torch.Generator().manual_seed(11)
+    for top_p in (0.0, 0.3, 0.8, 1.0):
+        for temperature in (0.5, 1.0, 2.0):
+            logits = torch.randn(16, 4096, generator=g) * 3.0
+            nxt, _ = R.top_p_argmax(logits.clone(), top_p, temperature)
+            assert torch.equal(nxt, torch.argmax(logits, -1))
+
+
+def test_tile_and_crop_rule():
+    import random
+    short = torch.arange(7, dtype=torch.float32)
+    out = R.tile_or_crop(short, 16, random.Random(0))
+    assert out.tolist() == [0, 1, 2, 3, 4, 5, 6, 0, 1, 2, 3, 4, 5, 6, 0, 1]
+    long_ = torch.arange(40, dtype=torch.float32)
+    rng = random.Random(5)
+    start = random.Random(5).randrange(40 - 16)
+    assert R.tile_or_crop(long_, 16, rng).tolist() == list(range(start, start + 16))
+    assert R.trim_at_stop([5, 6, 0, 9, 0]) == [5, 6]

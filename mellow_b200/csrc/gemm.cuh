@@ -44,11 +44,13 @@ __device__ __forceinline__ void epilogue_pair(const GemmArgs& g, int m, int n, f
         }
         if (g.out_f32) {
             float* o = g.out_f32 + (size_t)m * g.ldo + n;
-            if (has1) *reinterpret_cast<float2*>(o) = make_float2(v0, v1); else o[0] = v0;
+            if (has1 && !(g.ldo & 1)) *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
+            else { o[0] = v0; if (has1) o[1] = v1; }
         }
         if (g.out_hi) {
             size_t idx = (size_t)m * g.ldp + n;
-            if (has1) store_planes2(g.out_hi, g.out_lo, idx, v0, v1); else store_planes1(g.out_hi, g.out_lo, idx, v0);
+            if (has1 && !(g.ldp & 1)) store_planes2(g.out_hi, g.out_lo, idx, v0, v1);
+            else { store_planes1(g.out_hi, g.out_lo, idx, v0); if (has1) store_planes1(g.out_hi, g.out_lo, idx + 1, v1); }
         }
     } else if (EPI == EPI_SWIGLU) {
         // weight rows are interleaved (gate_j, up_j): down_proj(silu(gate) * up), modeling_llama.py:182-184

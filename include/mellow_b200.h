@@ -80,6 +80,11 @@ int mb_generate_host(void* h, const float* wave1_host, const float* wave2_host, 
 int mb_op_gemm(void* h, const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int act,
                void* stream);
 
+/* bench hook: launches the decode-attention kernel (+ its split combine) `iters` times over the handle's KV cache at
+ * context length `ctx`, cycling through the 30 layer caches so no launch re-reads L2-resident data; the caller
+ * brackets the call with CUDA events on `stream`. */
+int mb_bench_decode_attention(void* h, int B, int ctx, int iters, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

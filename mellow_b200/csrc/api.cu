@@ -747,6 +747,30 @@ int mb_generate_host(void* hv, const float* wave1_host, const float* wave2_host,
                        steps_out_host, st);
 }
 
+int mb_bench_decode_attention(void* hv, int B, int ctx, int iters, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    MB_TRY(check_ready(h, B));
+    if (ctx < 1 || ctx > h->t_max) return fail(h, "ctx out of range");
+    cudaSetDevice(h->device);
+    cudaStream_t st = pick_stream(h, stream);
+    const int step = ctx - kPrefix;
+    MB_CK(h, cudaMemcpyAsync(h->d_step, &step, sizeof(int), cudaMemcpyHostToDevice, st));
+    for (int i = 0; i < iters; ++i) {
+        const int l = i % kLayers;
+        DecodeAttnArgs a;
+        a.q = h->q; a.kc = kv_layer(h, h->kcache, l); a.vc = kv_layer(h, h->vcache, l);
+        a.kv_bf16 = h->policy == kPolicyFast; a.B = B; a.t_max = h->t_max;
+        int ns = (888 + 3 * B - 1) / (3 * B);
+        a.nsplit = ns < 1 ? 1 : (ns > 8 ? 8 : ns);
+        a.ctx_base = kPrefix; a.d_step = h->d_step;
+        a.part_acc = h->part_acc; a.part_ml = h->part_ml;
+        a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
+        MB_CK(h, launch_decode_attention(a, st));
+        h->launches += 2;
+    }
+    return 0;
+}
+
 int mb_op_gemm(void* hv, const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int act,
                void* stream) {
     Handle* h = reinterpret_cast<Handle*>(hv);

@@ -166,6 +166,9 @@ class Engine:
                                            top_p, eos_id, _ptr(out), ctypes.byref(steps), self._stream()))
         return out[:, :steps.value]
 
+    def bench_decode_attention(self, batch, ctx, iters):
+        self._ck(self.lib.mb_bench_decode_attention(self.handle, batch, ctx, iters, self._stream()))
+
     def op_gemm(self, a, w, bias=None, act=0):
         a, w = self._dev(a, torch.float32), self._dev(w, torch.float32)
         bias = self._dev(bias, torch.float32) if bias is not None else None

@@ -102,6 +102,7 @@ SYMBOLS = [
     ("mb_decode", _i, [_vp, _i, _i, _f, _f, _i, _vp, ctypes.POINTER(_i), _vp, _vp, _vp]),
     ("mb_generate", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, ctypes.POINTER(_i), _vp]),
     ("mb_generate_host", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, ctypes.POINTER(_i), _vp]),
+    ("mb_bench_decode_attention", _i, [_vp, _i, _i, _i, _vp]),
     ("mb_op_gemm", _i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 ]
 

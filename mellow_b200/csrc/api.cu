@@ -16,6 +16,7 @@ cudaError_t launch_gemm_umma(const GemmArgs& g, int epi, cudaStream_t st, bool* 
 
 namespace {
 
+constexpr int kMaxSplitK = 8;
 constexpr int kDepths[4] = {2, 2, 6, 2};
 constexpr int kHeadsPerStage[4] = {4, 8, 16, 32};
 inline int stage_dim(int i) { return kEmbed << i; }
@@ -161,7 +162,7 @@ struct Handle {
     bf16 *la_hi = nullptr, *la_lo = nullptr, *lh_hi = nullptr, *lh_lo = nullptr;
     void *kcache = nullptr, *vcache = nullptr;
     size_t kv_layer_elems = 0;
-    float *part_acc = nullptr, *part_ml = nullptr;
+    float *part_acc = nullptr, *part_ml = nullptr, *gemm_partial = nullptr;
     int *d_tokens = nullptr, *d_done = nullptr, *d_step = nullptr, *d_stop = nullptr, *d_ids = nullptr;
     float *wave_stage = nullptr;
     int prefix_B = 0;
@@ -363,6 +364,65 @@ inline void* kv_layer(const Handle* h, void* base, int l) {
     return reinterpret_cast<char*>(base) + (size_t)l * h->kv_layer_elems * esz;
 }
 
+inline int decode_nsplit(const Handle* h, int B) {
+    const int tiles_max = (h->t_max + 63) / 64;
+    int ns = (tiles_max + 1) / 2;                         // <= 2 key tiles per CTA, both prefetched up front
+    const int want = (888 + 3 * B - 1) / (3 * B);         // small batches: more splits to fill the 148 SMs
+    if (want > ns) ns = want;
+    return ns < 1 ? 1 : (ns > 8 ? 8 : ns);
+}
+
+int run_decode_attention(Handle* h, int l, int B, cudaStream_t st) {
+    DecodeAttnArgs a;
+    a.q = h->q; a.kc = kv_layer(h, h->kcache, l); a.vc = kv_layer(h, h->vcache, l);
+    a.kv_bf16 = h->policy == kPolicyFast; a.B = B; a.t_max = h->t_max;
+    a.nsplit = decode_nsplit(h, B);
+    a.ctx_base = kPrefix; a.d_step = h->d_step;
+    a.part_acc = h->part_acc; a.part_ml = h->part_ml;
+    a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
+    MB_CK(h, launch_decode_attention(a, st));
+    h->launches += 2;
+    return 0;
+}
+
+// Decode layer for B <= 128 rows (one M tile).  The residual stream update and the next RMSNorm are fused into
+// add_rmsnorm_kernel, which also reduces the split-K partial sums of o_proj / down_proj in a fixed order.
+// On entry la_hi/la_lo hold RMSNorm(x) with this layer's input_layernorm; on exit they hold RMSNorm(x) with
+// `next_norm` (the next layer's input_layernorm, or the final model norm).
+int lm_layer_decode_fused(Handle* h, int l, int B, const float* next_norm, cudaStream_t st) {
+    const LmLayerW& k = h->w.layer[l];
+    {
+        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.qkv, kHidden, B, kQkvDim, kHidden);
+        g.q_out = h->q;
+        g.k_cache = kv_layer(h, h->kcache, l); g.v_cache = kv_layer(h, h->vcache, l);
+        g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
+        g.rows_per_seq = 1; g.pos_base = kPrefix - 1; g.d_pos = h->d_step;
+        g.t_max = h->t_max; g.kv_bf16 = h->policy == kPolicyFast;
+        MB_TRY(run_gemm(h, g, EPI_QKV_ROPE, st));
+    }
+    MB_TRY(run_decode_attention(h, l, B, st));
+    {
+        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.o, kHidden, B, kHidden, kHidden);
+        g.split_k = 3; g.partial = h->gemm_partial;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    MB_CK(h, launch_add_rmsnorm(h->x, h->gemm_partial, 3, B, k.ln2, h->la_hi, lo_of(h, h->la_lo), st));
+    h->launches++;
+    {
+        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.gu, kHidden, B, 2 * kInter, kHidden);
+        g.out_hi = h->lh_hi; g.out_lo = lo_of(h, h->lh_lo); g.ldp = kInter;
+        MB_TRY(run_gemm(h, g, EPI_SWIGLU, st));
+    }
+    {
+        GemmArgs g = gemm_base(h, h->lh_hi, h->lh_lo, kInter, k.down, kInter, B, kHidden, kInter);
+        g.split_k = 4; g.partial = h->gemm_partial;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    }
+    MB_CK(h, launch_add_rmsnorm(h->x, h->gemm_partial, 4, B, next_norm, h->la_hi, lo_of(h, h->la_lo), st));
+    h->launches++;
+    return 0;
+}
+
 // one transformer layer over M rows of h->x.  prefill: rows_per_seq = 389; decode: rows_per_seq = 1.
 int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_t st) {
     const LmLayerW& k = h->w.layer[l];
@@ -380,16 +440,7 @@ int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_
         MB_TRY(run_gemm(h, g, EPI_QKV_ROPE, st));
     }
     if (decode) {
-        DecodeAttnArgs a;
-        a.q = h->q; a.kc = kv_layer(h, h->kcache, l); a.vc = kv_layer(h, h->vcache, l);
-        a.kv_bf16 = h->policy == kPolicyFast; a.B = B; a.t_max = h->t_max;
-        int ns = (888 + 3 * B - 1) / (3 * B);
-        a.nsplit = ns < 1 ? 1 : (ns > 8 ? 8 : ns);
-        a.ctx_base = kPrefix; a.d_step = h->d_step;
-        a.part_acc = h->part_acc; a.part_ml = h->part_ml;
-        a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
-        MB_CK(h, launch_decode_attention(a, st));
-        h->launches += 2;
+        MB_TRY(run_decode_attention(h, l, B, st));
     } else {
         MB_CK(h, launch_prefill_attention(h->q, kv_layer(h, h->kcache, l), kv_layer(h, h->vcache, l),
                                           h->policy == kPolicyFast, B, rows_per_seq, h->t_max, h->la_hi,
@@ -425,6 +476,15 @@ int lm_head(Handle* h, int B, int row_stride, int row_off, cudaStream_t st) {
 }
 
 int decode_step(Handle* h, int B, cudaStream_t st) {
+    if (B <= 128 && getenv("MB_DECODE_UNFUSED") == nullptr) {
+        MB_CK(h, launch_add_rmsnorm(h->x, nullptr, 0, B, h->w.layer[0].ln1, h->la_hi, lo_of(h, h->la_lo), st));
+        h->launches++;
+        for (int l = 0; l < kLayers; ++l)
+            MB_TRY(lm_layer_decode_fused(h, l, B, l + 1 < kLayers ? h->w.layer[l + 1].ln1 : h->w.lm_norm, st));
+        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, h->w.head, kHidden, B, kVocab, kHidden);
+        g.out_f32 = h->logits; g.ldo = kVocab;
+        return run_gemm(h, g, EPI_GENERIC, st);
+    }
     for (int l = 0; l < kLayers; ++l) MB_TRY(lm_layer(h, l, B, 1, true, st));
     return lm_head(h, B, 1, 0, st);
 }
@@ -592,6 +652,7 @@ static int create_body(Handle* h) {
     h->kcache = kc; h->vcache = vc;
     MB_TRY(dev_alloc(h, &h->part_acc, B * kHeads * 8 * kHeadDim));
     MB_TRY(dev_alloc(h, &h->part_ml, B * kHeads * 8 * 2));
+    MB_TRY(dev_alloc(h, &h->gemm_partial, (size_t)kMaxSplitK * 128 * kHidden));
     MB_TRY(dev_alloc(h, &h->d_tokens, B * h->max_new));
     MB_TRY(dev_alloc(h, &h->d_done, B));
     MB_TRY(dev_alloc(h, &h->d_step, 4));
@@ -756,17 +817,7 @@ int mb_bench_decode_attention(void* hv, int B, int ctx, int iters, void* stream)
     const int step = ctx - kPrefix;
     MB_CK(h, cudaMemcpyAsync(h->d_step, &step, sizeof(int), cudaMemcpyHostToDevice, st));
     for (int i = 0; i < iters; ++i) {
-        const int l = i % kLayers;
-        DecodeAttnArgs a;
-        a.q = h->q; a.kc = kv_layer(h, h->kcache, l); a.vc = kv_layer(h, h->vcache, l);
-        a.kv_bf16 = h->policy == kPolicyFast; a.B = B; a.t_max = h->t_max;
-        int ns = (888 + 3 * B - 1) / (3 * B);
-        a.nsplit = ns < 1 ? 1 : (ns > 8 ? 8 : ns);
-        a.ctx_base = kPrefix; a.d_step = h->d_step;
-        a.part_acc = h->part_acc; a.part_ml = h->part_ml;
-        a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
-        MB_CK(h, launch_decode_attention(a, st));
-        h->launches += 2;
+        MB_TRY(run_decode_attention(h, i % kLayers, B, st));
     }
     return 0;
 }

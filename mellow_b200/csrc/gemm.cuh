@@ -13,6 +13,7 @@ struct GemmArgs {
     const bf16* W_hi; const bf16* W_lo; int ldw;      // weights [N,K], K contiguous (nn.Linear layout)
     int M, N, K;                                      // K % 32 == 0
     int passes;                                       // 3: hi*hi + hi*lo + lo*hi ; 1: hi*hi
+    int split_k; float* partial;                      // split_k > 1: raw fp32 partial sums [split_k][M][N], no epilogue
     // EPI_GENERIC: v = act(acc + bias) + residual -> out_f32 and/or bf16 planes
     const float* bias;
     const float* residual; int ldr;

@@ -9,7 +9,6 @@ namespace {
 
 constexpr int BK = 32;
 constexpr int LDS = BK + 8;      // padded smem row (bf16 elements): 80 B, conflict-free for ldmatrix
-constexpr int STAGES = 3;
 
 __device__ __forceinline__ void ldsm_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, const bf16* p) {
     uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
@@ -23,7 +22,7 @@ __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int BM, int BN>
+template <int BM, int BN, int STAGES>
 struct Smem {
     bf16 a_hi[STAGES][BM][LDS];
     bf16 a_lo[STAGES][BM][LDS];
@@ -31,23 +30,27 @@ struct Smem {
     bf16 b_lo[STAGES][BN][LDS];
 };
 
-template <int BM, int BN, int WM, int WN, int EPI>
+template <int BM, int BN, int WM, int WN, int EPI, int STAGES>
 __global__ void __launch_bounds__(WM * WN * 32) gemm_mma_kernel(const GemmArgs g) {
     constexpr int NT = WM * WN * 32;
     constexpr int TM = BM / WM, TN = BN / WN;      // warp tile
     constexpr int MI = TM / 16, NI = TN / 8;
     static_assert(NI % 2 == 0, "warp tile N must be a multiple of 16");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem<BM, BN>& sm = *reinterpret_cast<Smem<BM, BN>*>(smem_raw);
+    Smem<BM, BN, STAGES>& sm = *reinterpret_cast<Smem<BM, BN, STAGES>*>(smem_raw);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wm = warp / WN, wn = warp % WN;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const bool split = g.passes == 3;
-    const int KT = g.K / BK;
+    // split-K: blockIdx.z owns a contiguous range of K blocks and writes a raw fp32 partial tile
+    const int kt_all = g.K / BK;
+    const int nsplit = g.split_k > 1 ? g.split_k : 1;
+    const int kt_begin = (int)(((long long)kt_all * blockIdx.z) / nsplit);
+    const int KT = (int)(((long long)kt_all * (blockIdx.z + 1)) / nsplit) - kt_begin;
 
     auto load_stage = [&](int stage, int kt) {
-        const int k0 = kt * BK;
+        const int k0 = (kt_begin + kt) * BK;
         // A: BM rows x 4 chunks of 16 B per plane
         for (int c = tid; c < BM * 4; c += NT) {
             const int r = c >> 2, ch = c & 3;
@@ -130,23 +133,29 @@ __global__ void __launch_bounds__(WM * WN * 32) gemm_mma_kernel(const GemmArgs g
             const int n = n0 + wn * TN + j * 8 + (lane & 3) * 2;
             if (n >= g.N) continue;
             const int r0 = m0 + wm * TM + i * 16 + (lane >> 2);
+            if (nsplit > 1) {
+                float* p = g.partial + (size_t)blockIdx.z * g.M * g.N;
+                if (r0 < g.M) *reinterpret_cast<float2*>(p + (size_t)r0 * g.N + n) = make_float2(acc[i][j][0], acc[i][j][1]);
+                if (r0 + 8 < g.M) *reinterpret_cast<float2*>(p + (size_t)(r0 + 8) * g.N + n) = make_float2(acc[i][j][2], acc[i][j][3]);
+                continue;
+            }
             if (r0 < g.M) epilogue_pair<EPI>(g, r0, n, acc[i][j][0], acc[i][j][1]);
             if (r0 + 8 < g.M) epilogue_pair<EPI>(g, r0 + 8, n, acc[i][j][2], acc[i][j][3]);
         }
     }
 }
 
-template <int BM, int BN, int WM, int WN, int EPI>
+template <int BM, int BN, int WM, int WN, int EPI, int STAGES = 3>
 cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
-    auto kern = gemm_mma_kernel<BM, BN, WM, WN, EPI>;
-    const int smem = (int)sizeof(Smem<BM, BN>);
+    auto kern = gemm_mma_kernel<BM, BN, WM, WN, EPI, STAGES>;
+    const int smem = (int)sizeof(Smem<BM, BN, STAGES>);
     static bool configured = false;     // per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.split_k > 1 ? g.split_k : 1);
     kern<<<grid, WM * WN * 32, smem, st>>>(g);
     return cudaGetLastError();
 }
@@ -154,9 +163,11 @@ cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
 template <int EPI>
 cudaError_t launch_epi(const GemmArgs& g, cudaStream_t st) {
     if (g.M <= 128 && g.N <= 4096) {
-        // decode-sized: one M tile; narrow N tiles so more SMs stream the weights
-        if (g.M <= 64) return launch_cfg<64, 32, 2, 2, EPI>(g, st);
-        return launch_cfg<128, 32, 4, 2, EPI>(g, st);
+        // decode-sized: one M tile; 16-column tiles (x split-K) so ~100+ SMs stream the weights, 6-deep cp.async ring
+        // (every CTA re-reads the whole activation tile from L2, so wide-N GEMMs take 32-column tiles)
+        if (g.M <= 64) return launch_cfg<64, 16, 4, 1, EPI, 6>(g, st);
+        if (g.N >= 2048) return launch_cfg<128, 32, 4, 2, EPI, 6>(g, st);
+        return launch_cfg<128, 16, 8, 1, EPI, 6>(g, st);
     }
     if (g.N % 96 == 0 && g.N % 128 != 0) return launch_cfg<128, 96, 4, 2, EPI>(g, st);
     return launch_cfg<128, 128, 2, 4, EPI>(g, st);
@@ -166,6 +177,7 @@ cudaError_t launch_epi(const GemmArgs& g, cudaStream_t st) {
 
 cudaError_t launch_gemm_mma(const GemmArgs& g, int epi, cudaStream_t st) {
     if (g.K % BK != 0 || g.M <= 0 || g.N <= 0) return cudaErrorInvalidValue;
+    if (g.split_k > 1 && (epi != EPI_GENERIC || !g.partial || (g.N & 1))) return cudaErrorInvalidValue;
     switch (epi) {
         case EPI_GENERIC: return launch_epi<EPI_GENERIC>(g, st);
         case EPI_SWIGLU: return launch_epi<EPI_SWIGLU>(g, st);

@@ -62,6 +62,8 @@ struct SampleArgs {
     int* done;                      // [B] row has emitted eos
     float* logits_dump;             // optional [max_len][B][V] temperature-scaled logits
 };
+cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, int M, const float* w, bf16* hi, bf16* lo,
+                               cudaStream_t st);
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st);
 cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st);
 

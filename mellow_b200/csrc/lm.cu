@@ -127,10 +127,9 @@ struct DecodeSmem {
     static constexpr int KLD = kHeadDim + 16 / sizeof(T);         // +16 B: conflict-free 16 B row reads
     T k[2][64][KLD];
     T v[2][64][kHeadDim];
-    float q[3][kHeadDim];
-    float sc[3][64];
+    __align__(16) float sc[3][64];
     float alpha[3], m[3], l[3];
-    float red[3][64];
+    float red[4][3][kHeadDim];
 };
 
 template <typename T>
@@ -148,10 +147,6 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
     const T* kb = reinterpret_cast<const T*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * kHeadDim;
     const T* vb = reinterpret_cast<const T*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * kHeadDim;
 
-    for (int e = tid; e < 3 * kHeadDim; e += 128)
-        sm.q[e >> 6][e & 63] = a.q[(size_t)b * kHidden + (kvh * 3 + (e >> 6)) * kHeadDim + (e & 63)];
-    if (tid < 3) { sm.m[tid] = -INFINITY; sm.l[tid] = 0.f; }
-
     auto load_tile = [&](int buf, int tile) {
         const int key0 = tile << 6;
         for (int c = tid; c < 64 * NCH; c += 128) {
@@ -163,40 +158,56 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
             cp_async16(&sm.v[buf][j][ch * E], vb + off, ok);
         }
     };
-
-    float acc[3] = {0.f, 0.f, 0.f};
-    const int d_own = tid & 63, khalf = tid >> 6;
     if (t_begin < t_end) load_tile(0, t_begin);
     cp_async_commit();
+    if (t_begin + 1 < t_end) load_tile(1, t_begin + 1);
+    cp_async_commit();
+
+    // score role: thread = (key j, half); each half owns every other 16 B chunk of the key row.  The matching
+    // slices of the three query heads live in registers.
+    const int sj = tid >> 1, shalf = tid & 1;
+    float qreg[3][kHeadDim / 2];
+    {
+        const float* qb = a.q + (size_t)b * kHidden + (kvh * 3) * kHeadDim;
+#pragma unroll
+        for (int h = 0; h < 3; ++h)
+#pragma unroll
+            for (int i = 0; i < NCH / 2; ++i)
+#pragma unroll
+                for (int e = 0; e < E; e += 4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(qb + h * kHeadDim + (2 * i + shalf) * E + e);
+                    qreg[h][i * E + e] = t4.x; qreg[h][i * E + e + 1] = t4.y;
+                    qreg[h][i * E + e + 2] = t4.z; qreg[h][i * E + e + 3] = t4.w;
+                }
+    }
+    if (tid < 3) { sm.m[tid] = -INFINITY; sm.l[tid] = 0.f; }
+
+    // PV role: thread = (dim pair, key quarter)
+    const int dp = (tid & 31) * 2, kq = tid >> 5;
+    float acc[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     for (int t = t_begin; t < t_end; ++t) {
         const int buf = (t - t_begin) & 1;
-        if (t + 1 < t_end) load_tile(buf ^ 1, t + 1);
-        cp_async_commit();
-        cp_async_wait<1>();
+        if (t + 1 < t_end) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
-        // scores: thread = (key j, half); each half takes every other 16 B chunk of the key row
         {
-            const int j = tid >> 1, half = tid & 1;
             float p0 = 0.f, p1 = 0.f, p2 = 0.f;
 #pragma unroll
             for (int i = 0; i < NCH / 2; ++i) {
-                const int ch = 2 * i + half;
-                const T* kp = &sm.k[buf][j][ch * E];
+                const T* kp = &sm.k[buf][sj][(2 * i + shalf) * E];
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const float kvv = kv_load(kp + e);
-                    const int d = ch * E + e;
-                    p0 += sm.q[0][d] * kvv; p1 += sm.q[1][d] * kvv; p2 += sm.q[2][d] * kvv;
+                    p0 += qreg[0][i * E + e] * kvv; p1 += qreg[1][i * E + e] * kvv; p2 += qreg[2][i * E + e] * kvv;
                 }
             }
             p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
             p1 += __shfl_xor_sync(0xffffffffu, p1, 1);
             p2 += __shfl_xor_sync(0xffffffffu, p2, 1);
-            if (half == 0) {
-                const bool ok = ((t << 6) + j) < ctx;
-                sm.sc[0][j] = ok ? p0 * 0.125f : -INFINITY;
-                sm.sc[1][j] = ok ? p1 * 0.125f : -INFINITY;
-                sm.sc[2][j] = ok ? p2 * 0.125f : -INFINITY;
+            if (shalf == 0) {
+                const bool ok = ((t << 6) + sj) < ctx;
+                sm.sc[0][sj] = ok ? p0 * 0.125f : -INFINITY;
+                sm.sc[1][sj] = ok ? p1 * 0.125f : -INFINITY;
+                sm.sc[2][sj] = ok ? p2 * 0.125f : -INFINITY;
             }
         }
         __syncthreads();
@@ -209,7 +220,6 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
             const float ls = warp_sum(e0 + e1);
             sm.sc[warp][lane] = e0;
             sm.sc[warp][lane + 32] = e1;
-            __syncwarp();
             if (lane == 0) {
                 const float al = expf(m_old - m_new);
                 sm.alpha[warp] = al;
@@ -219,28 +229,43 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
         }
         __syncthreads();
         {
-            const float a0 = sm.alpha[0], a1 = sm.alpha[1], a2 = sm.alpha[2];
-            float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-#pragma unroll 8
-            for (int jj = 0; jj < 32; ++jj) {
-                const int j = khalf * 32 + jj;
-                const float vv = kv_load(&sm.v[buf][j][d_own]);
-                x0 += sm.sc[0][j] * vv; x1 += sm.sc[1][j] * vv; x2 += sm.sc[2][j] * vv;
+            float x[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4) {
+                const int j = kq * 16 + jj;
+                float4 p[3];
+#pragma unroll
+                for (int h = 0; h < 3; ++h) p[h] = *reinterpret_cast<const float4*>(&sm.sc[h][j]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float v0 = kv_load(&sm.v[buf][j + u][dp]), v1 = kv_load(&sm.v[buf][j + u][dp + 1]);
+#pragma unroll
+                    for (int h = 0; h < 3; ++h) {
+                        const float pv = u == 0 ? p[h].x : (u == 1 ? p[h].y : (u == 2 ? p[h].z : p[h].w));
+                        x[h][0] += pv * v0; x[h][1] += pv * v1;
+                    }
+                }
             }
-            acc[0] = acc[0] * a0 + x0; acc[1] = acc[1] * a1 + x1; acc[2] = acc[2] * a2 + x2;
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+                const float al = sm.alpha[h];
+                acc[h][0] = acc[h][0] * al + x[h][0];
+                acc[h][1] = acc[h][1] * al + x[h][1];
+            }
         }
-        __syncthreads();
+        __syncthreads();                                             // tile buffer and sc are reused
+        if (t + 2 < t_end) load_tile(buf, t + 2);
+        cp_async_commit();
     }
     cp_async_wait<0>();
-    if (khalf == 1) { sm.red[0][d_own] = acc[0]; sm.red[1][d_own] = acc[1]; sm.red[2][d_own] = acc[2]; }
-    __syncthreads();
-    if (khalf == 0) {
 #pragma unroll
-        for (int hh = 0; hh < 3; ++hh) {
-            const size_t o = (((size_t)b * kHeads + kvh * 3 + hh) * a.nsplit + split);
-            a.part_acc[o * kHeadDim + d_own] = acc[hh] + sm.red[hh][d_own];
-            if (d_own == 0) { a.part_ml[o * 2] = sm.m[hh]; a.part_ml[o * 2 + 1] = sm.l[hh]; }
-        }
+    for (int h = 0; h < 3; ++h) { sm.red[kq][h][dp] = acc[h][0]; sm.red[kq][h][dp + 1] = acc[h][1]; }
+    __syncthreads();
+    for (int e = tid; e < 3 * kHeadDim; e += 128) {
+        const int h = e >> 6, d = e & 63;
+        const size_t o = (((size_t)b * kHeads + kvh * 3 + h) * a.nsplit + split);
+        a.part_acc[o * kHeadDim + d] = sm.red[0][h][d] + sm.red[1][h][d] + sm.red[2][h][d] + sm.red[3][h][d];
+        if (d == 0) { a.part_ml[o * 2] = sm.m[h]; a.part_ml[o * 2 + 1] = sm.l[h]; }
     }
 }
 
@@ -311,6 +336,41 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
             reinterpret_cast<const float4*>(a.embed + (size_t)tok * kHidden)[tid];
 }
 
+// Decode-path fusion: x[row] += sum_s partial[s][row] (split-K partial sums of the preceding o_proj / down_proj GEMM,
+// fixed summation order => deterministic), then RMSNorm(x[row]) -> bf16 hi/lo planes for the next GEMM.
+// n_partial == 0 gives a plain RMSNorm.  One warp per row.
+template <int S>
+__global__ void __launch_bounds__(128) add_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ partial,
+                                                          int M, const float* __restrict__ w,
+                                                          bf16* __restrict__ hi, bf16* __restrict__ lo) {
+    constexpr int PER = kHidden / 32;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float v[PER], p[S > 0 ? S : 1][PER], wv[PER];
+    float* xr = x + (size_t)row * kHidden;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) { v[j] = xr[lane + 32 * j]; wv[j] = w[lane + 32 * j]; }
+#pragma unroll
+    for (int s = 0; s < S; ++s)                                    // all loads in flight before the first add
+#pragma unroll
+        for (int j = 0; j < PER; ++j) p[s][j] = partial[((size_t)s * M + row) * kHidden + lane + 32 * j];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int j = 0; j < PER; ++j) v[j] += p[s][j];
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < PER; ++j) sq += v[j] * v[j];
+    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / kHidden) + 1e-5f);
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        const int i = lane + 32 * j;
+        if (S > 0) xr[i] = v[j];
+        store_planes1(hi, lo, (size_t)row * kHidden + i, wv[j] * (v[j] * rstd));
+    }
+}
+
 // step += 1; records the first step count at which every row has emitted eos (wrapper.py:247-249)
 __global__ void step_advance_kernel(int* d_step, const int* done, int B, int* d_stop_step) {
     __shared__ int all;
@@ -363,6 +423,18 @@ cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
     dim3 g2(kHeads, a.B);
     decode_combine_kernel<<<g2, 64, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, int M, const float* w, bf16* hi, bf16* lo,
+                               cudaStream_t st) {
+    const int grid = (M + 3) / 4;
+    switch (n_partial) {
+        case 0: add_rmsnorm_kernel<0><<<grid, 128, 0, st>>>(x, partial, M, w, hi, lo); break;
+        case 3: add_rmsnorm_kernel<3><<<grid, 128, 0, st>>>(x, partial, M, w, hi, lo); break;
+        case 4: add_rmsnorm_kernel<4><<<grid, 128, 0, st>>>(x, partial, M, w, hi, lo); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 

@@ -142,7 +142,7 @@ Layout& layout() {
 thread_local char g_create_error[512] = "";
 
 struct Handle {
-    int device = 0, max_batch = 0, max_new = 0, policy = 0, engine = 0;
+    int device = 0, max_batch = 0, max_new = 0, policy = 0, engine = 1;   // engine 1: tcgen05 where a tile fits
     int t_max = 0;
     bool bound = false;
     Weights w;

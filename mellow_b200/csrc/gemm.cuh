@@ -31,18 +31,16 @@ struct GemmArgs {
     int t_max; int kv_bf16;
 };
 
+// (m, n) and (m, n+1); n is even; caller guarantees m < M and n < N.  r0/r1: residual values (EPI_GENERIC), already
+// loaded by the caller so that engines can batch those loads ahead of the dependent stores.
 template <int EPI>
-__device__ __forceinline__ void epilogue_pair(const GemmArgs& g, int m, int n, float v0, float v1) {
-    // (m, n) and (m, n+1); n is even; caller guarantees m < M and n < N.
+__device__ __forceinline__ void epilogue_pair_r(const GemmArgs& g, int m, int n, float v0, float v1, float r0, float r1) {
     if (EPI == EPI_GENERIC) {
         const bool has1 = (n + 1 < g.N);
-        if (g.bias) { v0 += g.bias[n]; if (has1) v1 += g.bias[n + 1]; }
+        if (g.bias) { v0 += __ldg(g.bias + n); if (has1) v1 += __ldg(g.bias + n + 1); }
         if (g.act == ACT_GELU) { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
         else if (g.act == ACT_SIGMOID) { v0 = sigmoidf_(v0); v1 = sigmoidf_(v1); }
-        if (g.residual) {
-            const float* r = g.residual + (size_t)m * g.ldr + n;
-            v0 += r[0]; if (has1) v1 += r[1];
-        }
+        v0 += r0; v1 += r1;
         if (g.out_f32) {
             float* o = g.out_f32 + (size_t)m * g.ldo + n;
             if (has1 && !(g.ldo & 1)) *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
@@ -63,7 +61,7 @@ __device__ __forceinline__ void epilogue_pair(const GemmArgs& g, int m, int n, f
         const int pos = g.pos_base + (g.d_pos ? *g.d_pos : 0) + s;
         if (n < kHidden + kKvHeads * kHeadDim) {
             const int i = (n & (kHeadDim - 1)) >> 1;
-            const float c = g.rope_cos[pos * 32 + i], sn = g.rope_sin[pos * 32 + i];
+            const float c = __ldg(g.rope_cos + pos * 32 + i), sn = __ldg(g.rope_sin + pos * 32 + i);
             const float r0 = v0 * c - v1 * sn;
             const float r1 = v1 * c + v0 * sn;
             v0 = r0; v1 = r1;
@@ -81,6 +79,23 @@ __device__ __forceinline__ void epilogue_pair(const GemmArgs& g, int m, int n, f
             else kv_store2(reinterpret_cast<float*>(base) + off, v0, v1);
         }
     }
+}
+
+template <int EPI>
+__device__ __forceinline__ void load_residual_pair(const GemmArgs& g, int m, int n, float& r0, float& r1) {
+    r0 = 0.f; r1 = 0.f;
+    if (EPI == EPI_GENERIC && g.residual) {
+        const float* r = g.residual + (size_t)m * g.ldr + n;
+        r0 = r[0];
+        if (n + 1 < g.N) r1 = r[1];
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_pair(const GemmArgs& g, int m, int n, float v0, float v1) {
+    float r0, r1;
+    load_residual_pair<EPI>(g, m, n, r0, r1);
+    epilogue_pair_r<EPI>(g, m, n, v0, v1, r0, r1);
 }
 
 // Engine entry points (gemm_mma.cu, gemm_umma.cu)

@@ -12,6 +12,11 @@
 
 namespace mb {
 
+bool pdl_enabled() {
+    static const bool on = getenv("MB_NO_PDL") == nullptr;
+    return on;
+}
+
 cudaError_t launch_gemm_umma(const GemmArgs& g, int epi, cudaStream_t st, bool* handled);   // gemm_umma.cu
 
 namespace {
@@ -377,6 +382,7 @@ int run_decode_attention(Handle* h, int l, int B, cudaStream_t st) {
     a.q = h->q; a.kc = kv_layer(h, h->kcache, l); a.vc = kv_layer(h, h->vcache, l);
     a.kv_bf16 = h->policy == kPolicyFast; a.B = B; a.t_max = h->t_max;
     a.nsplit = decode_nsplit(h, B);
+    a.tps = ((h->t_max + 63) / 64 + a.nsplit - 1) / a.nsplit;
     a.ctx_base = kPrefix; a.d_step = h->d_step;
     a.part_acc = h->part_acc; a.part_ml = h->part_ml;
     a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
@@ -840,6 +846,9 @@ int mb_op_gemm(void* hv, const float* A, const float* W, const float* bias, floa
             rc = fail(h, "split_planes launch failed");
             break;
         }
+        // the GEMM kernels prefetch W before their programmatic-dependency wait (weights are never produced by the
+        // preceding kernel on the product path); here W was just written by split_planes, so drain the stream first
+        if (cudaStreamSynchronize(st) != cudaSuccess) { rc = fail(h, "stream sync failed"); break; }
         Plane wp{wh, wl};
         GemmArgs g = gemm_base(h, ah, al, K, wp, K, M, N, K);
         g.bias = bias; g.act = act; g.out_f32 = C; g.ldo = N;

@@ -98,6 +98,12 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
 }
 
+// Programmatic dependent launch (PDL): every kernel of the library triggers its dependents at entry and waits for its
+// predecessor right before the first dependent global access, so launch latency, prologues and weight prefetches of
+// kernel N+1 overlap the tail of kernel N (also inside the captured decode graph).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // KV-cache element types
 __device__ __forceinline__ float kv_load(const float* p) { return *p; }
 __device__ __forceinline__ float kv_load(const bf16* p) { return __bfloat162float(*p); }
@@ -107,6 +113,20 @@ __device__ __forceinline__ void kv_store2(bf16* p, float a, float b) {
     v.x = __float2bfloat16_rn(a);
     v.y = __float2bfloat16_rn(b);
     *reinterpret_cast<__nv_bfloat162*>(p) = v;
+}
+
+// Host: launch with the programmatic-stream-serialization attribute (disabled by MB_NO_PDL=1).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 }  // namespace mb

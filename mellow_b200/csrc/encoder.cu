@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(256) norm_kernel(const NormArgs a) {
     constexpr int PER = C / 32;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    pdl_trigger();
+    pdl_wait();
     if (row >= a.rows) return;
     float v[PER];
     if (KIND == NORM_LN_MERGE) {
@@ -68,15 +70,14 @@ template <int KIND>
 cudaError_t launch_norm_kind(const NormArgs& a, cudaStream_t st) {
     const int grid = (a.rows + 7) / 8;
     switch (a.C) {
-        case 96: norm_kernel<96, KIND><<<grid, 256, 0, st>>>(a); break;
-        case 192: norm_kernel<192, KIND><<<grid, 256, 0, st>>>(a); break;
-        case 384: norm_kernel<384, KIND><<<grid, 256, 0, st>>>(a); break;
-        case 576: norm_kernel<576, KIND><<<grid, 256, 0, st>>>(a); break;
-        case 768: norm_kernel<768, KIND><<<grid, 256, 0, st>>>(a); break;
-        case 1536: norm_kernel<1536, KIND><<<grid, 256, 0, st>>>(a); break;
+        case 96: return launch_k(norm_kernel<96, KIND>, dim3(grid), dim3(256), 0, st, a);
+        case 192: return launch_k(norm_kernel<192, KIND>, dim3(grid), dim3(256), 0, st, a);
+        case 384: return launch_k(norm_kernel<384, KIND>, dim3(grid), dim3(256), 0, st, a);
+        case 576: return launch_k(norm_kernel<576, KIND>, dim3(grid), dim3(256), 0, st, a);
+        case 768: return launch_k(norm_kernel<768, KIND>, dim3(grid), dim3(256), 0, st, a);
+        case 1536: return launch_k(norm_kernel<1536, KIND>, dim3(grid), dim3(256), 0, st, a);
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -104,6 +105,8 @@ __global__ void __launch_bounds__(64) window_attention_kernel(const float* __res
     const int sy = (y + shift) % R, sx = (x + shift) % R;
     const size_t tok = (size_t)clip * R * R + (size_t)sy * R + sx;
     const float* row = qkv + tok * 3 * C + head * kHd;
+    pdl_trigger();
+    pdl_wait();
     float q[kHd];
 #pragma unroll
     for (int d = 0; d < kHd; d += 4) {
@@ -162,6 +165,8 @@ __global__ void __launch_bounds__(256) tail_gather_kernel(const float* __restric
                                                           bf16* __restrict__ col_hi, bf16* __restrict__ col_lo) {
     const int n = blockIdx.y, t = blockIdx.x;                               // t in 0..32 ; t == 32 -> latent
     const float* yn = y + (size_t)n * 64 * kEncOut;
+    pdl_trigger();
+    pdl_wait();
     if (t == 32) {
         for (int c = threadIdx.x; c < kEncOut; c += 256) {
             float s = 0.f;
@@ -187,6 +192,8 @@ __global__ void __launch_bounds__(256) assemble33_kernel(const float* __restrict
                                                          const float* __restrict__ frames, bf16* __restrict__ a_hi,
                                                          bf16* __restrict__ a_lo) {
     const int n = blockIdx.y, r = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
     const float* src = (r == 0) ? latent + (size_t)n * kEncOut : frames + ((size_t)n * 32 + (r - 1)) * kEncOut;
     const size_t o = ((size_t)n * kAudioRows + r) * kEncOut;
     for (int c = threadIdx.x; c < kEncOut; c += 256) store_planes1(a_hi, a_lo, o + c, src[c]);
@@ -195,12 +202,16 @@ __global__ void __launch_bounds__(256) assemble33_kernel(const float* __restrict
 __global__ void __launch_bounds__(256) gelu_planes_kernel(const float* __restrict__ x, size_t n, bf16* __restrict__ hi,
                                                           bf16* __restrict__ lo) {
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (i < n) store_planes1(hi, lo, i, gelu_erf(x[i]));
 }
 
 __global__ void __launch_bounds__(256) split_planes_kernel(const float* __restrict__ x, size_t n, bf16* __restrict__ hi,
                                                            bf16* __restrict__ lo) {
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    pdl_trigger();
+    pdl_wait();
     if (i < n) store_planes1(hi, lo, i, x[i]);
 }
 
@@ -219,32 +230,27 @@ cudaError_t launch_window_attention(const float* qkv, const float* relbias, bf16
                                     int res, int C, int n_heads, int shift, cudaStream_t st) {
     if (C != n_heads * kHd || res % kWin != 0) return cudaErrorInvalidValue;
     dim3 grid(n_heads, (res / kWin) * (res / kWin), n_clips);
-    window_attention_kernel<<<grid, 64, 0, st>>>(qkv, relbias, out_hi, out_lo, res, C, n_heads, shift);
-    return cudaGetLastError();
+    return launch_k(window_attention_kernel, grid, dim3(64), 0, st, qkv, relbias, out_hi, out_lo, res, C, n_heads, shift);
 }
 
 cudaError_t launch_tail_gather(const float* y, int n_clips, float* latent, bf16* col_hi, bf16* col_lo,
                                cudaStream_t st) {
     dim3 grid(33, n_clips);
-    tail_gather_kernel<<<grid, 256, 0, st>>>(y, latent, col_hi, col_lo);
-    return cudaGetLastError();
+    return launch_k(tail_gather_kernel, grid, dim3(256), 0, st, y, latent, col_hi, col_lo);
 }
 
 cudaError_t launch_assemble33(const float* latent, const float* frames, int n_clips, bf16* a_hi, bf16* a_lo,
                               cudaStream_t st) {
     dim3 grid(kAudioRows, n_clips);
-    assemble33_kernel<<<grid, 256, 0, st>>>(latent, frames, a_hi, a_lo);
-    return cudaGetLastError();
+    return launch_k(assemble33_kernel, grid, dim3(256), 0, st, latent, frames, a_hi, a_lo);
 }
 
 cudaError_t launch_gelu_planes(const float* x, size_t n, bf16* hi, bf16* lo, cudaStream_t st) {
-    gelu_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, hi, lo);
-    return cudaGetLastError();
+    return launch_k(gelu_planes_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, n, hi, lo);
 }
 
 cudaError_t launch_split_planes(const float* x, size_t n, bf16* hi, bf16* lo, cudaStream_t st) {
-    split_planes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, hi, lo);
-    return cudaGetLastError();
+    return launch_k(split_planes_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, st, x, n, hi, lo);
 }
 
 }  // namespace mb

@@ -35,6 +35,8 @@ __global__ void __launch_bounds__(kFramesPerCta * 32) logmel_kernel(const float*
     const int f0 = blockIdx.x * kFramesPerCta;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float* x = wave + (size_t)clip * kClipSamples;
+    pdl_trigger();
+    pdl_wait();
 
     // center=True, pad_mode='reflect': padded[i] = x[reflect(i - 512)]
     const int s0 = f0 * kHop - kNfft / 2;
@@ -119,9 +121,11 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
     __shared__ float sw[kEmbed * 16];
     __shared__ float sb[kEmbed], sg[kEmbed], sbeta[kEmbed];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
     for (int i = tid; i < kEmbed * 16; i += 256) sw[i] = w.w[i];
     for (int i = tid; i < kEmbed; i += 256) { sb[i] = w.b[i]; sg[i] = w.ln_w[i]; sbeta[i] = w.ln_b[i]; }
     __syncthreads();
+    pdl_wait();
     const int clip = blockIdx.y, ph = blockIdx.x;
     const float* src = bn + (size_t)clip * kFrames * kMels;
     const float scale = (float)(kFrames - 1) / (float)(kStretch - 1);
@@ -179,14 +183,12 @@ cudaError_t launch_logmel(const float* wave, int n_clips, const FrontendW& w, fl
         configured = true;
     }
     dim3 grid((kFrames + kFramesPerCta - 1) / kFramesPerCta, n_clips);
-    logmel_kernel<<<grid, kFramesPerCta * 32, sizeof(LogmelSmem), st>>>(wave, w, logmel_out, bn_out);
-    return cudaGetLastError();
+    return launch_k(logmel_kernel, grid, dim3(kFramesPerCta * 32), sizeof(LogmelSmem), st, wave, w, logmel_out, bn_out);
 }
 
 cudaError_t launch_patch_embed(const float* bn, int n_clips, const PatchW& w, float* x_out, cudaStream_t st) {
     dim3 grid(kGrid0, n_clips);
-    patch_embed_kernel<<<grid, 256, 0, st>>>(bn, w, x_out);
-    return cudaGetLastError();
+    return launch_k(patch_embed_kernel, grid, dim3(256), 0, st, bn, w, x_out);
 }
 
 }  // namespace mb

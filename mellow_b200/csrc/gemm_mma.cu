@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(WM * WN * 32) gemm_mma_kernel(const GemmArgs g
     const int kt_begin = (int)(((long long)kt_all * blockIdx.z) / nsplit);
     const int KT = (int)(((long long)kt_all * (blockIdx.z + 1)) / nsplit) - kt_begin;
 
-    auto load_stage = [&](int stage, int kt) {
+    auto load_a = [&](int stage, int kt) {
         const int k0 = (kt_begin + kt) * BK;
         // A: BM rows x 4 chunks of 16 B per plane
         for (int c = tid; c < BM * 4; c += NT) {
@@ -60,6 +60,9 @@ __global__ void __launch_bounds__(WM * WN * 32) gemm_mma_kernel(const GemmArgs g
             cp_async16(&sm.a_hi[stage][r][ch * 8], g.A_hi + off, ok);
             if (split) cp_async16(&sm.a_lo[stage][r][ch * 8], g.A_lo + off, ok);
         }
+    };
+    auto load_b = [&](int stage, int kt) {
+        const int k0 = (kt_begin + kt) * BK;
         for (int c = tid; c < BN * 4; c += NT) {
             const int r = c >> 2, ch = c & 3;
             const int n = n0 + r;
@@ -78,9 +81,16 @@ __global__ void __launch_bounds__(WM * WN * 32) gemm_mma_kernel(const GemmArgs g
 #pragma unroll
             for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
 
+    // PDL: weights never depend on the preceding kernel, so the first ring slots of W are requested before waiting
+    // on it; the activation tiles follow after the wait (they join the same cp.async groups).
+    pdl_trigger();
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s)
+        if (s < KT) load_b(s, s);
+    pdl_wait();
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KT) load_stage(s, s);
+        if (s < KT) load_a(s, s);
         cp_async_commit();
     }
 
@@ -89,7 +99,7 @@ __global__ void __launch_bounds__(WM * WN * 32) gemm_mma_kernel(const GemmArgs g
         __syncthreads();
         {
             const int nk = kt + STAGES - 1;
-            if (nk < KT) load_stage(nk % STAGES, nk);
+            if (nk < KT) { load_a(nk % STAGES, nk); load_b(nk % STAGES, nk); }
             cp_async_commit();
         }
         const int st = kt % STAGES;
@@ -156,8 +166,7 @@ cudaError_t launch_cfg(const GemmArgs& g, cudaStream_t st) {
         configured = true;
     }
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.split_k > 1 ? g.split_k : 1);
-    kern<<<grid, WM * WN * 32, smem, st>>>(g);
-    return cudaGetLastError();
+    return launch_k(kern, grid, dim3(WM * WN * 32), (size_t)smem, st, g);
 }
 
 template <int EPI>

@@ -103,6 +103,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     const int KB = (g.K + BK - 1) / BK;
 
+    pdl_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(tmem_full, 1);
@@ -116,6 +117,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                                      // prologue above overlapped the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
@@ -263,8 +265,7 @@ cudaError_t launch_one(const GemmArgs& g, cudaStream_t st) {
         tb_lo = tb_hi;
     }
     dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
-    kern<<<grid, 192, C::SMEM, st>>>(ta_hi, ta_lo, tb_hi, tb_lo, g);
-    return cudaGetLastError();
+    return launch_k(kern, grid, dim3(192), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
 }
 
 template <int EPI>

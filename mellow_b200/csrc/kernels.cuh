@@ -45,6 +45,7 @@ struct DecodeAttnArgs {
     const float* q;                 // [B,576]
     const void* kc; const void* vc; // layer caches [B][3][t_max][64]
     int kv_bf16, B, t_max, nsplit;
+    int tps;                           // key tiles (64 keys) owned by each split: ceil(ceil(t_max/64)/nsplit)
     int ctx_base; const int* d_step;   // ctx = ctx_base + *d_step  (keys 0..ctx-1)
     float* part_acc; float* part_ml;   // [B][9][nsplit][64], [B][9][nsplit][2]
     bf16* out_hi; bf16* out_lo;        // [B,576]

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(144) prefix_kernel(const float* __restrict__ r
                                                      const float* __restrict__ embed, int B, float* __restrict__ prefix) {
     const int p = blockIdx.x, b = blockIdx.y;
     const int c4 = threadIdx.x;                                   // 144 float4 = 576 floats
+    pdl_trigger();
+    pdl_wait();
     float4 v;
     if (p < 2 * (kAudioSlots + 1)) {
         const int which = p / (kAudioSlots + 1);                  // 0: audio1, 1: audio2
@@ -59,6 +61,8 @@ __global__ void __launch_bounds__(64) prefill_attention_kernel(const float* __re
     const T* vb = vc + ((size_t)b * kKvHeads + kvh) * t_max * kHeadDim;
     float qr[kHeadDim], acc[kHeadDim];
     const float* qp = q + ((size_t)b * S + (active ? r : 0)) * kHidden + h * kHeadDim;
+    pdl_trigger();
+    pdl_wait();
 #pragma unroll
     for (int d = 0; d < kHeadDim; d += 4) {
         const float4 a = *reinterpret_cast<const float4*>(qp + d);
@@ -140,27 +144,37 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
     constexpr int NCH = kHeadDim / E;             // chunks per row
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int ctx = a.ctx_base + (a.d_step ? *a.d_step : 0);
-    const int ntiles = (ctx + 63) >> 6;
-    const int tps = (ntiles + a.nsplit - 1) / a.nsplit;
-    const int t_begin = split * tps, t_end = min(ntiles, t_begin + tps);
+    // Tile ownership is static (independent of the step counter): split s owns tiles [s*tps, (s+1)*tps).
+    const int t_begin = split * a.tps;
     const T* kb = reinterpret_cast<const T*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * kHeadDim;
     const T* vb = reinterpret_cast<const T*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * kHeadDim;
 
-    auto load_tile = [&](int buf, int tile) {
+    auto load_tile = [&](int buf, int tile, int ctx_limit) {
         const int key0 = tile << 6;
         for (int c = tid; c < 64 * NCH; c += 128) {
             const int j = c / NCH, ch = c - j * NCH;
             const int key = key0 + j;
-            const bool ok = key < ctx;
+            const bool ok = key < ctx_limit;
             const size_t off = (size_t)(ok ? key : 0) * kHeadDim + ch * E;
             cp_async16(&sm.k[buf][j][ch * E], kb + off, ok);
             cp_async16(&sm.v[buf][j][ch * E], vb + off, ok);
         }
     };
-    if (t_begin < t_end) load_tile(0, t_begin);
+    // PDL: tiles that lie entirely inside the prefill prefix (keys < ctx_base - 1) are immutable history for every
+    // decode step, so they are requested before waiting on the predecessor.  Nothing that the predecessor chain
+    // writes (the step counter, the newest K/V row, q) is touched before pdl_wait().
+    pdl_trigger();
+    const bool early0 = (t_begin + 1) * 64 < a.ctx_base;
+    const bool early1 = a.tps > 1 && (t_begin + 2) * 64 < a.ctx_base;
+    if (early0) load_tile(0, t_begin, a.ctx_base);
+    if (early1) load_tile(1, t_begin + 1, a.ctx_base);
+    pdl_wait();
+    const int ctx = a.ctx_base + (a.d_step ? *a.d_step : 0);
+    const int ntiles = (ctx + 63) >> 6;
+    const int t_end = min(ntiles, t_begin + a.tps);
+    if (!early0 && t_begin < t_end) load_tile(0, t_begin, ctx);
     cp_async_commit();
-    if (t_begin + 1 < t_end) load_tile(1, t_begin + 1);
+    if (!early1 && t_begin + 1 < t_end) load_tile(1, t_begin + 1, ctx);
     cp_async_commit();
 
     // score role: thread = (key j, half); each half owns every other 16 B chunk of the key row.  The matching
@@ -254,7 +268,7 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
             }
         }
         __syncthreads();                                             // tile buffer and sc are reused
-        if (t + 2 < t_end) load_tile(buf, t + 2);
+        if (t + 2 < t_end) load_tile(buf, t + 2, ctx);
         cp_async_commit();
     }
     cp_async_wait<0>();
@@ -272,6 +286,8 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
 __global__ void __launch_bounds__(64) decode_combine_kernel(const DecodeAttnArgs a) {
     const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
     const size_t base = ((size_t)b * kHeads + h) * a.nsplit;
+    pdl_trigger();
+    pdl_wait();
     float m = -INFINITY;
     for (int s = 0; s < a.nsplit; ++s) m = fmaxf(m, a.part_ml[(base + s) * 2]);
     float num = 0.f, den = 0.f;
@@ -296,6 +312,8 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
     __shared__ int sidx[32];
     __shared__ int stoken;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    pdl_trigger();
+    pdl_wait();
     const int step = *a.d_step;
     const float* lg = a.logits + (size_t)b * kVocab;
     const float tdiv = a.temperature > 0.f ? a.temperature : 1.0f;
@@ -349,8 +367,12 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(float* __restrict__ x,
     if (row >= M) return;
     float v[PER], p[S > 0 ? S : 1][PER], wv[PER];
     float* xr = x + (size_t)row * kHidden;
+    pdl_trigger();
 #pragma unroll
-    for (int j = 0; j < PER; ++j) { v[j] = xr[lane + 32 * j]; wv[j] = w[lane + 32 * j]; }
+    for (int j = 0; j < PER; ++j) wv[j] = w[lane + 32 * j];        // weights do not depend on the predecessor
+    pdl_wait();
+#pragma unroll
+    for (int j = 0; j < PER; ++j) v[j] = xr[lane + 32 * j];
 #pragma unroll
     for (int s = 0; s < S; ++s)                                    // all loads in flight before the first add
 #pragma unroll
@@ -374,6 +396,8 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(float* __restrict__ x,
 // step += 1; records the first step count at which every row has emitted eos (wrapper.py:247-249)
 __global__ void step_advance_kernel(int* d_step, const int* done, int B, int* d_stop_step) {
     __shared__ int all;
+    pdl_trigger();
+    pdl_wait();
     if (threadIdx.x == 0) all = 1;
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x)
@@ -391,18 +415,15 @@ __global__ void step_advance_kernel(int* d_step, const int* done, int B, int* d_
 cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embed, int B, float* prefix,
                           cudaStream_t st) {
     dim3 grid(kPrefix, B);
-    prefix_kernel<<<grid, 144, 0, st>>>(rows33, ids, embed, B, prefix);
-    return cudaGetLastError();
+    return launch_k(prefix_kernel, grid, dim3(144), 0, st, rows33, ids, embed, B, prefix);
 }
 
 cudaError_t launch_prefill_attention(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S,
                                      int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st) {
     dim3 grid((S + 63) / 64, kHeads, B);
     if (kv_bf16)
-        prefill_attention_kernel<bf16><<<grid, 64, 0, st>>>(q, (const bf16*)kc, (const bf16*)vc, S, t_max, out_hi, out_lo);
-    else
-        prefill_attention_kernel<float><<<grid, 64, 0, st>>>(q, (const float*)kc, (const float*)vc, S, t_max, out_hi, out_lo);
-    return cudaGetLastError();
+        return launch_k(prefill_attention_kernel<bf16>, grid, dim3(64), 0, st, q, (const bf16*)kc, (const bf16*)vc, S, t_max, out_hi, out_lo);
+    return launch_k(prefill_attention_kernel<float>, grid, dim3(64), 0, st, q, (const float*)kc, (const float*)vc, S, t_max, out_hi, out_lo);
 }
 
 cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
@@ -417,35 +438,29 @@ cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    if (a.kv_bf16) decode_attention_kernel<bf16><<<grid, 128, sizeof(DecodeSmem<bf16>), st>>>(a);
-    else decode_attention_kernel<float><<<grid, 128, sizeof(DecodeSmem<float>), st>>>(a);
-    cudaError_t e = cudaGetLastError();
+    cudaError_t e = a.kv_bf16 ? launch_k(decode_attention_kernel<bf16>, grid, dim3(128), sizeof(DecodeSmem<bf16>), st, a)
+                              : launch_k(decode_attention_kernel<float>, grid, dim3(128), sizeof(DecodeSmem<float>), st, a);
     if (e != cudaSuccess) return e;
-    dim3 g2(kHeads, a.B);
-    decode_combine_kernel<<<g2, 64, 0, st>>>(a);
-    return cudaGetLastError();
+    return launch_k(decode_combine_kernel, dim3(kHeads, a.B), dim3(64), 0, st, a);
 }
 
 cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, int M, const float* w, bf16* hi, bf16* lo,
                                cudaStream_t st) {
     const int grid = (M + 3) / 4;
     switch (n_partial) {
-        case 0: add_rmsnorm_kernel<0><<<grid, 128, 0, st>>>(x, partial, M, w, hi, lo); break;
-        case 3: add_rmsnorm_kernel<3><<<grid, 128, 0, st>>>(x, partial, M, w, hi, lo); break;
-        case 4: add_rmsnorm_kernel<4><<<grid, 128, 0, st>>>(x, partial, M, w, hi, lo); break;
+        case 0: return launch_k(add_rmsnorm_kernel<0>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo);
+        case 3: return launch_k(add_rmsnorm_kernel<3>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo);
+        case 4: return launch_k(add_rmsnorm_kernel<4>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo);
         default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st) {
-    sample_kernel<<<a.B, 1024, 0, st>>>(a);
-    return cudaGetLastError();
+    return launch_k(sample_kernel, dim3(a.B), dim3(1024), 0, st, a);
 }
 
 cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st) {
-    step_advance_kernel<<<1, 128, 0, st>>>(d_step, done, B, d_stop_step);
-    return cudaGetLastError();
+    return launch_k(step_advance_kernel, dim3(1), dim3(128), 0, st, d_step, done, B, d_stop_step);
 }
 
 }  // namespace mb

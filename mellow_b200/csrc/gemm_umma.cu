@@ -81,9 +81,12 @@ template <int BN, bool SPLIT>
 struct Cfg {
     static constexpr uint32_t B_BYTES = BN * BK * 2;
     static constexpr uint32_t STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
-    static constexpr int STAGES = SPLIT ? 3 : 5;
-    static constexpr uint32_t TMEM_COLS = 128;
+    static constexpr int STAGES_FIT = (int)((225u * 1024u - 1280u) / STAGE_BYTES);
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+    static constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(STAGES >= 2, "tile does not fit");
+    static_assert(4 * 32 * 65 * 4 <= STAGES * STAGE_BYTES, "epilogue staging tile must fit in the drained ring");
 };
 
 template <int BN, int EPI, bool SPLIT>
@@ -101,7 +104,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const int KB = (g.K + BK - 1) / BK;
+    // split-K: blockIdx.z owns a contiguous range of 64-wide k-blocks and writes a raw fp32 partial tile
+    const int kb_all = (g.K + BK - 1) / BK;
+    const int nsplit = g.split_k > 1 ? g.split_k : 1;
+    const int kb_begin = (int)(((long long)kb_all * blockIdx.z) / nsplit);
+    const int KB = (int)(((long long)kb_all * (blockIdx.z + 1)) / nsplit) - kb_begin;
 
     pdl_trigger();
     if (threadIdx.x == 0) {
@@ -117,21 +124,35 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_wait();                                                      // prologue above overlapped the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < KB; ++kb) {
+            // PDL: the weight (B) tiles of the first ring slots never depend on the preceding kernel, so they are
+            // requested before the dependency wait; the activation (A) tiles of those slots follow after it.
+            const int npre = KB < C::STAGES ? KB : C::STAGES;
+            for (int kb = 0; kb < npre; ++kb) {
+                unsigned char* st = smem + (size_t)kb * C::STAGE_BYTES;
+                mbar_expect_tx(&full[kb], C::STAGE_BYTES);
+                tma_load_2d(st + A_BYTES, &tm_b_hi, &full[kb], (kb_begin + kb) * BK, n0);
+                if (SPLIT) tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, &full[kb], (kb_begin + kb) * BK, n0);
+            }
+            pdl_wait();
+            for (int kb = 0; kb < npre; ++kb) {
+                unsigned char* st = smem + (size_t)kb * C::STAGE_BYTES;
+                tma_load_2d(st, &tm_a_hi, &full[kb], (kb_begin + kb) * BK, m0);
+                if (SPLIT) tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[kb], (kb_begin + kb) * BK, m0);
+            }
+            for (int kb = npre; kb < KB; ++kb) {
                 const int s = kb % C::STAGES;
                 const uint32_t ph = (kb / C::STAGES) & 1;
                 mbar_wait(&empty[s], ph ^ 1);
                 unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
                 mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                tma_load_2d(st, &tm_a_hi, &full[s], kb * BK, m0);
-                tma_load_2d(st + A_BYTES, &tm_b_hi, &full[s], kb * BK, n0);
+                tma_load_2d(st, &tm_a_hi, &full[s], (kb_begin + kb) * BK, m0);
+                tma_load_2d(st + A_BYTES, &tm_b_hi, &full[s], (kb_begin + kb) * BK, n0);
                 if (SPLIT) {
-                    tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[s], kb * BK, m0);
-                    tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, &full[s], kb * BK, n0);
+                    tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[s], (kb_begin + kb) * BK, m0);
+                    tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, &full[s], (kb_begin + kb) * BK, n0);
                 }
             }
         }
@@ -168,8 +189,31 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
         constexpr int LDT = 65;
         float* stage_t = reinterpret_cast<float*>(smem) + (size_t)q * 32 * LDT;
+        pdl_wait();                                                  // residual reads / output writes depend on the predecessor
         mbar_wait(tmem_full, 0);                                     // all MMAs retired: accumulator ready, smem ring idle
         tc_fence_after();
+        if (BN <= 32) {
+            // decode-sized tiles: 16-32 columns per row.  Every thread finishes its own row straight from registers
+            // (128 rows in parallel); the staged path below would leave 24 of 32 lanes idle.
+            const int m = m0 + q * 32 + lane;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (m < g.M) {
+                    if (nsplit > 1) {
+                        float* pz = g.partial + (size_t)blockIdx.z * g.M * g.N + (size_t)m * g.N + n0 + c0;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            if (n0 + c0 + j < g.N) *reinterpret_cast<float4*>(pz + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2)
+                            if (n0 + c0 + j < g.N) epilogue_pair<EPI>(g, m, n0 + c0 + j, v[j], v[j + 1]);
+                    }
+                }
+            }
+        } else
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 64) {
 #pragma unroll
@@ -183,7 +227,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             }
             __syncwarp();
             const int n = n0 + c0 + 2 * lane;
-            if (c0 + 2 * lane < BN && n < g.N) {
+            if (nsplit > 1) {
+                if (c0 + 2 * lane < BN && n < g.N) {
+                    float* pz = g.partial + (size_t)blockIdx.z * g.M * g.N;
+                    for (int r = 0; r < 32; ++r) {
+                        const int m = m0 + q * 32 + r;
+                        if (m >= g.M) break;
+                        *reinterpret_cast<float2*>(pz + (size_t)m * g.N + n) =
+                            make_float2(stage_t[r * LDT + 2 * lane], stage_t[r * LDT + 2 * lane + 1]);
+                    }
+                }
+            } else if (c0 + 2 * lane < BN && n < g.N) {
 #pragma unroll 1
                 for (int rb = 0; rb < 32; rb += 8) {
                     const int mb = m0 + q * 32 + rb;
@@ -264,13 +318,18 @@ cudaError_t launch_one(const GemmArgs& g, cudaStream_t st) {
         ta_lo = ta_hi;
         tb_lo = tb_hi;
     }
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.split_k > 1 ? g.split_k : 1);
     return launch_k(kern, grid, dim3(192), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
 }
 
 template <int EPI>
 cudaError_t launch_epi(const GemmArgs& g, cudaStream_t st) {
     const bool split = g.passes == 3;
+    if (g.M <= 128 && g.N <= 4096) {
+        // decode-sized (one 128-row UMMA tile): narrow N tiles (x split-K) so 60-110 SMs stream the weights
+        if (g.N >= 2048) return split ? launch_one<32, EPI, true>(g, st) : launch_one<32, EPI, false>(g, st);
+        return split ? launch_one<16, EPI, true>(g, st) : launch_one<16, EPI, false>(g, st);
+    }
     const bool bn96 = (g.N % 128 != 0) && (g.N % 96 == 0);
     if (bn96) return split ? launch_one<96, EPI, true>(g, st) : launch_one<96, EPI, false>(g, st);
     return split ? launch_one<128, EPI, true>(g, st) : launch_one<128, EPI, false>(g, st);
@@ -282,8 +341,8 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 cudaError_t launch_gemm_umma(const GemmArgs& g, int epi, cudaStream_t st, bool* handled) {
     *handled = false;
-    // the tcgen05 tiles are 128 rows tall: decode-sized problems (M <= 128) stay on the skinny split-K kernel
-    if (g.M <= 128 || g.split_k > 1 || g.K < BK || (g.K % 8) != 0 || (g.lda % 8) != 0 || (g.ldw % 8) != 0) return cudaSuccess;
+    if (g.M < 1 || g.K < BK || (g.K % 8) != 0 || (g.lda % 8) != 0 || (g.ldw % 8) != 0) return cudaSuccess;
+    if (g.split_k > 1 && (epi != EPI_GENERIC || !g.partial || (g.N & 1))) return cudaErrorInvalidValue;
     if (!aligned16(g.A_hi) || !aligned16(g.W_hi) || (g.passes == 3 && (!aligned16(g.A_lo) || !aligned16(g.W_lo)))) return cudaSuccess;
     if (!encode_fn()) return cudaSuccess;
     cudaError_t e;

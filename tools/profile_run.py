@@ -10,7 +10,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--max-len", type=int, default=4)
 ap.add_argument("--policy", default="split")
-ap.add_argument("--engine", type=int, default=0)
+ap.add_argument("--engine", type=int, default=1)
 ap.add_argument("--phase", default="generate", choices=["generate", "decode", "prefill"])
 args = ap.parse_args()
 B = args.batch

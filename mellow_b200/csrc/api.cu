@@ -450,9 +450,15 @@ int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_
     if (decode) {
         MB_TRY(run_decode_attention(h, l, B, st));
     } else {
-        MB_CK(h, launch_prefill_attention(h->q, kv_layer(h, h->kcache, l), kv_layer(h, h->vcache, l),
-                                          h->policy == kPolicyFast, B, rows_per_seq, h->t_max, h->la_hi,
-                                          lo_of(h, h->la_lo), st));
+        static const bool fp32_attn = getenv("MB_ATTN_FP32") != nullptr;      // CUDA-core fp32 kernel, kept for A/B checks
+        if (fp32_attn)
+            MB_CK(h, launch_prefill_attention(h->q, kv_layer(h, h->kcache, l), kv_layer(h, h->vcache, l),
+                                              h->policy == kPolicyFast, B, rows_per_seq, h->t_max, h->la_hi,
+                                              lo_of(h, h->la_lo), st));
+        else
+            MB_CK(h, launch_prefill_attention_mma(h->q, kv_layer(h, h->kcache, l), kv_layer(h, h->vcache, l),
+                                                  h->policy == kPolicyFast, B, rows_per_seq, h->t_max, h->la_hi,
+                                                  lo_of(h, h->la_lo), st));
         h->launches++;
     }
     {

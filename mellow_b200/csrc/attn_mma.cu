@@ -1,0 +1,223 @@
+// Causal prefill attention on the tensor cores (SmolLM2: 9 query heads, 3 kv heads, head_dim 64; reference path:
+// transformers modeling_llama.py:276-285 called cache-less from mellow/wrapper.py:217).
+//
+// Flash-style: CTA = 64 query rows of one (batch, head), 4 warps x 16 rows; K/V are streamed in 64-key tiles from the
+// KV cache the QKV GEMM epilogue just wrote, converted to bf16 hi/lo planes in shared memory; S = Q K^T and O += P V
+// are mma.sync.m16n8k16 with the same 3-pass operand split as the GEMMs (hi*hi + hi*lo + lo*hi, fp32 accumulate), the
+// online softmax runs in fp32 registers.  q/k head dims are pair-interleaved (gemm.cuh), which leaves q.k unchanged.
+#include "kernels.cuh"
+
+namespace mb {
+
+namespace {
+
+constexpr int TQ = 64, TK = 64, LDS = kHeadDim + 8;      // 144-byte rows: conflict-free ldmatrix
+
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const bf16* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, const bf16* p) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void pack_split(float x, float y, uint32_t& hi, uint32_t& lo) {
+    bf16 xh, xl, yh, yl;
+    split_bf16(x, xh, xl);
+    split_bf16(y, yh, yl);
+    __nv_bfloat162 h2, l2;
+    h2.x = xh; h2.y = yh;
+    l2.x = xl; l2.y = yl;
+    hi = *reinterpret_cast<uint32_t*>(&h2);
+    lo = *reinterpret_cast<uint32_t*>(&l2);
+}
+
+struct AttnSmem {
+    bf16 kh[TK][LDS], kl[TK][LDS], vh[TK][LDS], vl[TK][LDS];
+};
+
+// stage a [64 keys][64 dims] tile of the cache as bf16 hi/lo planes
+template <bool SPLIT>
+__device__ __forceinline__ void stage_tile(const float* src, int key0, int S, bf16 (*hi)[LDS], bf16 (*lo)[LDS], int tid) {
+    for (int e = tid; e < TK * (kHeadDim / 4); e += 128) {
+        const int j = e >> 4, c = (e & 15) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (key0 + j < S) v = *reinterpret_cast<const float4*>(src + (size_t)(key0 + j) * kHeadDim + c);
+        uint32_t h0, l0, h1, l1;
+        pack_split(v.x, v.y, h0, l0);
+        pack_split(v.z, v.w, h1, l1);
+        *reinterpret_cast<uint2*>(&hi[j][c]) = make_uint2(h0, h1);
+        if (SPLIT) *reinterpret_cast<uint2*>(&lo[j][c]) = make_uint2(l0, l1);
+    }
+}
+template <bool SPLIT>
+__device__ __forceinline__ void stage_tile(const bf16* src, int key0, int S, bf16 (*hi)[LDS], bf16 (*lo)[LDS], int tid) {
+    for (int e = tid; e < TK * (kHeadDim / 8); e += 128) {
+        const int j = e >> 3, c = (e & 7) * 8;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (key0 + j < S) v = *reinterpret_cast<const uint4*>(src + (size_t)(key0 + j) * kHeadDim + c);
+        *reinterpret_cast<uint4*>(&hi[j][c]) = v;
+    }
+}
+
+template <typename T, bool SPLIT>
+__global__ void __launch_bounds__(128) prefill_attention_mma_kernel(const float* __restrict__ q, const T* __restrict__ kc,
+                                                                    const T* __restrict__ vc, int S, int t_max,
+                                                                    bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
+    __shared__ __align__(16) AttnSmem sm;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int kvh = h / (kHeads / kKvHeads);
+    const T* kb = kc + ((size_t)b * kKvHeads + kvh) * t_max * kHeadDim;
+    const T* vb = vc + ((size_t)b * kKvHeads + kvh) * t_max * kHeadDim;
+    const int row0 = qt * TQ + warp * 16 + g, row1 = row0 + 8;
+    pdl_trigger();
+    pdl_wait();
+
+    // Q fragments (scaled by head_dim^-0.5 = 2^-3, exact) as bf16 hi/lo A operands for the 4 k16 steps
+    uint32_t qh[4][4], ql[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int row = (r & 1) ? row1 : row0;
+            const int col = ks * 16 + 2 * t + ((r & 2) ? 8 : 0);
+            float2 v = make_float2(0.f, 0.f);
+            if (row < S) v = *reinterpret_cast<const float2*>(q + ((size_t)b * S + row) * kHidden + h * kHeadDim + col);
+            pack_split(v.x * 0.125f, v.y * 0.125f, qh[ks][r], ql[ks][r]);
+        }
+    }
+    float o[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    const int n_tiles = min(qt + 1, (S + TK - 1) / TK);
+    for (int kt = 0; kt < n_tiles; ++kt) {
+        const int k0 = kt * TK;
+        __syncthreads();                                             // previous tile fully consumed
+        stage_tile<SPLIT>(kb, k0, S, sm.kh, sm.kl, tid);
+        stage_tile<SPLIT>(vb, k0, S, sm.vh, sm.vl, tid);
+        __syncthreads();
+
+        // S = (Q/8) K^T : 16 x 64 per warp
+        float s[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const int r = j * 8 + (lane & 7) + (lane >> 4) * 8;
+                const int c = ks * 16 + ((lane >> 3) & 1) * 8;
+                uint32_t bh[4], bl[4];
+                ldsm_x4(bh, &sm.kh[r][c]);
+                if (SPLIT) {
+                    ldsm_x4(bl, &sm.kl[r][c]);
+                    mma16816(s[j], ql[ks], bh[0], bh[1]);
+                    mma16816(s[j + 1], ql[ks], bh[2], bh[3]);
+                    mma16816(s[j], qh[ks], bl[0], bl[1]);
+                    mma16816(s[j + 1], qh[ks], bl[2], bl[3]);
+                }
+                mma16816(s[j], qh[ks], bh[0], bh[1]);
+                mma16816(s[j + 1], qh[ks], bh[2], bh[3]);
+            }
+        }
+        if (kt == qt) {                                              // diagonal tile: causal mask (key > row)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int key = k0 + j * 8 + 2 * t;
+                if (key > row0) s[j][0] = -INFINITY;
+                if (key + 1 > row0) s[j][1] = -INFINITY;
+                if (key > row1) s[j][2] = -INFINITY;
+                if (key + 1 > row1) s[j][3] = -INFINITY;
+            }
+        }
+        // online softmax (rows row0 / row1 live in the 4 lanes of a quad)
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+            mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+        }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);      // finite: key k0 <= row for every row of the tile
+        const float a0 = expf(m0 - mn0), a1 = expf(m1 - mn1);
+        m0 = mn0; m1 = mn1;
+        float ls0 = 0.f, ls1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            s[j][0] = expf(s[j][0] - mn0); s[j][1] = expf(s[j][1] - mn0);
+            s[j][2] = expf(s[j][2] - mn1); s[j][3] = expf(s[j][3] - mn1);
+            ls0 += s[j][0] + s[j][1];
+            ls1 += s[j][2] + s[j][3];
+            o[j][0] *= a0; o[j][1] *= a0; o[j][2] *= a1; o[j][3] *= a1;
+        }
+        l0 = l0 * a0 + ls0;
+        l1 = l1 * a1 + ls1;
+
+        // O += P V : P (16 x 64 keys) re-used from the score accumulators as A fragments
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t ph[4], pl[4];
+            pack_split(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+            pack_split(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+            pack_split(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+            pack_split(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+            for (int jd = 0; jd < 8; jd += 2) {
+                const int blk = lane >> 3;
+                const int r = kk * 16 + (blk & 1) * 8 + (lane & 7);
+                const int c = (jd + (blk >> 1)) * 8;
+                uint32_t bh[4], bl[4];
+                ldsm_x4_t(bh, &sm.vh[r][c]);
+                if (SPLIT) {
+                    ldsm_x4_t(bl, &sm.vl[r][c]);
+                    mma16816(o[jd], pl, bh[0], bh[1]);
+                    mma16816(o[jd + 1], pl, bh[2], bh[3]);
+                    mma16816(o[jd], ph, bl[0], bl[1]);
+                    mma16816(o[jd + 1], ph, bl[2], bl[3]);
+                }
+                mma16816(o[jd], ph, bh[0], bh[1]);
+                mma16816(o[jd + 1], ph, bh[2], bh[3]);
+            }
+        }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+    for (int jd = 0; jd < 8; ++jd) {
+        const int col = h * kHeadDim + jd * 8 + 2 * t;
+        if (row0 < S) store_planes2(out_hi, out_lo, ((size_t)b * S + row0) * kHidden + col, o[jd][0] * i0, o[jd][1] * i0);
+        if (row1 < S) store_planes2(out_hi, out_lo, ((size_t)b * S + row1) * kHidden + col, o[jd][2] * i1, o[jd][3] * i1);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S,
+                                         int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st) {
+    dim3 grid((S + TQ - 1) / TQ, kHeads, B);
+    if (kv_bf16)
+        return launch_k(prefill_attention_mma_kernel<bf16, false>, grid, dim3(128), 0, st, q, (const bf16*)kc,
+                        (const bf16*)vc, S, t_max, out_hi, out_lo);
+    return launch_k(prefill_attention_mma_kernel<float, true>, grid, dim3(128), 0, st, q, (const float*)kc,
+                    (const float*)vc, S, t_max, out_hi, out_lo);
+}
+
+}  // namespace mb

@@ -41,6 +41,9 @@ cudaError_t launch_split_planes(const float* x, size_t n, bf16* hi, bf16* lo, cu
 cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embed, int B, float* prefix, cudaStream_t st);
 cudaError_t launch_prefill_attention(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S, int t_max,
                                      bf16* out_hi, bf16* out_lo, cudaStream_t st);
+// tensor-core (mma.sync, split operands) version of the same attention (attn_mma.cu)
+cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S,
+                                         int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st);
 struct DecodeAttnArgs {
     const float* q;                 // [B,576]
     const void* kc; const void* vc; // layer caches [B][3][t_max][64]

@@ -31,8 +31,30 @@ struct GemmArgs {
     int t_max; int kv_bf16;
 };
 
-// (m, n) and (m, n+1); n is even; caller guarantees m < M and n < N.  r0/r1: residual values (EPI_GENERIC), already
-// loaded by the caller so that engines can batch those loads ahead of the dependent stores.
+// Per-(row, column pair) auxiliary operands an epilogue needs from global memory: the residual pair (EPI_GENERIC) or
+// the RoPE (cos, sin) of that row's position (EPI_QKV_ROPE).  Engines load them ahead of time / in batches so the
+// epilogue is not a chain of exposed memory latencies.
+template <int EPI>
+__device__ __forceinline__ void load_aux_pair(const GemmArgs& g, int m, int n, float& r0, float& r1) {
+    r0 = 0.f; r1 = 0.f;
+    if (EPI == EPI_GENERIC) {
+        if (g.residual) {
+            const float* r = g.residual + (size_t)m * g.ldr + n;
+            r0 = r[0];
+            if (n + 1 < g.N) r1 = r[1];
+        }
+    } else if (EPI == EPI_QKV_ROPE) {
+        if (n < kHidden + kKvHeads * kHeadDim) {
+            const int b = m / g.rows_per_seq;
+            const int pos = g.pos_base + (g.d_pos ? *g.d_pos : 0) + (m - b * g.rows_per_seq);
+            const int i = (n & (kHeadDim - 1)) >> 1;
+            r0 = __ldg(g.rope_cos + pos * 32 + i);
+            r1 = __ldg(g.rope_sin + pos * 32 + i);
+        }
+    }
+}
+
+// (m, n) and (m, n+1); n is even; caller guarantees m < M and n < N.  (r0, r1) come from load_aux_pair.
 template <int EPI>
 __device__ __forceinline__ void epilogue_pair_r(const GemmArgs& g, int m, int n, float v0, float v1, float r0, float r1) {
     if (EPI == EPI_GENERIC) {
@@ -59,12 +81,10 @@ __device__ __forceinline__ void epilogue_pair_r(const GemmArgs& g, int m, int n,
         const int b = m / g.rows_per_seq;
         const int s = m - b * g.rows_per_seq;
         const int pos = g.pos_base + (g.d_pos ? *g.d_pos : 0) + s;
-        if (n < kHidden + kKvHeads * kHeadDim) {
-            const int i = (n & (kHeadDim - 1)) >> 1;
-            const float c = __ldg(g.rope_cos + pos * 32 + i), sn = __ldg(g.rope_sin + pos * 32 + i);
-            const float r0 = v0 * c - v1 * sn;
-            const float r1 = v1 * c + v0 * sn;
-            v0 = r0; v1 = r1;
+        if (n < kHidden + kKvHeads * kHeadDim) {                   // q and k columns: rotate-half pair (v0, v1)
+            const float x0 = v0 * r0 - v1 * r1;
+            const float x1 = v1 * r0 + v0 * r1;
+            v0 = x0; v1 = x1;
         }
         if (n < kHidden) {
             *reinterpret_cast<float2*>(g.q_out + (size_t)m * kHidden + n) = make_float2(v0, v1);
@@ -82,20 +102,131 @@ __device__ __forceinline__ void epilogue_pair_r(const GemmArgs& g, int m, int n,
 }
 
 template <int EPI>
-__device__ __forceinline__ void load_residual_pair(const GemmArgs& g, int m, int n, float& r0, float& r1) {
-    r0 = 0.f; r1 = 0.f;
-    if (EPI == EPI_GENERIC && g.residual) {
-        const float* r = g.residual + (size_t)m * g.ldr + n;
-        r0 = r[0];
-        if (n + 1 < g.N) r1 = r[1];
+__device__ __forceinline__ void epilogue_pair(const GemmArgs& g, int m, int n, float v0, float v1) {
+    float r0, r1;
+    load_aux_pair<EPI>(g, m, n, r0, r1);
+    epilogue_pair_r<EPI>(g, m, n, v0, v1, r0, r1);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Row-vector epilogue for engines whose threads own whole accumulator rows (tcgen05.ld gives one row per thread):
+// 16 consecutive columns n..n+15 of row m (n % 16 == 0) are finished with 16-byte loads / stores.  Few instructions
+// per element matter more here than perfect coalescing: the epilogue warps run one per scheduler.
+__device__ __forceinline__ void ld4(const float* p, float* d) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+}
+__device__ __forceinline__ void ldg4(const float* p, float* d) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    d[0] = t.x; d[1] = t.y; d[2] = t.z; d[3] = t.w;
+}
+__device__ __forceinline__ void st4(float* p, const float* s) {
+    *reinterpret_cast<float4*>(p) = make_float4(s[0], s[1], s[2], s[3]);
+}
+// 8 floats -> 8 bf16 hi (+ 8 bf16 lo) as one 16-byte store per plane
+__device__ __forceinline__ void store_planes8(bf16* hi, bf16* lo, size_t idx, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        bf16 ah, al, bh, bl;
+        split_bf16(v[2 * j], ah, al);
+        split_bf16(v[2 * j + 1], bh, bl);
+        __nv_bfloat162 h2, l2;
+        h2.x = ah; h2.y = bh; l2.x = al; l2.y = bl;
+        h[j] = *reinterpret_cast<uint32_t*>(&h2);
+        l[j] = *reinterpret_cast<uint32_t*>(&l2);
     }
+    *reinterpret_cast<uint4*>(hi + idx) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (lo) *reinterpret_cast<uint4*>(lo + idx) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 template <int EPI>
-__device__ __forceinline__ void epilogue_pair(const GemmArgs& g, int m, int n, float v0, float v1) {
-    float r0, r1;
-    load_residual_pair<EPI>(g, m, n, r0, r1);
-    epilogue_pair_r<EPI>(g, m, n, v0, v1, r0, r1);
+__device__ __forceinline__ void epilogue_row16(const GemmArgs& g, int m, int n, float* v) {
+    bool vec = (n + 16 <= g.N);
+    if (EPI == EPI_GENERIC)
+        vec = vec && (!g.out_f32 || (g.ldo & 3) == 0) && (!g.residual || (g.ldr & 3) == 0) && (!g.out_hi || (g.ldp & 7) == 0);
+    if (!vec) {                                                    // ragged tail / odd leading dimension
+#pragma unroll
+        for (int j = 0; j < 16; j += 2)
+            if (n + j < g.N) epilogue_pair<EPI>(g, m, n + j, v[j], v[j + 1]);
+        return;
+    }
+    if (EPI == EPI_GENERIC) {
+        if (g.bias) {
+            float bq[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) ldg4(g.bias + n + j, bq + j);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += bq[j];
+        }
+        if (g.act == ACT_GELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
+        } else if (g.act == ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = sigmoidf_(v[j]);
+        }
+        if (g.residual) {
+            float r[16];
+            const float* rp = g.residual + (size_t)m * g.ldr + n;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) ld4(rp + j, r + j);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += r[j];
+        }
+        if (g.out_f32) {
+            float* o = g.out_f32 + (size_t)m * g.ldo + n;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) st4(o + j, v + j);
+        }
+        if (g.out_hi) {
+            const size_t idx = (size_t)m * g.ldp + n;
+            store_planes8(g.out_hi, g.out_lo, idx, v);
+            store_planes8(g.out_hi, g.out_lo, idx + 8, v + 8);
+        }
+    } else if (EPI == EPI_SWIGLU) {
+        float hv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) hv[j] = siluf_(v[2 * j]) * v[2 * j + 1];
+        store_planes8(g.out_hi, g.out_lo, (size_t)m * g.ldp + (n >> 1), hv);
+    } else {
+        const int b = m / g.rows_per_seq;
+        const int s = m - b * g.rows_per_seq;
+        const int pos = g.pos_base + (g.d_pos ? *g.d_pos : 0) + s;
+        if (n < kHidden + kKvHeads * kHeadDim) {                   // 8 rotate-half pairs of one head
+            const int i0 = (n & (kHeadDim - 1)) >> 1;              // multiple of 8
+            float c[8], sn[8];
+            ldg4(g.rope_cos + pos * 32 + i0, c); ldg4(g.rope_cos + pos * 32 + i0 + 4, c + 4);
+            ldg4(g.rope_sin + pos * 32 + i0, sn); ldg4(g.rope_sin + pos * 32 + i0 + 4, sn + 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float x0 = v[2 * j] * c[j] - v[2 * j + 1] * sn[j];
+                const float x1 = v[2 * j + 1] * c[j] + v[2 * j] * sn[j];
+                v[2 * j] = x0; v[2 * j + 1] = x1;
+            }
+        }
+        if (n < kHidden) {
+            float* o = g.q_out + (size_t)m * kHidden + n;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) st4(o + j, v + j);
+        } else {
+            const int nn = n - kHidden;
+            const bool is_v = nn >= kKvHeads * kHeadDim;
+            const int c2 = is_v ? nn - kKvHeads * kHeadDim : nn;
+            const int kvh = c2 >> 6, dd = c2 & 63;
+            const size_t off = (((size_t)b * kKvHeads + kvh) * g.t_max + pos) * kHeadDim + dd;
+            void* base = is_v ? g.v_cache : g.k_cache;
+            if (g.kv_bf16) {
+                bf16* o = reinterpret_cast<bf16*>(base) + off;
+                store_planes8(o, nullptr, 0, v);
+                store_planes8(o, nullptr, 8, v + 8);
+            } else {
+                float* o = reinterpret_cast<float*>(base) + off;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) st4(o + j, v + j);
+            }
+        }
+    }
 }
 
 // Engine entry points (gemm_mma.cu, gemm_umma.cu)

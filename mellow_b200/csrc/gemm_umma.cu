@@ -12,6 +12,8 @@
 // (TMEM lane quadrant = warp % 4).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "gemm.cuh"
 
 namespace mb {
@@ -77,18 +79,43 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 template <int BN, bool SPLIT>
 struct Cfg {
     static constexpr uint32_t B_BYTES = BN * BK * 2;
     static constexpr uint32_t STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
-    static constexpr int STAGES_FIT = (int)((225u * 1024u - 1280u) / STAGE_BYTES);
+    static constexpr uint32_t STAGING_BYTES = 0;
+    static constexpr uint32_t BUDGET = 227u * 1024u - 1024u - 256u - STAGING_BYTES;
+    static constexpr int STAGES_FIT = (int)(BUDGET / STAGE_BYTES);
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
-    static constexpr uint32_t TMEM_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : 128);
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                             // two accumulators: MMA of tile i+1
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;   // overlaps epilogue of tile i
     static_assert(STAGES >= 2, "tile does not fit");
-    static_assert(4 * 32 * 65 * 4 <= STAGES * STAGE_BYTES, "epilogue staging tile must fit in the drained ring");
 };
 
+struct TileCoord { int m0, n0, z, kb_begin, KB; };
+
+template <int BN>
+__device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile, int tiles_n, int per_split, int nsplit) {
+    TileCoord t;
+    t.z = tile / per_split;
+    const int rem = tile - t.z * per_split;
+    const int mt = rem / tiles_n;
+    t.m0 = mt * BM;
+    t.n0 = (rem - mt * tiles_n) * BN;
+    const int kb_all = (g.K + BK - 1) / BK;
+    t.kb_begin = (int)(((long long)kb_all * t.z) / nsplit);
+    t.KB = (int)(((long long)kb_all * (t.z + 1)) / nsplit) - t.kb_begin;
+    return t;
+}
+
+// Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence (n fastest, so the CTAs that run
+// concurrently share A rows and the whole W in L2).  The smem ring runs continuously across tiles; the accumulator
+// is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
 template <int BN, int EPI, bool SPLIT>
 __global__ void __launch_bounds__(192, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
@@ -97,23 +124,24 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     using C = Cfg<BN, SPLIT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+    float* staging = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES);
     uint64_t* empty = full + C::STAGES;
-    uint64_t* tmem_full = empty + C::STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tfull = empty + C::STAGES;       // [2] accumulator ready
+    uint64_t* tempty = tfull + 2;              // [2] accumulator drained by the 4 epilogue warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    // split-K: blockIdx.z owns a contiguous range of 64-wide k-blocks and writes a raw fp32 partial tile
-    const int kb_all = (g.K + BK - 1) / BK;
     const int nsplit = g.split_k > 1 ? g.split_k : 1;
-    const int kb_begin = (int)(((long long)kb_all * blockIdx.z) / nsplit);
-    const int KB = (int)(((long long)kb_all * (blockIdx.z + 1)) / nsplit) - kb_begin;
+    const int tiles_n = (g.N + BN - 1) / BN;
+    const int per_split = tiles_n * ((g.M + BM - 1) / BM);
+    const int total = per_split * nsplit;
 
     pdl_trigger();
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
+        mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -127,32 +155,43 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            // PDL: the weight (B) tiles of the first ring slots never depend on the preceding kernel, so they are
-            // requested before the dependency wait; the activation (A) tiles of those slots follow after it.
-            const int npre = KB < C::STAGES ? KB : C::STAGES;
-            for (int kb = 0; kb < npre; ++kb) {
-                unsigned char* st = smem + (size_t)kb * C::STAGE_BYTES;
-                mbar_expect_tx(&full[kb], C::STAGE_BYTES);
-                tma_load_2d(st + A_BYTES, &tm_b_hi, &full[kb], (kb_begin + kb) * BK, n0);
-                if (SPLIT) tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, &full[kb], (kb_begin + kb) * BK, n0);
-            }
-            pdl_wait();
-            for (int kb = 0; kb < npre; ++kb) {
-                unsigned char* st = smem + (size_t)kb * C::STAGE_BYTES;
-                tma_load_2d(st, &tm_a_hi, &full[kb], (kb_begin + kb) * BK, m0);
-                if (SPLIT) tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[kb], (kb_begin + kb) * BK, m0);
-            }
-            for (int kb = npre; kb < KB; ++kb) {
-                const int s = kb % C::STAGES;
-                const uint32_t ph = (kb / C::STAGES) & 1;
-                mbar_wait(&empty[s], ph ^ 1);
-                unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
-                mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                tma_load_2d(st, &tm_a_hi, &full[s], (kb_begin + kb) * BK, m0);
-                tma_load_2d(st + A_BYTES, &tm_b_hi, &full[s], (kb_begin + kb) * BK, n0);
-                if (SPLIT) {
-                    tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[s], (kb_begin + kb) * BK, m0);
-                    tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, &full[s], (kb_begin + kb) * BK, n0);
+            int it = 0;
+            bool first = true;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const TileCoord t = tile_coord<BN>(g, tile, tiles_n, per_split, nsplit);
+                int kb = 0;
+                if (first) {
+                    // PDL: the weight (B) tiles of the first ring slots never depend on the preceding kernel, so they
+                    // are requested before the dependency wait; the activation (A) tiles of those slots follow it.
+                    first = false;
+                    const int npre = t.KB < C::STAGES ? t.KB : C::STAGES;
+                    for (int i = 0; i < npre; ++i) {
+                        unsigned char* st = smem + (size_t)i * C::STAGE_BYTES;
+                        mbar_expect_tx(&full[i], C::STAGE_BYTES);
+                        tma_load_2d(st + A_BYTES, &tm_b_hi, &full[i], (t.kb_begin + i) * BK, t.n0);
+                        if (SPLIT) tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, &full[i], (t.kb_begin + i) * BK, t.n0);
+                    }
+                    pdl_wait();
+                    for (int i = 0; i < npre; ++i) {
+                        unsigned char* st = smem + (size_t)i * C::STAGE_BYTES;
+                        tma_load_2d(st, &tm_a_hi, &full[i], (t.kb_begin + i) * BK, t.m0);
+                        if (SPLIT) tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, t.m0);
+                    }
+                    kb = npre;
+                    it = npre;
+                }
+                for (; kb < t.KB; ++kb, ++it) {
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
+                    mbar_expect_tx(&full[s], C::STAGE_BYTES);
+                    tma_load_2d(st, &tm_a_hi, &full[s], (t.kb_begin + kb) * BK, t.m0);
+                    tma_load_2d(st + A_BYTES, &tm_b_hi, &full[s], (t.kb_begin + kb) * BK, t.n0);
+                    if (SPLIT) {
+                        tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, t.m0);
+                        tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, &full[s], (t.kb_begin + kb) * BK, t.n0);
+                    }
                 }
             }
         }
@@ -160,101 +199,77 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         if (lane == 0) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3, M>>4
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % C::STAGES;
-                const uint32_t ph = (kb / C::STAGES) & 1;
-                mbar_wait(&full[s], ph);
+            int it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+                const TileCoord t = tile_coord<BN>(g, tile, tiles_n, per_split, nsplit);
+                const int buf = lt & 1;
+                mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_hi = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
-                const uint32_t b_hi = a_hi + A_BYTES;
-                const uint32_t a_lo = b_hi + C::B_BYTES;
-                const uint32_t b_lo = a_lo + A_BYTES;
+                const uint32_t tacc = tmem_base + (uint32_t)buf * C::ACC_COLS;
+                for (int kb = 0; kb < t.KB; ++kb, ++it) {
+                    const int s = it % C::STAGES;
+                    const uint32_t ph = (it / C::STAGES) & 1;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
+                    const uint32_t b_hi = a_hi + A_BYTES;
+                    const uint32_t a_lo = b_hi + C::B_BYTES;
+                    const uint32_t b_lo = a_lo + A_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    const uint32_t off = k * 32;                     // 16 bf16 = 32 B along the swizzled row
-                    umma_bf16(tmem_base, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | k) != 0);
-                    if (SPLIT) {
-                        umma_bf16(tmem_base, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1);
-                        umma_bf16(tmem_base, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint32_t off = k * 32;                 // 16 bf16 = 32 B along the swizzled row
+                        umma_bf16(tacc, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | k) != 0);
+                        if (SPLIT) {
+                            umma_bf16(tacc, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1);
+                            umma_bf16(tacc, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+                        }
                     }
+                    umma_commit(&empty[s]);                          // frees the smem stage once these MMAs retire
                 }
-                umma_commit(&empty[s]);                              // frees the smem stage once these MMAs retire
+                umma_commit(&tfull[buf]);                            // accumulator complete
             }
-            umma_commit(tmem_full);                                  // accumulator complete
         }
     } else {
-        // Each thread owns one accumulator row in TMEM, but row-per-thread global stores touch 32 different rows per
-        // instruction.  The drained smem ring is reused as a per-warp [32 rows][64+1] fp32 staging tile so that the
-        // fused epilogue runs with lane = column pair: every store instruction covers one contiguous row segment.
+        // One accumulator row per thread (TMEM lane = tile row).  Columns are drained 32 at a time into registers
+        // and finished by the vectorised row epilogue; after the last tcgen05.ld the accumulator goes back to the
+        // MMA warp, so the stores of tile i overlap the MMAs of tile i+1.
         const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
-        constexpr int LDT = 65;
-        float* stage_t = reinterpret_cast<float*>(smem) + (size_t)q * 32 * LDT;
         pdl_wait();                                                  // residual reads / output writes depend on the predecessor
-        mbar_wait(tmem_full, 0);                                     // all MMAs retired: accumulator ready, smem ring idle
-        tc_fence_after();
-        if (BN <= 32) {
-            // decode-sized tiles: 16-32 columns per row.  Every thread finishes its own row straight from registers
-            // (128 rows in parallel); the staged path below would leave 24 of 32 lanes idle.
-            const int m = m0 + q * 32 + lane;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+            const TileCoord t = tile_coord<BN>(g, tile, tiles_n, per_split, nsplit);
+            const int buf = lt & 1;
+            const int m = t.m0 + q * 32 + lane;
+            mbar_wait(&tfull[buf], (lt >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + (uint32_t)buf * C::ACC_COLS + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 16) {
-                float v[16];
-                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                float v[32];
+                tmem_ld16(tacc + (uint32_t)c0, v);
+                if (c0 + 16 < BN) tmem_ld16(tacc + (uint32_t)(c0 + 16), v + 16);
+                if (c0 + 32 >= BN) {                                 // accumulator fully read: hand it back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[buf]);
+                }
                 if (m < g.M) {
-                    if (nsplit > 1) {
-                        float* pz = g.partial + (size_t)blockIdx.z * g.M * g.N + (size_t)m * g.N + n0 + c0;
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            if (n0 + c0 + j < g.N) *reinterpret_cast<float4*>(pz + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
+                    for (int h = 0; h < 32; h += 16) {
+                        const int n = t.n0 + c0 + h;
+                        if (c0 + h < BN && n < g.N) {
+                            if (nsplit > 1) {
+                                float* pz = g.partial + (size_t)t.z * g.M * g.N + (size_t)m * g.N + n;
 #pragma unroll
-                        for (int j = 0; j < 16; j += 2)
-                            if (n0 + c0 + j < g.N) epilogue_pair<EPI>(g, m, n0 + c0 + j, v[j], v[j + 1]);
+                                for (int j = 0; j < 16; j += 4)
+                                    if (n + j < g.N) st4(pz + j, v + h + j);
+                            } else {
+                                epilogue_row16<EPI>(g, m, n, v + h);
+                            }
+                        }
                     }
                 }
             }
-        } else
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 64) {
-#pragma unroll
-            for (int cc = 0; cc < 64; cc += 16) {
-                if (c0 + cc < BN) {
-                    float v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + cc), v);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) stage_t[lane * LDT + cc + j] = v[j];
-                }
-            }
-            __syncwarp();
-            const int n = n0 + c0 + 2 * lane;
-            if (nsplit > 1) {
-                if (c0 + 2 * lane < BN && n < g.N) {
-                    float* pz = g.partial + (size_t)blockIdx.z * g.M * g.N;
-                    for (int r = 0; r < 32; ++r) {
-                        const int m = m0 + q * 32 + r;
-                        if (m >= g.M) break;
-                        *reinterpret_cast<float2*>(pz + (size_t)m * g.N + n) =
-                            make_float2(stage_t[r * LDT + 2 * lane], stage_t[r * LDT + 2 * lane + 1]);
-                    }
-                }
-            } else if (c0 + 2 * lane < BN && n < g.N) {
-#pragma unroll 1
-                for (int rb = 0; rb < 32; rb += 8) {
-                    const int mb = m0 + q * 32 + rb;
-                    float res[8][2];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {                     // residual loads of 8 rows in flight together
-                        res[i][0] = 0.f; res[i][1] = 0.f;
-                        if (mb + i < g.M) load_residual_pair<EPI>(g, mb + i, n, res[i][0], res[i][1]);
-                    }
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (mb + i < g.M)
-                            epilogue_pair_r<EPI>(g, mb + i, n, stage_t[(rb + i) * LDT + 2 * lane],
-                                                 stage_t[(rb + i) * LDT + 2 * lane + 1], res[i][0], res[i][1]);
-                }
-            }
-            __syncwarp();
         }
     }
     tc_fence_before();
@@ -318,7 +333,14 @@ cudaError_t launch_one(const GemmArgs& g, cudaStream_t st) {
         ta_lo = ta_hi;
         tb_lo = tb_hi;
     }
-    dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM, g.split_k > 1 ? g.split_k : 1);
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long total = (long long)((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM) * (g.split_k > 1 ? g.split_k : 1);
+    dim3 grid((unsigned)(total < num_sms ? total : num_sms));
     return launch_k(kern, grid, dim3(192), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
 }
 
@@ -330,6 +352,8 @@ cudaError_t launch_epi(const GemmArgs& g, cudaStream_t st) {
         if (g.N >= 2048) return split ? launch_one<32, EPI, true>(g, st) : launch_one<32, EPI, false>(g, st);
         return split ? launch_one<16, EPI, true>(g, st) : launch_one<16, EPI, false>(g, st);
     }
+    if (g.N % 256 == 0 && g.M >= 1024 && getenv("MB_NO_BN256") == nullptr)       // widest tile: A tile re-used over 256 columns
+        return split ? launch_one<256, EPI, true>(g, st) : launch_one<256, EPI, false>(g, st);
     const bool bn96 = (g.N % 128 != 0) && (g.N % 96 == 0);
     if (bn96) return split ? launch_one<96, EPI, true>(g, st) : launch_one<96, EPI, false>(g, st);
     return split ? launch_one<128, EPI, true>(g, st) : launch_one<128, EPI, false>(g, st);

@@ -371,11 +371,12 @@ inline void* kv_layer(const Handle* h, void* base, int l) {
 
 constexpr int kMaxAttnSplit = 16;
 inline int decode_nsplit(const Handle* h, int B) {
+    // One CTA per (row, kv head) streams the whole context through a 2-tile cp.async ring and writes the final
+    // output itself when that already gives >= ~2.5 CTAs per SM (B >= 128); smaller batches split the keys so the
+    // 148 SMs stay busy and merge the partial softmax states in decode_combine_kernel.
     const int tiles_max = (h->t_max + 63) / 64;
-    int ns = (tiles_max + 1) / 2;                         // 2 key tiles per CTA, both requested up front (measured
-                                                          // faster than 1 tile per CTA at twice the occupancy)
-    const int want = (888 + 3 * B - 1) / (3 * B);         // small batches: more splits to fill the 148 SMs
-    if (want > ns) ns = want;
+    int ns = (384 + 3 * B - 1) / (3 * B);
+    if (ns > tiles_max) ns = tiles_max;
     return ns < 1 ? 1 : (ns > kMaxAttnSplit ? kMaxAttnSplit : ns);
 }
 
@@ -389,7 +390,7 @@ int run_decode_attention(Handle* h, int l, int B, cudaStream_t st) {
     a.part_acc = h->part_acc; a.part_ml = h->part_ml;
     a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
     MB_CK(h, launch_decode_attention(a, st));
-    h->launches += 2;
+    h->launches += a.nsplit == 1 ? 1 : 2;
     return 0;
 }
 

@@ -277,9 +277,15 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
     __syncthreads();
     for (int e = tid; e < 3 * kHeadDim; e += 128) {
         const int h = e >> 6, d = e & 63;
-        const size_t o = (((size_t)b * kHeads + kvh * 3 + h) * a.nsplit + split);
-        a.part_acc[o * kHeadDim + d] = sm.red[0][h][d] + sm.red[1][h][d] + sm.red[2][h][d] + sm.red[3][h][d];
-        if (d == 0) { a.part_ml[o * 2] = sm.m[h]; a.part_ml[o * 2 + 1] = sm.l[h]; }
+        const float acc_hd = sm.red[0][h][d] + sm.red[1][h][d] + sm.red[2][h][d] + sm.red[3][h][d];
+        if (a.nsplit == 1) {
+            // this CTA saw every key of its (row, kv head): finish here, no partials, no combine kernel
+            store_planes1(a.out_hi, a.out_lo, (size_t)b * kHidden + (kvh * 3 + h) * kHeadDim + d, acc_hd / sm.l[h]);
+        } else {
+            const size_t o = (((size_t)b * kHeads + kvh * 3 + h) * a.nsplit + split);
+            a.part_acc[o * kHeadDim + d] = acc_hd;
+            if (d == 0) { a.part_ml[o * 2] = sm.m[h]; a.part_ml[o * 2 + 1] = sm.l[h]; }
+        }
     }
 }
 
@@ -440,7 +446,7 @@ cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
     }
     cudaError_t e = a.kv_bf16 ? launch_k(decode_attention_kernel<bf16>, grid, dim3(128), sizeof(DecodeSmem<bf16>), st, a)
                               : launch_k(decode_attention_kernel<float>, grid, dim3(128), sizeof(DecodeSmem<float>), st, a);
-    if (e != cudaSuccess) return e;
+    if (e != cudaSuccess || a.nsplit == 1) return e;
     return launch_k(decode_combine_kernel, dim3(kHeads, a.B), dim3(64), 0, st, a);
 }
 

@@ -198,7 +198,12 @@ def run_ours(args):
         return eng.prefill(B, want_logits=False)
     ms_prefill, _ = timed(prefill_only, 2, 1)
     ms_decode, dtoks = timed(lambda: eng.decode(B, max_len), 1, 1)
+    # prefill is tensor-pipe bound: 112.18 GFLOP of algorithmic work per pair; under the split
+    # policy every contraction is issued as 3 bf16 MMA passes, so the tensor pipe does 3x that
+    prefill_tflops = 112.18e9 * B / (ms_prefill * 1e-3) / 1e12
     phases = {"prefill_ms": ms_prefill, "prefill_pairs_per_s": world * B / (ms_prefill * 1e-3),
+              "prefill_algorithmic_tflops_per_gpu": prefill_tflops,
+              "prefill_mma_tflops_per_gpu": prefill_tflops * (3 if args.policy == "split" else 1),
               "decode_ms_per_token_step": ms_decode / max_len,
               "decode_tokens_per_s": world * B * dtoks.shape[1] / (ms_decode * 1e-3)}
 
@@ -211,8 +216,13 @@ def run_ours(args):
     ms_attn /= iters
     alg_bytes = 2 * B * KV_HEADS * ctx * HEAD_DIM * kv_bytes + 2 * B * HIDDEN * 4
     achieved = alg_bytes / (ms_attn * 1e-3) / 1e9
-    roofline = {"kernel": "decode_attention_kernel (+decode_combine_kernel)", "bound": "hbm", "achieved": achieved,
-                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_decode_attention_b128_ctx539_ncu_full.json")
+    if os.path.isfile(tpath) and B == 128 and ctx == 539 and kv_bytes == 4:
+        with open(tpath) as f:                       # dram__bytes_read+write per launch from the committed ncu --set full capture
+            traffic = json.load(f)["traffic_bytes_per_launch"]
+    roofline = {"kernel": "decode_attention_kernel", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms_attn * 1e3, "ctx": ctx,
                 "share_of_decode_step": LAYERS * ms_attn / (ms_decode / max_len)}
 

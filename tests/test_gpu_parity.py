@@ -226,3 +226,65 @@ def test_wrapper_drop_in_surface(tmp_path, golden):
     assert isinstance(out, list) and len(out) == 2 and all(isinstance(s, str) for s in out)
     with pytest.raises(ValueError):
         MellowWrapper(config="v0", model="v1", device=0)
+
+
+def test_tcgen05_and_mma_engines_agree(engine, oracle_taps, golden):
+    """The tcgen05/TMA engine (default) and the mma.sync bring-up engine must give the same greedy ids."""
+    prefix = oracle_taps["prefix"]
+    out = {}
+    try:
+        for eng_id in (0, 1):
+            engine.set_gemm_engine(eng_id)
+            engine.set_prefix(prefix)
+            out[eng_id] = engine.prefill(2)
+            toks = engine.decode(2, 8)
+            assert toks.cpu().tolist() == golden["tokens"][:, :8].tolist(), f"engine {eng_id}"
+    finally:
+        engine.set_gemm_engine(1)
+    assert maxerr(out[0], out[1]) < LOGIT_TOL
+
+
+def test_unfused_decode_path_matches(engine, oracle_taps, golden, monkeypatch):
+    """B > 128 uses the per-kernel decode layer (residual in the GEMM epilogue, separate RMSNorm); force it at B=2."""
+    prefix = oracle_taps["prefix"]
+    monkeypatch.setenv("MB_DECODE_UNFUSED", "1")
+    monkeypatch.setenv("MB_NO_GRAPH", "1")
+    engine.set_prefix(prefix)
+    engine.prefill(2, want_logits=False)
+    toks = engine.decode(2, 8)
+    assert toks.cpu().tolist() == golden["tokens"][:, :8].tolist()
+
+
+def test_odd_batch_and_determinism(engine, inputs, golden):
+    """B=3 (ragged use of a 4-row handle): rows are independent, results repeat bit-for-bit."""
+    w1 = torch.cat([inputs["wave1"], inputs["wave1"][:1]])
+    w2 = torch.cat([inputs["wave2"], inputs["wave2"][:1]])
+    ids = torch.cat([inputs["ids"], inputs["ids"][:1]])
+    a = engine.generate(w1, w2, ids, 10).cpu()
+    b = engine.generate(w1, w2, ids, 10).cpu()
+    assert torch.equal(a, b)
+    want = golden["tokens"][:, :10].tolist()
+    assert a.tolist() == [want[0], want[1], want[0]]
+
+
+def test_full_size_batch_128_rows_match_golden(sd, engine, inputs, golden):
+    """BASELINE.json's batch-128 configuration: 64 copies of the two golden pairs; every row must reproduce its golden
+    ids (row independence at full size, the persistent tcgen05 tiles and the unsplit decode attention path)."""
+    from mellow_b200.engine import Engine
+    big = Engine(None, device=0, max_batch=128, max_new_tokens=16, policy="split", arena=engine.arena)
+    try:
+        w1 = inputs["wave1"].repeat(64, 1)
+        w2 = inputs["wave2"].repeat(64, 1)
+        ids = inputs["ids"].repeat(64, 1)
+        toks = big.generate(w1, w2, ids, 12).cpu()
+        assert toks.shape == (128, 12)
+        want = torch.from_numpy(golden["tokens"]).to(torch.int32)
+        assert torch.equal(toks[0::2], want[0:1].expand(64, -1))
+        assert torch.equal(toks[1::2], want[1:2].expand(64, -1))
+    finally:
+        big.close()
+
+
+def test_fast_policy_generate_runs_end_to_end(engine_fast, inputs):
+    toks = engine_fast.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 6)
+    assert toks.shape == (2, 6) and int(toks.min()) >= 0 and int(toks.max()) < 49152

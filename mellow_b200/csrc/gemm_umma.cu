@@ -8,8 +8,8 @@
 //   * epilogue: four warps read the accumulator with tcgen05.ld (one row per thread) and run the same fused
 //     epilogues as the mma.sync engine (gemm.cuh): bias / GELU / sigmoid / residual, SwiGLU, QKV + RoPE + KV write.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-// (TMEM lane quadrant = warp % 4).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue
+// (TMEM lane quadrant = warp % 4, two warps per quadrant alternating 32-column chunks).
 #include <cuda.h>
 
 #include <cstdlib>
@@ -23,6 +23,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;                  // 64 bf16 = 128 B = one swizzle row
 constexpr uint32_t A_BYTES = BM * BK * 2;
+constexpr int kEpiWarps = 8;            // two epilogue warps per TMEM lane quadrant (= per SM sub-partition)
+constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -48,6 +50,25 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+                 " [%0], [%1, {%4, %5}], [%2], %3;"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "h"(mask), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor fields)
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     uint64_t d = 0;
@@ -116,8 +137,11 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile, int
 // Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence (n fastest, so the CTAs that run
 // concurrently share A rows and the whole W in L2).  The smem ring runs continuously across tiles; the accumulator
 // is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-template <int BN, int EPI, bool SPLIT>
-__global__ void __launch_bounds__(192, 1)
+// CL > 1 (decode-sized GEMMs): CL CTAs of a thread-block cluster own CL consecutive N tiles of the same 128-row
+// activation tile.  Each CTA loads 1/CL of every A k-block and TMA-multicasts it to all of them, so the activation
+// bytes pulled from L2 drop CL-fold; a stage is recycled only after all CL consumers released it (multicast commit).
+template <int BN, int EPI, bool SPLIT, int CL>
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                  const GemmArgs g) {
@@ -137,11 +161,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int per_split = tiles_n * ((g.M + BM - 1) / BM);
     const int total = per_split * nsplit;
 
+    const uint32_t crank = CL > 1 ? cluster_rank() : 0u;
+    constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
+    constexpr uint32_t A_PART = A_BYTES / CL;                        // bytes of the A tile this CTA fetches per plane
     pdl_trigger();
     if (threadIdx.x == 0) {
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], 4); mbar_init(&tempty[1], 4);
+        mbar_init(&tempty[0], kEpiWarps); mbar_init(&tempty[1], kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -150,6 +177,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                                  // peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -174,8 +202,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     pdl_wait();
                     for (int i = 0; i < npre; ++i) {
                         unsigned char* st = smem + (size_t)i * C::STAGE_BYTES;
-                        tma_load_2d(st, &tm_a_hi, &full[i], (t.kb_begin + i) * BK, t.m0);
-                        if (SPLIT) tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, t.m0);
+                        if (CL > 1) {
+                            const int mr = t.m0 + (int)crank * (BM / CL);
+                            tma_load_2d_mc(st + crank * A_PART, &tm_a_hi, &full[i], (t.kb_begin + i) * BK, mr, cmask);
+                            if (SPLIT) tma_load_2d_mc(st + A_BYTES + C::B_BYTES + crank * A_PART, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, mr, cmask);
+                        } else {
+                            tma_load_2d(st, &tm_a_hi, &full[i], (t.kb_begin + i) * BK, t.m0);
+                            if (SPLIT) tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, t.m0);
+                        }
                     }
                     kb = npre;
                     it = npre;
@@ -186,11 +220,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     mbar_wait(&empty[s], ph ^ 1);
                     unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
                     mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                    tma_load_2d(st, &tm_a_hi, &full[s], (t.kb_begin + kb) * BK, t.m0);
                     tma_load_2d(st + A_BYTES, &tm_b_hi, &full[s], (t.kb_begin + kb) * BK, t.n0);
-                    if (SPLIT) {
-                        tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, t.m0);
-                        tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, &full[s], (t.kb_begin + kb) * BK, t.n0);
+                    if (SPLIT) tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, &full[s], (t.kb_begin + kb) * BK, t.n0);
+                    if (CL > 1) {
+                        const int mr = t.m0 + (int)crank * (BM / CL);
+                        tma_load_2d_mc(st + crank * A_PART, &tm_a_hi, &full[s], (t.kb_begin + kb) * BK, mr, cmask);
+                        if (SPLIT) tma_load_2d_mc(st + A_BYTES + C::B_BYTES + crank * A_PART, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, mr, cmask);
+                    } else {
+                        tma_load_2d(st, &tm_a_hi, &full[s], (t.kb_begin + kb) * BK, t.m0);
+                        if (SPLIT) tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, t.m0);
                     }
                 }
             }
@@ -224,7 +262,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                             umma_bf16(tacc, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
                         }
                     }
-                    umma_commit(&empty[s]);                          // frees the smem stage once these MMAs retire
+                    if (CL > 1) umma_commit_mc(&empty[s], cmask);    // every producer of the cluster writes into this stage
+                    else umma_commit(&empty[s]);                     // frees the smem stage once these MMAs retire
                 }
                 umma_commit(&tfull[buf]);                            // accumulator complete
             }
@@ -234,6 +273,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         // and finished by the vectorised row epilogue; after the last tcgen05.ld the accumulator goes back to the
         // MMA warp, so the stores of tile i overlap the MMAs of tile i+1.
         const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;                            // the two warps of a quadrant alternate 32-column chunks
         pdl_wait();                                                  // residual reads / output writes depend on the predecessor
         int lt = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
@@ -243,12 +283,18 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             mbar_wait(&tfull[buf], (lt >> 1) & 1);
             tc_fence_after();
             const uint32_t tacc = tmem_base + (uint32_t)buf * C::ACC_COLS + ((uint32_t)(q * 32) << 16);
+            constexpr int kChunks = (BN + 31) / 32;
+            if (half * 32 >= BN) {                                   // narrow tile: nothing for the second warp to drain
+                if (lane == 0) mbar_arrive(&tempty[buf]);
+                continue;
+            }
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int ci = half; ci < kChunks; ci += 2) {
+                const int c0 = ci * 32;
                 float v[32];
                 tmem_ld16(tacc + (uint32_t)c0, v);
                 if (c0 + 16 < BN) tmem_ld16(tacc + (uint32_t)(c0 + 16), v + 16);
-                if (c0 + 32 >= BN) {                                 // accumulator fully read: hand it back
+                if (ci + 2 >= kChunks) {                             // this warp has read its share: hand the accumulator back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[buf]);
@@ -274,6 +320,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();                                  // no CTA leaves while peers may still signal it
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
@@ -313,10 +360,10 @@ bool make_map(CUtensorMap* map, const bf16* ptr, int rows, int K, int ld, int bo
     return r == CUDA_SUCCESS;
 }
 
-template <int BN, int EPI, bool SPLIT>
+template <int BN, int EPI, bool SPLIT, int CL = 1>
 cudaError_t launch_one(const GemmArgs& g, cudaStream_t st) {
     using C = Cfg<BN, SPLIT>;
-    auto kern = gemm_umma_kernel<BN, EPI, SPLIT>;
+    auto kern = gemm_umma_kernel<BN, EPI, SPLIT, CL>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -324,10 +371,10 @@ cudaError_t launch_one(const GemmArgs& g, cudaStream_t st) {
         configured = true;
     }
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    if (!make_map(&ta_hi, g.A_hi, g.M, g.K, g.lda, BM) || !make_map(&tb_hi, g.W_hi, g.N, g.K, g.ldw, BN))
+    if (!make_map(&ta_hi, g.A_hi, g.M, g.K, g.lda, BM / CL) || !make_map(&tb_hi, g.W_hi, g.N, g.K, g.ldw, BN))
         return cudaErrorInvalidValue;
     if (SPLIT) {
-        if (!make_map(&ta_lo, g.A_lo, g.M, g.K, g.lda, BM) || !make_map(&tb_lo, g.W_lo, g.N, g.K, g.ldw, BN))
+        if (!make_map(&ta_lo, g.A_lo, g.M, g.K, g.lda, BM / CL) || !make_map(&tb_lo, g.W_lo, g.N, g.K, g.ldw, BN))
             return cudaErrorInvalidValue;
     } else {
         ta_lo = ta_hi;
@@ -341,15 +388,35 @@ cudaError_t launch_one(const GemmArgs& g, cudaStream_t st) {
     }
     const long long total = (long long)((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM) * (g.split_k > 1 ? g.split_k : 1);
     dim3 grid((unsigned)(total < num_sms ? total : num_sms));
-    return launch_k(kern, grid, dim3(192), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
+    if (CL == 1) return launch_k(kern, grid, dim3(kThreads), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
+    // cluster launch (caller guarantees: one tile per CTA, tiles_n % CL == 0)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, g);
 }
 
 template <int EPI>
 cudaError_t launch_epi(const GemmArgs& g, cudaStream_t st) {
     const bool split = g.passes == 3;
     if (g.M <= 128 && g.N <= 4096) {
-        // decode-sized (one 128-row UMMA tile): narrow N tiles (x split-K) so 60-110 SMs stream the weights
-        if (g.N >= 2048) return split ? launch_one<32, EPI, true>(g, st) : launch_one<32, EPI, false>(g, st);
+        // decode-sized (one 128-row UMMA tile): narrow N tiles (x split-K) so 60-144 SMs stream the weights; clusters
+        // of 4 CTAs multicast the shared activation tile when the tile count allows it
+        static const bool no_cluster = getenv("MB_CLUSTER4") == nullptr;   // measured: multicast clusters are ~10% slower here (latency-bound, not A-traffic-bound), off by default
+        const int bn = g.N >= 2048 ? 32 : 16;
+        const int tiles_n = (g.N + bn - 1) / bn;
+        const bool cl4 = !no_cluster && tiles_n % 4 == 0 && tiles_n * (g.split_k > 1 ? g.split_k : 1) <= 148;
+        if (bn == 32) {
+            if (cl4) return split ? launch_one<32, EPI, true, 4>(g, st) : launch_one<32, EPI, false, 4>(g, st);
+            return split ? launch_one<32, EPI, true>(g, st) : launch_one<32, EPI, false>(g, st);
+        }
+        if (cl4) return split ? launch_one<16, EPI, true, 4>(g, st) : launch_one<16, EPI, false, 4>(g, st);
         return split ? launch_one<16, EPI, true>(g, st) : launch_one<16, EPI, false>(g, st);
     }
     if (g.N % 256 == 0 && g.M >= 1024 && getenv("MB_NO_BN256") == nullptr)       // widest tile: A tile re-used over 256 columns

@@ -260,7 +260,11 @@ int swin_block(Handle* h, float* x, int n_clips, int stage, int b, cudaStream_t 
         g.bias = k.qkv_b; g.out_f32 = h->qkv; g.ldo = 3 * C;
         MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
     }
-    MB_CK(h, launch_window_attention(h->qkv, k.relbias, h->a_hi, lo_of(h, h->a_lo), n_clips, R, C, nH, shift, st));
+    static const bool fp32_win = getenv("MB_ATTN_FP32") != nullptr;            // CUDA-core fp32 kernel, kept for A/B checks
+    if (fp32_win)
+        MB_CK(h, launch_window_attention(h->qkv, k.relbias, h->a_hi, lo_of(h, h->a_lo), n_clips, R, C, nH, shift, st));
+    else
+        MB_CK(h, launch_window_attention_mma(h->qkv, k.relbias, h->a_hi, lo_of(h, h->a_lo), n_clips, R, C, nH, shift, st));
     h->launches++;
     {
         GemmArgs g = gemm_base(h, h->a_hi, h->a_lo, C, k.proj, C, M, C, C);

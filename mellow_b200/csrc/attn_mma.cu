@@ -208,7 +208,181 @@ __global__ void __launch_bounds__(128) prefill_attention_mma_kernel(const float*
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// (Shifted-)window attention of the Swin blocks on the tensor cores (reference mellow/model/htsat.py:301-332,
+// 414-449).  CTA = (head, window, clip), 4 warps x 16 query tokens; the 64 keys of the window form a single tile, so
+// the softmax is a plain one-pass softmax.  head_dim 24 is zero-padded to 32 (two k16 steps / four n8 tiles).
+// Shift, window partition / reverse and the -100 mask are index arithmetic exactly as in window_attention_kernel.
+constexpr int WHD = 24, WLD = 32 + 8;
+
+struct WinSmem {
+    bf16 kh[kWinTok][WLD], kl[kWinTok][WLD], vh[kWinTok][WLD], vl[kWinTok][WLD];
+    int tok[kWinTok];
+    int lab[kWinTok];
+};
+
+__device__ __forceinline__ int shift_band2(int v, int R) { return v < R - kWin ? 0 : (v < R - kWin / 2 ? 1 : 2); }
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(128) window_attention_mma_kernel(const float* __restrict__ qkv,
+                                                                   const float* __restrict__ relbias,
+                                                                   bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
+                                                                   int R, int C, int shift) {
+    __shared__ __align__(16) WinSmem sm;
+    const int head = blockIdx.x, win = blockIdx.y, clip = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int nwx = R / kWin;
+    const int wy = win / nwx, wx = win - wy * nwx;
+    pdl_trigger();
+    if (tid < kWinTok) {
+        const int y = wy * kWin + (tid >> 3), x = wx * kWin + (tid & 7);      // coordinates in the shifted frame
+        const int sy = (y + shift) % R, sx = (x + shift) % R;
+        sm.tok[tid] = clip * R * R + sy * R + sx;
+        sm.lab[tid] = shift > 0 ? shift_band2(y, R) * 3 + shift_band2(x, R) : 0;
+    }
+    pdl_wait();
+    __syncthreads();
+    // stage K and V of this head: 64 tokens x 24 dims (+8 zero dims) as bf16 hi/lo
+    for (int e = tid; e < kWinTok * 8; e += 128) {
+        const int j = e >> 3, c = (e & 7) * 4;                                // 8 float4 slots per token row (6 real)
+        float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+        if (c < WHD) {
+            const float* row = qkv + (size_t)sm.tok[j] * 3 * C + head * WHD + c;
+            kv = *reinterpret_cast<const float4*>(row + C);
+            vv = *reinterpret_cast<const float4*>(row + 2 * C);
+        }
+        uint32_t h0, l0, h1, l1;
+        pack_split(kv.x, kv.y, h0, l0); pack_split(kv.z, kv.w, h1, l1);
+        *reinterpret_cast<uint2*>(&sm.kh[j][c]) = make_uint2(h0, h1);
+        if (SPLIT) *reinterpret_cast<uint2*>(&sm.kl[j][c]) = make_uint2(l0, l1);
+        pack_split(vv.x, vv.y, h0, l0); pack_split(vv.z, vv.w, h1, l1);
+        *reinterpret_cast<uint2*>(&sm.vh[j][c]) = make_uint2(h0, h1);
+        if (SPLIT) *reinterpret_cast<uint2*>(&sm.vl[j][c]) = make_uint2(l0, l1);
+    }
+    // Q fragments straight from global (q rows of the qkv weight are pre-scaled by head_dim^-0.5 at pack time)
+    const int i0 = warp * 16 + g, i1 = i0 + 8;
+    uint32_t qh[2][4], ql[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int i = (r & 1) ? i1 : i0;
+            const int col = ks * 16 + 2 * t + ((r & 2) ? 8 : 0);
+            float2 v = make_float2(0.f, 0.f);
+            if (col < WHD) v = *reinterpret_cast<const float2*>(qkv + (size_t)sm.tok[i] * 3 * C + head * WHD + col);
+            pack_split(v.x, v.y, qh[ks][r], ql[ks][r]);
+        }
+    }
+    __syncthreads();
+
+    float s[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+            const int r = j * 8 + (lane & 7) + (lane >> 4) * 8;
+            const int c = ks * 16 + ((lane >> 3) & 1) * 8;
+            uint32_t bh[4], bl[4];
+            ldsm_x4(bh, &sm.kh[r][c]);
+            if (SPLIT) {
+                ldsm_x4(bl, &sm.kl[r][c]);
+                mma16816(s[j], ql[ks], bh[0], bh[1]);
+                mma16816(s[j + 1], ql[ks], bh[2], bh[3]);
+                mma16816(s[j], qh[ks], bl[0], bl[1]);
+                mma16816(s[j + 1], qh[ks], bl[2], bl[3]);
+            }
+            mma16816(s[j], qh[ks], bh[0], bh[1]);
+            mma16816(s[j + 1], qh[ks], bh[2], bh[3]);
+        }
+    }
+    // + relative position bias (+ shifted-window mask), softmax over the 64 keys
+    const float* bias = relbias + (size_t)head * kWinTok * kWinTok;
+    const int lab0 = sm.lab[i0], lab1 = sm.lab[i1];
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int key = j * 8 + 2 * t;
+        const float2 b0 = __ldg(reinterpret_cast<const float2*>(bias + i0 * kWinTok + key));
+        const float2 b1 = __ldg(reinterpret_cast<const float2*>(bias + i1 * kWinTok + key));
+        const int lk0 = sm.lab[key], lk1 = sm.lab[key + 1];
+        s[j][0] += b0.x + (lk0 != lab0 ? -100.0f : 0.f);
+        s[j][1] += b0.y + (lk1 != lab0 ? -100.0f : 0.f);
+        s[j][2] += b1.x + (lk0 != lab1 ? -100.0f : 0.f);
+        s[j][3] += b1.y + (lk1 != lab1 ? -100.0f : 0.f);
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        s[j][0] = expf(s[j][0] - mx0); s[j][1] = expf(s[j][1] - mx0);
+        s[j][2] = expf(s[j][2] - mx1); s[j][3] = expf(s[j][3] - mx1);
+        l0 += s[j][0] + s[j][1];
+        l1 += s[j][2] + s[j][3];
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float r0 = 1.0f / l0, r1 = 1.0f / l1;
+    // the reference normalises the probabilities before attn @ v (softmax then matmul, htsat.py:323-329)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j][0] *= r0; s[j][1] *= r0; s[j][2] *= r1; s[j][3] *= r1; }
+
+    float o[4][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        uint32_t ph[4], pl[4];
+        pack_split(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+        pack_split(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+        pack_split(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+        pack_split(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+        for (int jd = 0; jd < 4; jd += 2) {
+            const int blk = lane >> 3;
+            const int r = kk * 16 + (blk & 1) * 8 + (lane & 7);
+            const int c = (jd + (blk >> 1)) * 8;
+            uint32_t bh[4], bl[4];
+            ldsm_x4_t(bh, &sm.vh[r][c]);
+            if (SPLIT) {
+                ldsm_x4_t(bl, &sm.vl[r][c]);
+                mma16816(o[jd], pl, bh[0], bh[1]);
+                mma16816(o[jd + 1], pl, bh[2], bh[3]);
+                mma16816(o[jd], ph, bl[0], bl[1]);
+                mma16816(o[jd + 1], ph, bl[2], bl[3]);
+            }
+            mma16816(o[jd], ph, bh[0], bh[1]);
+            mma16816(o[jd + 1], ph, bh[2], bh[3]);
+        }
+    }
+    const size_t ob0 = (size_t)sm.tok[i0] * C + head * WHD, ob1 = (size_t)sm.tok[i1] * C + head * WHD;
+#pragma unroll
+    for (int jd = 0; jd < 3; ++jd) {
+        const int col = jd * 8 + 2 * t;
+        store_planes2(out_hi, out_lo, ob0 + col, o[jd][0], o[jd][1]);
+        store_planes2(out_hi, out_lo, ob1 + col, o[jd][2], o[jd][3]);
+    }
+}
+
 }  // namespace
+
+cudaError_t launch_window_attention_mma(const float* qkv, const float* relbias, bf16* out_hi, bf16* out_lo, int n_clips,
+                                        int res, int C, int n_heads, int shift, cudaStream_t st) {
+    if (C != n_heads * WHD || res % kWin != 0) return cudaErrorInvalidValue;
+    dim3 grid(n_heads, (res / kWin) * (res / kWin), n_clips);
+    if (out_lo)
+        return launch_k(window_attention_mma_kernel<true>, grid, dim3(128), 0, st, qkv, relbias, out_hi, out_lo, res, C, shift);
+    return launch_k(window_attention_mma_kernel<false>, grid, dim3(128), 0, st, qkv, relbias, out_hi, out_lo, res, C, shift);
+}
 
 cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S,
                                          int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st) {

@@ -31,6 +31,8 @@ struct NormArgs {
 cudaError_t launch_norm(const NormArgs& a, int kind, cudaStream_t st);
 cudaError_t launch_window_attention(const float* qkv, const float* relbias, bf16* out_hi, bf16* out_lo, int n_clips,
                                     int res, int C, int n_heads, int shift, cudaStream_t st);
+cudaError_t launch_window_attention_mma(const float* qkv, const float* relbias, bf16* out_hi, bf16* out_lo, int n_clips,
+                                        int res, int C, int n_heads, int shift, cudaStream_t st);   // attn_mma.cu
 cudaError_t launch_tail_gather(const float* y, int n_clips, float* latent, bf16* col_hi, bf16* col_lo, cudaStream_t st);
 cudaError_t launch_assemble33(const float* latent, const float* frames, int n_clips, bf16* a_hi, bf16* a_lo,
                               cudaStream_t st);

@@ -1,6 +1,9 @@
 // Launchers of the non-GEMM kernels (frontend.cu, encoder.cu, lm.cu).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
+#include "gemm.cuh"
 
 namespace mb {
 
@@ -72,5 +75,27 @@ cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, in
                                cudaStream_t st);
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st);
 cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st);
+
+// ---- decode_chain.cu: one persistent kernel for the GEMM / norm phases between two decode-attention kernels
+enum { CH_GEMM = 0, CH_ADDNORM = 1 };
+constexpr int kChainMaxOps = 6;
+constexpr int kChainMaps = 12;
+struct ChainOp {
+    int kind;
+    int map_a, map_b;                  // index of the hi-plane tensor map in ChainMaps (lo plane = index + 1)
+    int bn;                            // weight-tile width of a GEMM phase: 16 or 32 columns
+    int epi;                           // EPI_* of a GEMM phase without split-K
+    GemmArgs g;                        // M, N, K, split_k, partial and the epilogue operands
+    float* x; const float* partial; int n_partial; const float* w; bf16* hi; bf16* lo;   // CH_ADDNORM
+};
+struct ChainArgs {
+    int n_ops;
+    int split;                         // operand policy: 1 = hi/lo planes and 3 MMA passes
+    unsigned* bar;                     // [kChainMaxOps] grid-barrier counters of this launch (zeroed once per decode step)
+    ChainOp op[kChainMaxOps];
+};
+struct ChainMaps { CUtensorMap m[kChainMaps]; };
+cudaError_t build_chain_map(CUtensorMap* map, const bf16* ptr, int rows, int K, int ld, int box_rows);
+cudaError_t launch_decode_chain(const ChainMaps& maps, const ChainArgs& args, cudaStream_t st);
 
 }  // namespace mb

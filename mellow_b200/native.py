@@ -16,8 +16,8 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libmellow_b200.so")
 HASH_PATH = os.path.join(CSRC, "libmellow_b200.srchash")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-SOURCES = ["api.cu", "frontend.cu", "encoder.cu", "lm.cu", "attn_mma.cu", "gemm_mma.cu", "gemm_umma.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh"]
+SOURCES = ["api.cu", "frontend.cu", "encoder.cu", "lm.cu", "attn_mma.cu", "gemm_mma.cu", "gemm_umma.cu", "decode_chain.cu"]
+HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", "umma.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

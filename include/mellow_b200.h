@@ -75,6 +75,14 @@ int mb_generate_host(void* h, const float* wave1_host, const float* wave2_host, 
                      int max_len, float temperature, float top_p, int eos_id, int* tokens_out_host,
                      int* steps_out_host, void* stream);
 
+/* ---- audio ingest (replaces torchaudio Resample + the tile/crop of wrapper.py:146-167) ----
+ * pcm [n_in] f32 at orig*g Hz -> out [n_out] f32 at new*g Hz, n_out = ceil(new*n_in/orig); kernel [new][klen] f32 is the
+ * windowed-sinc filter bank (klen = 2*width + orig) built by the host exactly like torchaudio's. */
+int mb_audio_resample(void* h, const float* pcm, long long n_in, int orig, int new_, const float* kernel, int klen,
+                      int width, float* out, long long n_out, void* stream);
+/* out [320000] = samples tiled from the start (total < 320000, start = 0) or cropped at `start` (total >= 320000) */
+int mb_audio_fit(void* h, const float* samples, long long total, long long start, float* out, void* stream);
+
 /* ---- op-level test hooks (parity tests of single kernels) ---- */
 /* C[M,N] = A[M,K] * W[N,K]^T (+bias) with the library's GEMM engine and operand policy; fp32 device in/out */
 int mb_op_gemm(void* h, const float* A, const float* W, const float* bias, float* C, int M, int N, int K, int act,

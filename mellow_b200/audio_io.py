@@ -28,6 +28,43 @@ def read_wav(path):
     return torch.from_numpy(np.ascontiguousarray(x.T)), int(sr)
 
 
+def sinc_resample_kernel(orig_freq, new_freq, lowpass_filter_width=6, rolloff=0.99):
+    """The filter bank of torchaudio.transforms.Resample (sinc_interp_hann defaults), built in float64 and cast to
+    float32 exactly like torchaudio.functional._get_sinc_resample_kernel does.
+    -> (kernel [new, 2*width+orig] float32, width, orig, new) with orig/new reduced by their gcd."""
+    g = math.gcd(int(orig_freq), int(new_freq))
+    orig, new = int(orig_freq) // g, int(new_freq) // g
+    base = min(orig, new) * rolloff
+    width = int(math.ceil(lowpass_filter_width * orig / base))
+    idx = np.arange(-width, width + orig, dtype=np.float64)[None, :] / orig
+    # torchaudio evaluates the per-phase offset `arange(0, -new, -1) / new` on an int64 tensor, i.e. in float32
+    # (torch's default dtype), before adding the float64 grid: reproduce that rounding
+    phase = (np.arange(0, -new, -1).astype(np.float32) / np.float32(new)).astype(np.float64)
+    t = phase[:, None] + idx
+    t = t * base
+    t = np.clip(t, -lowpass_filter_width, lowpass_filter_width)
+    window = np.cos(t * math.pi / lowpass_filter_width / 2.0) ** 2
+    t = t * math.pi
+    scale = base / orig
+    with np.errstate(divide="ignore", invalid="ignore"):
+        kern = np.where(t == 0, 1.0, np.sin(t) / t)
+    kern = kern * window * scale
+    return torch.from_numpy(kern.astype(np.float32)), width, orig, new
+
+
+def resampled_length(n_in, orig, new):
+    """torchaudio: ceil(new * length / orig), evaluated in floating point like `_apply_sinc_resample_kernel`."""
+    return int(math.ceil(new * n_in / orig))
+
+
+def plan_fit(total, target, rng=random):
+    """Tile-or-crop decision of reference wrapper.py:152-167 for a flattened clip of `total` samples: returns the
+    start offset (0 when tiling; one `rng.randrange` draw when cropping, the same draw the reference makes)."""
+    if target >= total:
+        return 0
+    return rng.randrange(total - target)
+
+
 def load_audio_into_tensor(path, audio_duration, sample_rate_target, resample=True, rng=random):
     """Restates reference wrapper.py:141-168 (same branch conditions and the same ``random.randrange`` draw)."""
     audio, sr = read_wav(path)

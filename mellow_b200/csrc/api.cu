@@ -924,6 +924,26 @@ int mb_generate_host(void* hv, const float* wave1_host, const float* wave2_host,
                        steps_out_host, st);
 }
 
+int mb_audio_resample(void* hv, const float* pcm, long long n_in, int orig, int new_, const float* kernel, int klen,
+                      int width, float* out, long long n_out, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    if (n_in < 1 || orig < 1 || new_ < 1 || klen != 2 * width + orig || n_out < 1) return fail(h, "mb_audio_resample: bad arguments");
+    cudaSetDevice(h->device);
+    MB_CK(h, launch_resample(pcm, n_in, orig, new_, kernel, klen, width, out, n_out, pick_stream(h, stream)));
+    h->launches++;
+    return 0;
+}
+
+int mb_audio_fit(void* hv, const float* samples, long long total, long long start, float* out, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    if (total < 1 || start < 0 || (total >= kClipSamples && start + kClipSamples > total) || (total < kClipSamples && start != 0))
+        return fail(h, "mb_audio_fit: bad arguments");
+    cudaSetDevice(h->device);
+    MB_CK(h, launch_fit(samples, total, start, out, pick_stream(h, stream)));
+    h->launches++;
+    return 0;
+}
+
 int mb_bench_decode_attention(void* hv, int B, int ctx, int iters, void* stream) {
     Handle* h = reinterpret_cast<Handle*>(hv);
     MB_TRY(check_ready(h, B));

@@ -22,6 +22,11 @@ cudaError_t launch_logmel(const float* wave, int n_clips, const FrontendW& w, fl
 struct PatchW { const float* w; const float* b; const float* ln_w; const float* ln_b; };
 cudaError_t launch_patch_embed(const float* bn, int n_clips, const PatchW& w, float* x_out, cudaStream_t st);
 
+// ---- audio.cu
+cudaError_t launch_resample(const float* x, long long n_in, int orig, int nw, const float* kern, int klen, int width,
+                            float* y, long long n_out, cudaStream_t st);
+cudaError_t launch_fit(const float* src, long long total, long long start, float* out, cudaStream_t st);
+
 // ---- encoder.cu
 enum { NORM_LN = 0, NORM_RMS = 1, NORM_LN_MERGE = 2 };
 struct NormArgs {

@@ -166,6 +166,41 @@ class Engine:
                                            top_p, eos_id, _ptr(out), ctypes.byref(steps), self._stream()))
         return out[:, :steps.value]
 
+    # ------------------------------------------------------------------ audio ingest
+    def _resample_kernel(self, sr_in, sr_out):
+        key = (int(sr_in), int(sr_out))
+        cache = self.__dict__.setdefault("_rs_cache", {})
+        if key not in cache:
+            from .audio_io import sinc_resample_kernel
+            kern, width, orig, new = sinc_resample_kernel(sr_in, sr_out)
+            cache[key] = (kern.contiguous().to(self.device), width, orig, new)
+        return cache[key]
+
+    def prepare_clip(self, pcm, sample_rate, target_rate=S.SAMPLE_RATE, resample=True, rng=None, out=None):
+        """pcm (channels, n) float32 host/device tensor -> (320000,) device tensor: per-channel polyphase resampling to
+        `target_rate`, channels concatenated (reference wrapper.py:146-149), then tile-or-crop (wrapper.py:152-167)."""
+        import random as _random
+        from .audio_io import plan_fit, resampled_length
+        rng = rng or _random
+        pcm = self._dev(pcm if pcm.dim() == 2 else pcm[None, :], torch.float32)
+        ch, n_in = pcm.shape
+        if resample and int(sample_rate) != int(target_rate):
+            kern, width, orig, new = self._resample_kernel(sample_rate, target_rate)
+            n_out = resampled_length(n_in, orig, new)
+            flat = torch.empty(ch * n_out, device=self.device)
+            for c in range(ch):
+                self._ck(self.lib.mb_audio_resample(self.handle, _ptr(pcm[c]), n_in, orig, new, _ptr(kern), kern.shape[1],
+                                                    width, ctypes.c_void_p(flat.data_ptr() + 4 * c * n_out), n_out,
+                                                    self._stream()))
+        else:
+            flat = pcm.reshape(-1)
+        total = flat.numel()
+        start = plan_fit(total, S.CLIP_SAMPLES, rng)
+        if out is None:
+            out = torch.empty(S.CLIP_SAMPLES, device=self.device)
+        self._ck(self.lib.mb_audio_fit(self.handle, _ptr(flat), total, start, _ptr(out), self._stream()))
+        return out
+
     def bench_decode_attention(self, batch, ctx, iters):
         self._ck(self.lib.mb_bench_decode_attention(self.handle, batch, ctx, iters, self._stream()))
 

@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libmellow_b200.so")
 HASH_PATH = os.path.join(CSRC, "libmellow_b200.srchash")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-SOURCES = ["api.cu", "frontend.cu", "encoder.cu", "lm.cu", "attn_mma.cu", "gemm_mma.cu", "gemm_umma.cu", "decode_chain.cu"]
+SOURCES = ["api.cu", "frontend.cu", "encoder.cu", "lm.cu", "attn_mma.cu", "gemm_mma.cu", "gemm_umma.cu", "decode_chain.cu", "audio.cu"]
 HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", "umma.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -102,6 +102,8 @@ SYMBOLS = [
     ("mb_decode", _i, [_vp, _i, _i, _f, _f, _i, _vp, ctypes.POINTER(_i), _vp, _vp, _vp]),
     ("mb_generate", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, ctypes.POINTER(_i), _vp]),
     ("mb_generate_host", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, ctypes.POINTER(_i), _vp]),
+    ("mb_audio_resample", _i, [_vp, _vp, _ll, _i, _i, _vp, _i, _i, _vp, _ll, _vp]),
+    ("mb_audio_fit", _i, [_vp, _vp, _ll, _ll, _vp, _vp]),
     ("mb_bench_decode_attention", _i, [_vp, _i, _i, _i, _vp]),
     ("mb_op_gemm", _i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 ]

@@ -86,11 +86,15 @@ class MellowWrapper:
         return load_audio_into_tensor(audio_path, audio_duration, self.args.data["sampling_rate"], resample, random)
 
     def preprocess_audio(self, audio_files, resample):
-        """-> (B, 320000) float32 pinned host tensor (the reference stacks (1, L) rows on the device, wrapper.py:170-179)."""
+        """-> (B, 320000) float32 DEVICE tensor.  Files are decoded on the host; resampling to 32 kHz, channel
+        flattening and tile-or-crop run on the GPU (the reference does all of it serially on the host and uploads
+        one clip at a time, wrapper.py:170-179).  The `random.randrange` draws happen in file order like the reference."""
+        from .audio_io import read_wav
         n = len(audio_files)
-        out = torch.empty(n, S.CLIP_SAMPLES, dtype=torch.float32).pin_memory()
+        out = torch.empty(n, S.CLIP_SAMPLES, dtype=torch.float32, device=self.model.device)
         for i, audio_file in enumerate(audio_files):
-            out[i] = self.load_audio_into_tensor(audio_file, self.args.data["segment_seconds"], resample)
+            pcm, sr = read_wav(audio_file)
+            self.model.prepare_clip(pcm, sr, self.args.data["sampling_rate"], resample, random, out=out[i])
         return out
 
     def preprocess_text(self, prompts):
@@ -121,7 +125,7 @@ class MellowWrapper:
         preds = []
         for s in range(0, len(examples), self.max_batch):                   # micro-batches of the handle's capacity
             e = min(len(examples), s + self.max_batch)
-            toks = self.model.generate_host(audio1[s:e], audio2[s:e], ids[s:e], max_len, temperature=temperature,
-                                            top_p=top_p, eos_id=stop_id)
-            preds.extend(self._detokenize(toks))
+            toks = self.model.generate(audio1[s:e], audio2[s:e], ids[s:e], max_len, temperature=temperature,
+                                       top_p=top_p, eos_id=stop_id)
+            preds.extend(self._detokenize(toks.cpu()))
         return preds

@@ -288,3 +288,27 @@ def test_full_size_batch_128_rows_match_golden(sd, engine, inputs, golden):
 def test_fast_policy_generate_runs_end_to_end(engine_fast, inputs):
     toks = engine_fast.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 6)
     assert toks.shape == (2, 6) and int(toks.min()) >= 0 and int(toks.max()) < 49152
+
+
+@pytest.mark.parametrize("sr,channels,seconds", [(44100, 1, 9.152), (44100, 1, 10.112), (48000, 2, 3.0), (16000, 1, 12.5),
+                                                 (22050, 1, 4.0), (32000, 1, 10.0), (32000, 2, 7.0)])
+def test_gpu_audio_ingest_matches_torchaudio_host_path(engine, tmp_path, sr, channels, seconds):
+    """Row f1: wav -> 32 kHz (polyphase sinc = torchaudio Resample) -> channels flattened -> tile / random crop, on the
+    GPU, against the host path that restates reference wrapper.py:141-168 with torchaudio itself."""
+    import random
+    import wave as wavmod
+    from mellow_b200.audio_io import load_audio_into_tensor, read_wav
+    n = int(sr * seconds)
+    g = torch.Generator().manual_seed(sr + channels)
+    pcm16 = (torch.rand(n, channels, generator=g) * 2 - 1).mul(20000).round().to(torch.int16)
+    path = str(tmp_path / "a.wav")
+    with wavmod.open(path, "wb") as f:
+        f.setnchannels(channels); f.setsampwidth(2); f.setframerate(sr)
+        f.writeframes(pcm16.numpy().astype("<i2").tobytes())
+    want = load_audio_into_tensor(path, 10, 32000, True, random.Random(3))
+    pcm, got_sr = read_wav(path)
+    assert got_sr == sr and pcm.shape == (channels, n)
+    got = engine.prepare_clip(pcm, sr, 32000, True, random.Random(3)).cpu()
+    assert got.shape == (320000,)
+    err = (got - want).abs().max().item()
+    assert err < 2e-6, f"sr={sr} ch={channels}: max abs err {err}"

@@ -142,3 +142,25 @@ def test_create_fails_loudly_without_gpu(lib):
     h = lib.mb_create(0, 1, 8, 0)
     assert not h
     assert b"no CUDA device" in lib.mb_last_error(None)
+
+
+def test_resample_filter_bank_equals_torchaudio():
+    """the polyphase filter bank handed to the GPU resampler is torchaudio's, bit for bit."""
+    import torchaudio.transforms as T
+    from mellow_b200.audio_io import resampled_length, sinc_resample_kernel
+    for sr_in in (44100, 48000, 22050, 16000, 8000):
+        kern, width, orig, new = sinc_resample_kernel(sr_in, 32000)
+        ref = T.Resample(sr_in, 32000)
+        assert width == ref.width and kern.shape[1] == 2 * width + orig
+        assert torch.equal(kern, ref.kernel[:, 0, :])
+        x = torch.zeros(1, 4567)
+        assert ref(x).shape[1] == resampled_length(4567, orig, new)
+
+
+def test_plan_fit_draws_like_the_reference():
+    import random
+    from mellow_b200.audio_io import plan_fit
+    assert plan_fit(1000, 320000, random.Random(1)) == 0                   # short clip: tiled, no draw
+    rng = random.Random(7)
+    want = random.Random(7).randrange(323585 - 320000)
+    assert plan_fit(323585, 320000, rng) == want                          # long clip: one randrange draw

@@ -167,7 +167,9 @@ struct Handle {
     bf16 *la_hi = nullptr, *la_lo = nullptr, *lh_hi = nullptr, *lh_lo = nullptr;
     void *kcache = nullptr, *vcache = nullptr;
     size_t kv_layer_elems = 0;
-    float *part_acc = nullptr, *part_ml = nullptr, *gemm_partial = nullptr;
+    float *part_acc = nullptr, *part_ml = nullptr, *gemm_partial = nullptr, *cand_val = nullptr;
+    int* cand_idx = nullptr;
+    bool logits_fused = false;           // the last lm_head wrote argmax candidates instead of logits
     unsigned* chain_bar = nullptr;       // [kLayers][8] grid-barrier counters of the fused decode chain
     int *d_tokens = nullptr, *d_done = nullptr, *d_step = nullptr, *d_stop = nullptr, *d_ids = nullptr;
     float *wave_stage = nullptr;
@@ -233,6 +235,7 @@ int run_gemm(Handle* h, const GemmArgs& g, int epi, cudaStream_t st) {
         MB_CK(h, launch_gemm_umma(g, epi, st, &handled));
         if (handled) { h->launches++; return 0; }
     }
+    if (epi == EPI_ARGMAX) return fail(h, "argmax epilogue needs the tcgen05 engine");
     MB_CK(h, launch_gemm_mma(g, epi, st));
     h->launches++;
     return 0;
@@ -555,16 +558,28 @@ int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_
     return 0;
 }
 
-// final RMSNorm of one row per sequence + lm_head -> h->logits [B,V]
-int lm_head(Handle* h, int B, int row_stride, int row_off, cudaStream_t st) {
-    MB_TRY(run_norm(h, NORM_RMS, h->x, h->w.lm_norm, nullptr, B, kHidden, h->la_hi, h->la_lo, nullptr, row_stride,
-                    row_off, 0, st));
+// lm_head over the planes in la_hi/la_lo.  fused: write per-16-column argmax candidates for sample_kernel instead of
+// the [B,49152] logits (the decode loop); otherwise the full fp32 logits (parity dumps, mb_prefill).
+int lm_head_gemm(Handle* h, int B, bool fused, cudaStream_t st) {
     GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, h->w.head, kHidden, B, kVocab, kHidden);
+    fused = fused && h->engine == 1;                      // the argmax epilogue exists in the row-per-thread engine only
+    h->logits_fused = fused;
+    if (fused) {
+        g.cand_val = h->cand_val; g.cand_idx = h->cand_idx;
+        return run_gemm(h, g, EPI_ARGMAX, st);
+    }
     g.out_f32 = h->logits; g.ldo = kVocab;
     return run_gemm(h, g, EPI_GENERIC, st);
 }
 
-int decode_step(Handle* h, int B, cudaStream_t st) {
+// final RMSNorm of one row per sequence + lm_head
+int lm_head(Handle* h, int B, int row_stride, int row_off, bool fused, cudaStream_t st) {
+    MB_TRY(run_norm(h, NORM_RMS, h->x, h->w.lm_norm, nullptr, B, kHidden, h->la_hi, h->la_lo, nullptr, row_stride,
+                    row_off, 0, st));
+    return lm_head_gemm(h, B, fused, st);
+}
+
+int decode_step(Handle* h, int B, bool fused, cudaStream_t st) {
     if (B <= 128 && h->engine == 1 && getenv("MB_DECODE_UNFUSED") == nullptr && getenv("MB_CHAIN") != nullptr) {
         // Experimental (MB_CHAIN=1): 2 kernels per layer, decode attention + one persistent chain kernel whose phases
         // are separated by software grid barriers.  Parity-green, but measured 10 % slower than the PDL-linked
@@ -587,27 +602,25 @@ int decode_step(Handle* h, int B, cudaStream_t st) {
             MB_TRY(run_decode_attention(h, l, B, st));
             MB_TRY(lm_layer_decode_chain(h, l, B, st));
         }
-        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, h->w.head, kHidden, B, kVocab, kHidden);
-        g.out_f32 = h->logits; g.ldo = kVocab;
-        return run_gemm(h, g, EPI_GENERIC, st);
+        return lm_head_gemm(h, B, fused, st);
     }
     if (B <= 128 && getenv("MB_DECODE_UNFUSED") == nullptr) {
         MB_CK(h, launch_add_rmsnorm(h->x, nullptr, 0, B, h->w.layer[0].ln1, h->la_hi, lo_of(h, h->la_lo), st));
         h->launches++;
         for (int l = 0; l < kLayers; ++l)
             MB_TRY(lm_layer_decode_fused(h, l, B, l + 1 < kLayers ? h->w.layer[l + 1].ln1 : h->w.lm_norm, st));
-        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, h->w.head, kHidden, B, kVocab, kHidden);
-        g.out_f32 = h->logits; g.ldo = kVocab;
-        return run_gemm(h, g, EPI_GENERIC, st);
+        return lm_head_gemm(h, B, fused, st);
     }
     for (int l = 0; l < kLayers; ++l) MB_TRY(lm_layer(h, l, B, 1, true, st));
-    return lm_head(h, B, 1, 0, st);
+    return lm_head(h, B, 1, 0, fused, st);
 }
 
 int sample_and_advance(Handle* h, int B, int max_len, float temperature, float top_p, int eos_id, float* logits_dump,
                        const int* forced, cudaStream_t st) {
     SampleArgs a;
-    a.logits = h->logits; a.embed = h->w.embed; a.B = B; a.max_len = max_len; a.eos_id = eos_id;
+    a.logits = h->logits_fused ? nullptr : h->logits;
+    a.cand_val = h->cand_val; a.cand_idx = h->cand_idx; a.n_cand = kVocab / 16;
+    a.embed = h->w.embed; a.B = B; a.max_len = max_len; a.eos_id = eos_id;
     a.temperature = temperature; a.top_p = top_p; a.d_step = h->d_step; a.tokens_out = h->d_tokens;
     a.forced = forced; a.x_next = h->x; a.done = h->d_done; a.logits_dump = logits_dump;
     MB_CK(h, launch_sample(a, st));
@@ -624,7 +637,7 @@ int check_ready(Handle* h, int B) {
 
 int do_prefill(Handle* h, int B, float* logits_out, cudaStream_t st) {
     for (int l = 0; l < kLayers; ++l) MB_TRY(lm_layer(h, l, B, kPrefix, false, st));
-    MB_TRY(lm_head(h, B, kPrefix, kPrefix - 1, st));
+    MB_TRY(lm_head(h, B, kPrefix, kPrefix - 1, /*fused=*/false, st));   // step-0 logits stay available to mb_prefill callers
     if (logits_out)
         MB_CK(h, cudaMemcpyAsync(logits_out, h->logits, (size_t)B * kVocab * 4, cudaMemcpyDeviceToDevice, st));
     return 0;
@@ -649,7 +662,7 @@ int do_decode(Handle* h, int B, int max_len, float temperature, float top_p, int
             cudaGraph_t graph = nullptr;
             const long long before = h->launches;
             MB_CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            int rc = decode_step(h, B, st);
+            int rc = decode_step(h, B, /*fused=*/true, st);
             if (rc == 0) rc = sample_and_advance(h, B, max_len, temperature, top_p, eos_id, nullptr, nullptr, st);
             cudaError_t ce = cudaStreamEndCapture(st, &graph);
             if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -666,7 +679,7 @@ int do_decode(Handle* h, int B, int max_len, float temperature, float top_p, int
             MB_CK(h, cudaGraphLaunch(h->graph, st));
             h->launches += h->g_launches;
         } else {
-            MB_TRY(decode_step(h, B, st));
+            MB_TRY(decode_step(h, B, /*fused=*/logits_dump == nullptr, st));
             MB_TRY(sample_and_advance(h, B, max_len, temperature, top_p, eos_id, logits_dump, forced, st));
         }
         if ((s & 15) == 0) {          // the reference syncs every step (wrapper.py:248); poll the stop flag sparsely
@@ -758,6 +771,8 @@ static int create_body(Handle* h) {
     MB_TRY(dev_alloc(h, &h->lh_hi, M * kInter));
     MB_TRY(dev_alloc(h, &h->lh_lo, M * kInter));
     MB_TRY(dev_alloc(h, &h->logits, B * kVocab));
+    MB_TRY(dev_alloc(h, &h->cand_val, B * (kVocab / 16)));
+    MB_TRY(dev_alloc(h, &h->cand_idx, B * (kVocab / 16)));
     h->t_max = kPrefix + h->max_new;
     h->kv_layer_elems = B * kKvHeads * h->t_max * kHeadDim;
     const size_t esz = h->policy == kPolicyFast ? 2 : 4;

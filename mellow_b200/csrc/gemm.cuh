@@ -5,7 +5,7 @@
 
 namespace mb {
 
-enum { EPI_GENERIC = 0, EPI_SWIGLU = 1, EPI_QKV_ROPE = 2 };
+enum { EPI_GENERIC = 0, EPI_SWIGLU = 1, EPI_QKV_ROPE = 2, EPI_ARGMAX = 3 };
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SIGMOID = 2 };
 
 struct GemmArgs {
@@ -29,6 +29,9 @@ struct GemmArgs {
     int rows_per_seq;                                 // m = b*rows_per_seq + s
     int pos_base; const int* d_pos;                   // position = pos_base + (d_pos ? *d_pos : 0) + s
     int t_max; int kv_bf16;
+    // EPI_ARGMAX (lm_head fused with the first stage of the sampling step): per row and per 16-column group the
+    // (max logit, first arg max) candidate is written instead of the 49152 logits; sample_kernel finishes the scan.
+    float* cand_val; int* cand_idx;                   // [M][N/16]
 };
 
 // Per-(row, column pair) auxiliary operands an epilogue needs from global memory: the residual pair (EPI_GENERIC) or
@@ -77,6 +80,8 @@ __device__ __forceinline__ void epilogue_pair_r(const GemmArgs& g, int m, int n,
         // weight rows are interleaved (gate_j, up_j): down_proj(silu(gate) * up), modeling_llama.py:182-184
         float h = siluf_(v0) * v1;
         store_planes1(g.out_hi, g.out_lo, (size_t)m * g.ldp + (n >> 1), h);
+    } else if (EPI == EPI_ARGMAX) {
+        // only reachable through epilogue_row16 (N % 16 == 0 is enforced by the launcher)
     } else {
         const int b = m / g.rows_per_seq;
         const int s = m - b * g.rows_per_seq;
@@ -189,6 +194,15 @@ __device__ __forceinline__ void epilogue_row16(const GemmArgs& g, int m, int n, 
 #pragma unroll
         for (int j = 0; j < 8; ++j) hv[j] = siluf_(v[2 * j]) * v[2 * j + 1];
         store_planes8(g.out_hi, g.out_lo, (size_t)m * g.ldp + (n >> 1), hv);
+    } else if (EPI == EPI_ARGMAX) {
+        float best = v[0];
+        int bi = 0;
+#pragma unroll
+        for (int j = 1; j < 16; ++j)
+            if (v[j] > best) { best = v[j]; bi = j; }              // strict >: first index wins ties, like torch.argmax
+        const size_t c = (size_t)m * (g.N >> 4) + (n >> 4);
+        g.cand_val[c] = best;
+        g.cand_idx[c] = n + bi;
     } else {
         const int b = m / g.rows_per_seq;
         const int s = m - b * g.rows_per_seq;

@@ -323,6 +323,10 @@ cudaError_t launch_gemm_umma(const GemmArgs& g, int epi, cudaStream_t st, bool* 
         case EPI_GENERIC: e = launch_epi<EPI_GENERIC>(g, st); break;
         case EPI_SWIGLU: e = launch_epi<EPI_SWIGLU>(g, st); break;
         case EPI_QKV_ROPE: e = launch_epi<EPI_QKV_ROPE>(g, st); break;
+        case EPI_ARGMAX:
+            if ((g.N & 15) || !g.cand_val || !g.cand_idx) return cudaErrorInvalidValue;
+            e = launch_epi<EPI_ARGMAX>(g, st);
+            break;
         default: return cudaErrorInvalidValue;
     }
     *handled = (e == cudaSuccess);

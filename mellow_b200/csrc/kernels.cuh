@@ -65,7 +65,8 @@ struct DecodeAttnArgs {
 };
 cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st);
 struct SampleArgs {
-    const float* logits;            // [B,V]
+    const float* logits;            // [B,V] (null when the candidates below are used)
+    const float* cand_val; const int* cand_idx; int n_cand;   // [B][n_cand] per-16-column (max, first argmax) from lm_head
     const float* embed;             // [V,576] fp32 table (next-token embedding gather)
     int B, max_len, eos_id;
     float temperature, top_p;

@@ -321,15 +321,25 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
     pdl_trigger();
     pdl_wait();
     const int step = *a.d_step;
-    const float* lg = a.logits + (size_t)b * kVocab;
+    const float* lg = a.logits ? a.logits + (size_t)b * kVocab : nullptr;
     const float tdiv = a.temperature > 0.f ? a.temperature : 1.0f;
     float* dump = a.logits_dump ? a.logits_dump + ((size_t)step * a.B + b) * kVocab : nullptr;
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    for (int i = tid; i < kVocab; i += 1024) {
-        const float v = lg[i] / tdiv;
-        if (dump) dump[i] = v;
-        if (v > best) { best = v; bi = i; }                        // strided scan keeps the smallest index per thread
+    if (a.logits) {
+        for (int i = tid; i < kVocab; i += 1024) {
+            const float v = lg[i] / tdiv;
+            if (dump) dump[i] = v;
+            if (v > best) { best = v; bi = i; }                    // strided scan keeps the smallest index per thread
+        }
+    } else {
+        // lm_head already reduced every 16-column group to its (max, first argmax); dividing by a positive
+        // temperature cannot change the order, so the candidates are compared unscaled
+        for (int i = tid; i < a.n_cand; i += 1024) {
+            const float v = a.cand_val[(size_t)b * a.n_cand + i];
+            const int ix = a.cand_idx[(size_t)b * a.n_cand + i];
+            if (v > best || (v == best && ix < bi)) { best = v; bi = ix; }
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

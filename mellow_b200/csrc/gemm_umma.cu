@@ -187,7 +187,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         // and finished by the vectorised row epilogue; after the last tcgen05.ld the accumulator goes back to the
         // MMA warp, so the stores of tile i overlap the MMAs of tile i+1.
         const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;                            // the two warps of a quadrant alternate 32-column chunks
+        const int half = (warp - 2) >> 2;                            // the warps of a quadrant take 32-column chunks round-robin
+        constexpr int kSub = kEpiWarps / 4;
         pdl_wait();                                                  // residual reads / output writes depend on the predecessor
         int lt = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
@@ -203,12 +204,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 continue;
             }
 #pragma unroll 1
-            for (int ci = half; ci < kChunks; ci += 2) {
+            for (int ci = half; ci < kChunks; ci += kSub) {
                 const int c0 = ci * 32;
                 float v[32];
                 tmem_ld16(tacc + (uint32_t)c0, v);
                 if (c0 + 16 < BN) tmem_ld16(tacc + (uint32_t)(c0 + 16), v + 16);
-                if (ci + 2 >= kChunks) {                             // this warp has read its share: hand the accumulator back
+                if (ci + kSub >= kChunks) {                          // this warp has read its share: hand the accumulator back
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[buf]);

@@ -312,3 +312,16 @@ def test_gpu_audio_ingest_matches_torchaudio_host_path(engine, tmp_path, sr, cha
     assert got.shape == (320000,)
     err = (got - want).abs().max().item()
     assert err < 2e-6, f"sr={sr} ch={channels}: max abs err {err}"
+
+
+def test_greedy_prefix_consistency_and_batch_permutation(engine, inputs, golden):
+    """Size-independent properties of the path: (1) a shorter max_len yields a prefix of the longer run (the decode
+    graph for one max_len must not change what earlier steps emit); (2) permuting the examples of a batch permutes
+    the outputs (no row depends on its batch neighbours)."""
+    long_ = engine.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 12).cpu()
+    short = engine.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 5).cpu()
+    assert torch.equal(short, long_[:, :5])
+    perm = torch.tensor([1, 0])
+    swapped = engine.generate(inputs["wave1"][perm], inputs["wave2"][perm], inputs["ids"][perm], 12).cpu()
+    assert torch.equal(swapped, long_[perm])
+    assert long_.tolist() == golden["tokens"].tolist()

@@ -63,7 +63,8 @@ int mb_set_prefix(void* h, const float* prefix, int B, void* stream);
 /* LM prefill over the 389-token prefix, fills the KV cache; logits_out [B,49152] f32 of the last position (may be NULL) */
 int mb_prefill(void* h, int B, float* logits_out, void* stream);
 /* decode loop.  tokens_out [B,max_len] i32 (row stride max_len); *steps_out_host = number of valid columns (the
- * reference breaks once every row has emitted eos_id).  logits_dump [max_len][B][49152] f32 (NULL = off);
+ * reference breaks once every row has emitted eos_id).  Each row is valid up to and including its first eos_id: the
+ * reference discards what follows (wrapper.py:254), and finished rows stop streaming their KV cache here.  logits_dump [max_len][B][49152] f32 (NULL = off);
  * forced_tokens [B,max_len] i32 (NULL = off): teacher forcing, tokens_out still records the model's own argmax. */
 int mb_decode(void* h, int B, int max_len, float temperature, float top_p, int eos_id, int* tokens_out,
               int* steps_out_host, float* logits_dump, const int* forced_tokens, void* stream);

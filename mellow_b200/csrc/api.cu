@@ -388,13 +388,14 @@ inline int decode_nsplit(const Handle* h, int B) {
     return ns < 1 ? 1 : (ns > kMaxAttnSplit ? kMaxAttnSplit : ns);
 }
 
-int run_decode_attention(Handle* h, int l, int B, cudaStream_t st) {
+int run_decode_attention(Handle* h, int l, int B, cudaStream_t st, bool skip_done = true) {
     DecodeAttnArgs a;
     a.q = h->q; a.kc = kv_layer(h, h->kcache, l); a.vc = kv_layer(h, h->vcache, l);
     a.kv_bf16 = h->policy == kPolicyFast; a.B = B; a.t_max = h->t_max;
     a.nsplit = decode_nsplit(h, B);
     a.tps = ((h->t_max + 63) / 64 + a.nsplit - 1) / a.nsplit;
     a.ctx_base = kPrefix; a.d_step = h->d_step;
+    a.done = skip_done ? h->d_done : nullptr;
     a.part_acc = h->part_acc; a.part_ml = h->part_ml;
     a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
     MB_CK(h, launch_decode_attention(a, st));
@@ -968,7 +969,7 @@ int mb_bench_decode_attention(void* hv, int B, int ctx, int iters, void* stream)
     const int step = ctx - kPrefix;
     MB_CK(h, cudaMemcpyAsync(h->d_step, &step, sizeof(int), cudaMemcpyHostToDevice, st));
     for (int i = 0; i < iters; ++i) {
-        MB_TRY(run_decode_attention(h, i % kLayers, B, st));
+        MB_TRY(run_decode_attention(h, i % kLayers, B, st, /*skip_done=*/false));
     }
     return 0;
 }

@@ -60,6 +60,7 @@ struct DecodeAttnArgs {
     int kv_bf16, B, t_max, nsplit;
     int tps;                           // key tiles (64 keys) owned by each split: ceil(ceil(t_max/64)/nsplit)
     int ctx_base; const int* d_step;   // ctx = ctx_base + *d_step  (keys 0..ctx-1)
+    const int* done;                   // optional [B]: rows that already emitted the stop token skip their K/V stream
     float* part_acc; float* part_ml;   // [B][9][nsplit][64], [B][9][nsplit][2]
     bf16* out_hi; bf16* out_lo;        // [B,576]
 };

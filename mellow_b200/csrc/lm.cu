@@ -169,6 +169,10 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
     if (early0) load_tile(0, t_begin, a.ctx_base);
     if (early1) load_tile(1, t_begin + 1, a.ctx_base);
     pdl_wait();
+    // a row that has emitted the stop token is finished (the reference cuts its text there,
+    // wrapper.py:254); its later tokens are never read, so its K/V stream -- the dominant decode traffic -- is skipped.
+    // The uniform exit happens after the cp.async groups above are drained by the hardware at CTA exit.
+    if (a.done && a.done[b]) { cp_async_commit(); cp_async_wait<0>(); return; }
     const int ctx = a.ctx_base + (a.d_step ? *a.d_step : 0);
     const int ntiles = (ctx + 63) >> 6;
     const int t_end = min(ntiles, t_begin + a.tps);
@@ -294,6 +298,7 @@ __global__ void __launch_bounds__(64) decode_combine_kernel(const DecodeAttnArgs
     const size_t base = ((size_t)b * kHeads + h) * a.nsplit;
     pdl_trigger();
     pdl_wait();
+    if (a.done && a.done[b]) return;                               // finished row: partials were not produced
     float m = -INFINITY;
     for (int s = 0; s < a.nsplit; ++s) m = fmaxf(m, a.part_ml[(base + s) * 2]);
     float num = 0.f, den = 0.f;

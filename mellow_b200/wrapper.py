@@ -115,6 +115,8 @@ class MellowWrapper:
         examples: list of [audio path 1, audio path 2, text prompt]; max_len: maximum number of generated tokens;
         top_p / temperature: accepted for signature parity -- like the reference, the decision is an argmax and is
         independent of both; stop_token: token that ends a row; audio_resample: resample inputs to 32 kHz."""
+        if len(examples) == 0:
+            return []
         paths1 = [e[0] for e in examples]
         paths2 = [e[1] for e in examples]
         prompts = [e[2] for e in examples]

@@ -325,3 +325,17 @@ def test_greedy_prefix_consistency_and_batch_permutation(engine, inputs, golden)
     swapped = engine.generate(inputs["wave1"][perm], inputs["wave2"][perm], inputs["ids"][perm], 12).cpu()
     assert torch.equal(swapped, long_[perm])
     assert long_.tolist() == golden["tokens"].tolist()
+
+
+def test_finished_rows_do_not_disturb_the_others(engine, oracle_taps, golden):
+    """Row f3: once a row has emitted the stop id its KV stream is skipped; the other rows must be unaffected and the
+    finished row must be exact up to and including its stop token."""
+    prefix = oracle_taps["prefix"]
+    stop = int(golden["tokens"][0, 1])                       # row 0 emits it at step 1; row 1 never does
+    assert stop not in golden["tokens"][1].tolist()
+    engine.set_prefix(prefix)
+    engine.prefill(2, want_logits=False)
+    toks = engine.decode(2, 12, eos_id=stop).cpu()
+    assert toks.shape == (2, 12)                             # row 1 never stops, so the loop runs to max_len
+    assert toks[1].tolist() == golden["tokens"][1].tolist()
+    assert toks[0, :2].tolist() == golden["tokens"][0, :2].tolist()

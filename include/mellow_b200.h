@@ -45,6 +45,14 @@ const char* mb_last_error(void* h); /* h may be NULL for mb_create failures */
 int mb_bind_weights(void* h, const void* dev_arena, long long nbytes);
 long long mb_workspace_bytes(void* h);
 int mb_set_gemm_engine(void* h, int engine); /* 0 = mma.sync bring-up engine, 1 = tcgen05 engine where a tile fits */
+/* decode row groups: the batch is cut into `groups` contiguous row groups whose per-layer kernel chains run on
+ * concurrent streams (1..4; 0 = automatic: 2 from 96 rows up).  Results do not depend on it (rows are independent). */
+int mb_set_decode_groups(void* h, int groups);
+/* profiling aid: dev_trace_buf = {u32 n; u32 cap; {u64 globaltimer_ns; u32 id*16+phase; u32 smid} ev[cap]} in device
+ * memory (NULL = off).  The decode-step kernels stamp entry / dependency-wait-return / exit of their first CTA and
+ * the exit of their last CTA; id = kind*1000 + group*100 + layer (kind 1 QKV, 2 attention, 3 o_proj, 4 add+norm,
+ * 5 gate/up, 6 down, 7 add+norm, 8 lm_head).  tools/decode_timeline.py prints the timeline. */
+int mb_set_trace(void* h, void* dev_trace_buf);
 long long mb_kernel_launches(void* h);       /* kernels launched by this handle so far (counting graph replays) */
 
 /* ---- stages (each can be profiled / parity-checked in isolation) ---- */
@@ -52,6 +60,13 @@ long long mb_kernel_launches(void* h);       /* kernels launched by this handle 
 int mb_frontend(void* h, const float* wave, int n_clips, float* logmel_out, float* bn_out, void* stream);
 /* wave1, wave2 [B,320000] -> rows_out [2][B][33][576] f32 (may be NULL; the handle keeps its own copy for mb_prefix) */
 int mb_encode(void* h, const float* wave1, const float* wave2, int B, float* rows_out, void* stream);
+/* SURVEY 8 row f4 -- the encoder outputs the reference returns as od1/od2 (mellow/model/mellow.py:100-108,
+ * htsat.py:782-796,950-955) for the n_clips = 2*B clips of the last mb_encode / mb_generate (audio1 rows first):
+ * clipwise_out [n,527] = sigmoid(mean_t conv), framewise_rows_out [n,32,527] = sigmoid(conv) (the reference repeats
+ * each row 32x to 1024 frames), latent_out [n,768], frame_embed_out [n,32,768] = c2l(frame rows) (rows 1.. of the
+ * reference's `embedding`, before the 32x repeat).  Any pointer may be NULL. */
+int mb_encode_heads(void* h, int n_clips, float* clipwise_out, float* framewise_rows_out, float* latent_out,
+                    float* frame_embed_out, void* stream);
 /* debug tap: run the encoder on `wave` [n_clips,320000] and copy the residual stream after stage `stage`:
  * 0 = patch embed [n,4096,96], 1..4 = after Swin stage (incl. merging) [n,1024,192] [n,256,384] [n,64,768] [n,64,768],
  * 5 = latent [n,768] followed by c2l frame rows [n,32,768] */

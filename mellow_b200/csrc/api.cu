@@ -12,16 +12,25 @@
 
 namespace mb {
 
+namespace { thread_local int g_pdl_off = 0; }
 bool pdl_enabled() {
     static const bool on = getenv("MB_NO_PDL") == nullptr;
-    return on;
+    return on && g_pdl_off == 0;
 }
+// Scope in which kernels are launched with a full (non-programmatic) dependency: the first kernel after a stream
+// fork / join of the row-group decode step, whose predecessors are event edges rather than one kernel.
+struct PdlOff {
+    bool on;
+    explicit PdlOff(bool enable = true) : on(enable) { if (on) ++g_pdl_off; }
+    ~PdlOff() { if (on) --g_pdl_off; }
+};
 
 cudaError_t launch_gemm_umma(const GemmArgs& g, int epi, cudaStream_t st, bool* handled);   // gemm_umma.cu
 
 namespace {
 
-constexpr int kMaxSplitK = 8;
+constexpr int kMaxSplitK = 12;
+constexpr int kMaxGroups = 4;
 constexpr int kDepths[4] = {2, 2, 6, 2};
 constexpr int kHeadsPerStage[4] = {4, 8, 16, 32};
 inline int stage_dim(int i) { return kEmbed << i; }
@@ -174,12 +183,18 @@ struct Handle {
     int *d_tokens = nullptr, *d_done = nullptr, *d_step = nullptr, *d_stop = nullptr, *d_ids = nullptr;
     float *wave_stage = nullptr;
     int prefix_B = 0;
+    int enc_clips = 0;                   // clips of the last full encoder pass (its tail buffers feed mb_encode_heads)
     // decode graph cache
     cudaGraphExec_t graph = nullptr;
     int g_B = 0, g_max_len = 0, g_eos = 0, g_launches = 0;
     float g_temp = 0.f;
     cudaStream_t g_stream = nullptr;
     cudaStream_t own_stream = nullptr;   // used when the caller passes NULL (the legacy stream cannot be graph-captured)
+    // row-group decode: groups 1.. run on their own streams, forked from / joined to the caller's stream by events
+    cudaStream_t grp_stream[kMaxGroups - 1] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups - 1] = {}, ev_attn[kMaxGroups] = {};
+    int groups = 0;                      // mb_set_decode_groups: 0 = automatic
+    TraceBuf* trace = nullptr;           // mb_set_trace: optional in-kernel timeline of the decode kernels
 };
 
 inline cudaStream_t pick_stream(Handle* h, void* stream) { return stream ? (cudaStream_t)stream : h->own_stream; }
@@ -226,10 +241,19 @@ GemmArgs gemm_base(const Handle* h, const bf16* a_hi, const bf16* a_lo, int lda,
     g.W_hi = wgt.hi; g.W_lo = lo_of(h, wgt.lo); g.ldw = ldw;
     g.M = M; g.N = N; g.K = K;
     g.passes = h->policy == kPolicySplit ? 3 : 1;
+    static const int dbg = getenv("MB_GEMM_DBG") ? atoi(getenv("MB_GEMM_DBG")) : 0;
+    g.dbg = M <= 128 ? dbg : 0;
     return g;
 }
 
 int run_gemm(Handle* h, const GemmArgs& g, int epi, cudaStream_t st) {
+    if (h->engine == 1 && g.resident) {
+        const int bn = g.bn_hint ? g.bn_hint : (g.N >= 2048 ? 32 : 16);
+        cudaError_t e = launch_gemm_skinny(g, epi, bn, st);
+        if (e == cudaSuccess) { h->launches++; return 0; }
+        if (e != cudaErrorNotSupported) MB_CK(h, e);
+        (void)cudaGetLastError();
+    }
     if (h->engine == 1) {
         bool handled = false;
         MB_CK(h, launch_gemm_umma(g, epi, st, &handled));
@@ -345,6 +369,7 @@ int encoder_body(Handle* h, int n_clips, int stop_stage, float* tap_out, float* 
     }
     MB_CK(h, launch_assemble33(h->latent, h->frames, n_clips, h->a33_hi, lo_of(h, h->a33_lo), st));
     h->launches++;
+    h->enc_clips = n_clips;
     const int M33 = n_clips * kAudioRows;
     {
         GemmArgs g = gemm_base(h, h->a33_hi, h->a33_lo, kEncOut, h->w.proj1, kEncOut, M33, kProj, kEncOut);
@@ -388,55 +413,126 @@ inline int decode_nsplit(const Handle* h, int B) {
     return ns < 1 ? 1 : (ns > kMaxAttnSplit ? kMaxAttnSplit : ns);
 }
 
-int run_decode_attention(Handle* h, int l, int B, cudaStream_t st, bool skip_done = true) {
+// Tiling of the split-K decode GEMMs (gemm_umma.cu launch_epi): N-tile width x K split.  The default follows the
+// measured rule "a decode GEMM costs what its CTAs' tcgen05.mma COUNT costs": wide tiles, 1-2 k-blocks per CTA.
+// MB_DEC_TILING=0 restores the 16-column tiles with split 3 / 4.
+struct DecodeTiling { int o_bn, o_split, down_bn, down_split, resident; };
+const DecodeTiling& decode_tiling() {
+    static const DecodeTiling t = [] {
+        const char* e = getenv("MB_DEC_TILING");
+        const int mode = e ? atoi(e) : 0;
+        const char* r = getenv("MB_DEC_RESIDENT");
+        const int res = r ? atoi(r) : 1;
+        if (mode == 1) return DecodeTiling{48, 9, 48, 12, res};
+        if (mode == 2) return DecodeTiling{64, 9, 64, 12, res};
+        if (mode == 3) return DecodeTiling{48, 9, 48, 6, res};
+        if (mode == 4) return DecodeTiling{48, 3, 48, 6, res};
+        return DecodeTiling{0, 3, 0, 4, res};
+    }();
+    return t;
+}
+
+// Row groups of the decode step (see decode_step).  MB_DECODE_GROUPS / MB_DECODE_COMPACT override the defaults for
+// A/B measurements.
+int decode_groups(const Handle* h, int B) {
+    static const int forced = getenv("MB_DECODE_GROUPS") ? atoi(getenv("MB_DECODE_GROUPS")) : 0;
+    int G = h->groups > 0 ? h->groups : (forced > 0 ? forced : 1);
+    if (G > kMaxGroups) G = kMaxGroups;
+    if (G > B) G = B;
+    if (h->engine != 1) G = 1;
+    return G < 1 ? 1 : G;
+}
+int decode_stagger(int G) {
+    static const int forced = getenv("MB_DECODE_STAGGER") ? atoi(getenv("MB_DECODE_STAGGER")) : -1;
+    return G > 1 ? (forced >= 0 ? forced : 0) : 0;
+}
+int decode_compact(int G) {
+    static const int forced = getenv("MB_DECODE_COMPACT") ? atoi(getenv("MB_DECODE_COMPACT")) : -1;
+    return forced >= 0 ? forced : 1;
+}
+
+// Rows [r0, r0+n) of the batch; n_all = rows of the whole step (all row groups), which sets the key split.
+int run_decode_attention(Handle* h, int l, int r0, int n, int n_all, cudaStream_t st, bool skip_done = true) {
     DecodeAttnArgs a;
-    a.q = h->q; a.kc = kv_layer(h, h->kcache, l); a.vc = kv_layer(h, h->vcache, l);
-    a.kv_bf16 = h->policy == kPolicyFast; a.B = B; a.t_max = h->t_max;
-    a.nsplit = decode_nsplit(h, B);
+    const size_t esz = h->policy == kPolicyFast ? 2 : 4;
+    const size_t kv_off = (size_t)r0 * kKvHeads * h->t_max * kHeadDim * esz;
+    a.q = h->q + (size_t)r0 * kHidden;
+    a.kc = reinterpret_cast<char*>(kv_layer(h, h->kcache, l)) + kv_off;
+    a.vc = reinterpret_cast<char*>(kv_layer(h, h->vcache, l)) + kv_off;
+    a.kv_bf16 = h->policy == kPolicyFast; a.B = n; a.t_max = h->t_max;
+    a.nsplit = decode_nsplit(h, n_all);
     a.tps = ((h->t_max + 63) / 64 + a.nsplit - 1) / a.nsplit;
     a.ctx_base = kPrefix; a.d_step = h->d_step;
-    a.done = skip_done ? h->d_done : nullptr;
-    a.part_acc = h->part_acc; a.part_ml = h->part_ml;
-    a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
+    a.done = skip_done ? h->d_done + r0 : nullptr;
+    a.part_acc = h->part_acc + (size_t)r0 * kHeads * a.nsplit * kHeadDim;
+    a.part_ml = h->part_ml + (size_t)r0 * kHeads * a.nsplit * 2;
+    a.out_hi = h->la_hi + (size_t)r0 * kHidden; a.out_lo = lo_of(h, h->la_lo + (size_t)r0 * kHidden);
+    a.trace = h->trace; a.trace_id = 2000 + (r0 ? 100 : 0) + l;
     MB_CK(h, launch_decode_attention(a, st));
     h->launches += a.nsplit == 1 ? 1 : 2;
     return 0;
 }
+int run_decode_attention(Handle* h, int l, int B, cudaStream_t st, bool skip_done = true) {
+    return run_decode_attention(h, l, 0, B, B, st, skip_done);
+}
 
-// Decode layer for B <= 128 rows (one M tile).  The residual stream update and the next RMSNorm are fused into
-// add_rmsnorm_kernel, which also reduces the split-K partial sums of o_proj / down_proj in a fixed order.
-// On entry la_hi/la_lo hold RMSNorm(x) with this layer's input_layernorm; on exit they hold RMSNorm(x) with
-// `next_norm` (the next layer's input_layernorm, or the final model norm).
-int lm_layer_decode_fused(Handle* h, int l, int B, const float* next_norm, cudaStream_t st) {
+// Decode layer for one row group [r0, r0+n), n <= 128 rows (one M tile).  The residual stream update and the next
+// RMSNorm are fused into add_rmsnorm_kernel, which also reduces the split-K partial sums of o_proj / down_proj in a
+// fixed order.  On entry la_hi/la_lo hold RMSNorm(x) with this layer's input_layernorm; on exit they hold RMSNorm(x)
+// with `next_norm` (the next layer's input_layernorm, or the final model norm).  Every row is independent of every
+// other row, so the values are identical however the batch is cut into groups.
+int lm_layer_decode_fused(Handle* h, int l, int r0, int n, int n_all, int compact, float* partial,
+                          const float* next_norm, cudaStream_t st, cudaEvent_t attn_wait = nullptr,
+                          cudaEvent_t attn_record = nullptr) {
     const LmLayerW& k = h->w.layer[l];
+    const DecodeTiling& tl = decode_tiling();
+    const size_t esz = h->policy == kPolicyFast ? 2 : 4;
+    const size_t kv_off = (size_t)r0 * kKvHeads * h->t_max * kHeadDim * esz;
+    float* x = h->x + (size_t)r0 * kHidden;
+    bf16* la_hi = h->la_hi + (size_t)r0 * kHidden; bf16* la_lo = h->la_lo + (size_t)r0 * kHidden;
+    bf16* lh_hi = h->lh_hi + (size_t)r0 * kInter; bf16* lh_lo = h->lh_lo + (size_t)r0 * kInter;
     {
-        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.qkv, kHidden, B, kQkvDim, kHidden);
-        g.q_out = h->q;
-        g.k_cache = kv_layer(h, h->kcache, l); g.v_cache = kv_layer(h, h->vcache, l);
+        GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.qkv, kHidden, n, kQkvDim, kHidden);
+        g.compact = compact; g.resident = tl.resident;
+        g.trace = h->trace; g.trace_id = 1000 + (r0 ? 100 : 0) + l;
+        g.q_out = h->q + (size_t)r0 * kHidden;
+        g.k_cache = reinterpret_cast<char*>(kv_layer(h, h->kcache, l)) + kv_off;
+        g.v_cache = reinterpret_cast<char*>(kv_layer(h, h->vcache, l)) + kv_off;
         g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
         g.rows_per_seq = 1; g.pos_base = kPrefix - 1; g.d_pos = h->d_step;
         g.t_max = h->t_max; g.kv_bf16 = h->policy == kPolicyFast;
         MB_TRY(run_gemm(h, g, EPI_QKV_ROPE, st));
     }
-    MB_TRY(run_decode_attention(h, l, B, st));
+    if (attn_wait) MB_CK(h, cudaStreamWaitEvent(st, attn_wait, 0));
     {
-        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.o, kHidden, B, kHidden, kHidden);
-        g.split_k = 3; g.partial = h->gemm_partial;
+        PdlOff off(attn_wait != nullptr);                  // two predecessors: the QKV kernel and the other group's event
+        MB_TRY(run_decode_attention(h, l, r0, n, n_all, st));
+    }
+    if (attn_record) MB_CK(h, cudaEventRecord(attn_record, st));
+    {
+        GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.o, kHidden, n, kHidden, kHidden);
+        g.compact = compact; g.resident = tl.resident;
+        g.trace = h->trace; g.trace_id = 3000 + (r0 ? 100 : 0) + l;
+        g.split_k = tl.o_split; g.bn_hint = tl.o_bn; g.partial = partial;
         MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
     }
-    MB_CK(h, launch_add_rmsnorm(h->x, h->gemm_partial, 3, B, k.ln2, h->la_hi, lo_of(h, h->la_lo), st));
+    MB_CK(h, launch_add_rmsnorm(x, partial, tl.o_split, n, k.ln2, la_hi, lo_of(h, la_lo), st, h->trace, 4000 + (r0 ? 100 : 0) + l));
     h->launches++;
     {
-        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.gu, kHidden, B, 2 * kInter, kHidden);
-        g.out_hi = h->lh_hi; g.out_lo = lo_of(h, h->lh_lo); g.ldp = kInter;
+        GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.gu, kHidden, n, 2 * kInter, kHidden);
+        g.compact = compact; g.resident = tl.resident;
+        g.trace = h->trace; g.trace_id = 5000 + (r0 ? 100 : 0) + l;
+        g.out_hi = lh_hi; g.out_lo = lo_of(h, lh_lo); g.ldp = kInter;
         MB_TRY(run_gemm(h, g, EPI_SWIGLU, st));
     }
     {
-        GemmArgs g = gemm_base(h, h->lh_hi, h->lh_lo, kInter, k.down, kInter, B, kHidden, kInter);
-        g.split_k = 4; g.partial = h->gemm_partial;
+        GemmArgs g = gemm_base(h, lh_hi, lh_lo, kInter, k.down, kInter, n, kHidden, kInter);
+        g.compact = compact; g.resident = tl.resident;
+        g.trace = h->trace; g.trace_id = 6000 + (r0 ? 100 : 0) + l;
+        g.split_k = tl.down_split; g.bn_hint = tl.down_bn; g.partial = partial;
         MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
     }
-    MB_CK(h, launch_add_rmsnorm(h->x, h->gemm_partial, 4, B, next_norm, h->la_hi, lo_of(h, h->la_lo), st));
+    MB_CK(h, launch_add_rmsnorm(x, partial, tl.down_split, n, next_norm, la_hi, lo_of(h, la_lo), st, h->trace, 7000 + (r0 ? 100 : 0) + l));
     h->launches++;
     return 0;
 }
@@ -563,6 +659,7 @@ int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_
 // the [B,49152] logits (the decode loop); otherwise the full fp32 logits (parity dumps, mb_prefill).
 int lm_head_gemm(Handle* h, int B, bool fused, cudaStream_t st) {
     GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, h->w.head, kHidden, B, kVocab, kHidden);
+    g.trace = h->trace; g.trace_id = 8000;
     fused = fused && h->engine == 1;                      // the argmax epilogue exists in the row-per-thread engine only
     h->logits_fused = fused;
     if (fused) {
@@ -606,10 +703,48 @@ int decode_step(Handle* h, int B, bool fused, cudaStream_t st) {
         return lm_head_gemm(h, B, fused, st);
     }
     if (B <= 128 && getenv("MB_DECODE_UNFUSED") == nullptr) {
-        MB_CK(h, launch_add_rmsnorm(h->x, nullptr, 0, B, h->w.layer[0].ln1, h->la_hi, lo_of(h, h->la_lo), st));
-        h->launches++;
-        for (int l = 0; l < kLayers; ++l)
-            MB_TRY(lm_layer_decode_fused(h, l, B, l + 1 < kLayers ? h->w.layer[l + 1].ln1 : h->w.lm_norm, st));
+        // Row groups: the batch is cut into G contiguous row groups whose per-layer kernel chains (7 PDL-linked
+        // kernels per layer) run on G streams.  Each chain is latency-bound (a dependent kernel every ~6 us) except
+        // its HBM-bound attention kernel, so while one group streams its K/V the other groups' GEMM / norm phases
+        // run; the compact GEMM variants keep two CTAs per SM so that the chains do not queue behind each other's
+        // shared memory.  Rows never interact, so the result does not depend on G.  lm_head runs once over all rows
+        // after the join (its 113 MB weight stream is the cost, not the rows).
+        const int G = decode_groups(h, B);
+        const int compact = decode_compact(G);
+        // Chains that start together stay in lock-step (all groups stream K/V at the same time, then all wait on
+        // their GEMM phases), which gains nothing.  stagger 1: group g starts when group g-1 has finished its first
+        // attention, half a layer period later.  stagger 2: the attention kernels of a layer are chained through
+        // events (g waits for g-1, group 0 of the next layer for the last group), so exactly one group streams K/V at
+        // any time while the others are in their GEMM / norm phases.
+        const int stagger = decode_stagger(G);
+        if (G > 1) MB_CK(h, cudaEventRecord(h->ev_fork, st));
+        for (int gi = 1; gi < G; ++gi) MB_CK(h, cudaStreamWaitEvent(h->grp_stream[gi - 1], h->ev_fork, 0));
+        for (int l = 0; l < kLayers; ++l) {
+            for (int gi = 0; gi < G; ++gi) {
+                const int r0 = (int)(((long long)B * gi) / G), n = (int)(((long long)B * (gi + 1)) / G) - r0;
+                cudaStream_t sg = gi == 0 ? st : h->grp_stream[gi - 1];
+                float* partial = h->gemm_partial + (size_t)gi * kMaxSplitK * 128 * kHidden;
+                if (l == 0) {
+                    if (stagger == 1 && gi > 0) MB_CK(h, cudaStreamWaitEvent(sg, h->ev_attn[gi - 1], 0));
+                    PdlOff off(gi > 0);                     // a forked chain starts behind event edges, not a kernel
+                    MB_CK(h, launch_add_rmsnorm(h->x + (size_t)r0 * kHidden, nullptr, 0, n, h->w.layer[0].ln1,
+                                                h->la_hi + (size_t)r0 * kHidden, lo_of(h, h->la_lo + (size_t)r0 * kHidden), sg));
+                    h->launches++;
+                }
+                cudaEvent_t wait_ev = nullptr, rec_ev = nullptr;
+                if (stagger == 2) {
+                    wait_ev = gi > 0 ? h->ev_attn[gi - 1] : (l > 0 ? h->ev_attn[G - 1] : nullptr);
+                    rec_ev = h->ev_attn[gi];
+                } else if (stagger == 1 && l == 0 && gi + 1 < G) {
+                    rec_ev = h->ev_attn[gi];
+                }
+                MB_TRY(lm_layer_decode_fused(h, l, r0, n, B, compact, partial,
+                                             l + 1 < kLayers ? h->w.layer[l + 1].ln1 : h->w.lm_norm, sg, wait_ev, rec_ev));
+            }
+        }
+        for (int gi = 1; gi < G; ++gi) MB_CK(h, cudaEventRecord(h->ev_join[gi - 1], h->grp_stream[gi - 1]));
+        for (int gi = 1; gi < G; ++gi) MB_CK(h, cudaStreamWaitEvent(st, h->ev_join[gi - 1], 0));
+        PdlOff off(G > 1);                                  // after the join lm_head has G predecessors
         return lm_head_gemm(h, B, fused, st);
     }
     for (int l = 0; l < kLayers; ++l) MB_TRY(lm_layer(h, l, B, 1, true, st));
@@ -733,6 +868,13 @@ void mb_destroy(void* hv) {
     cudaSetDevice(h->device);
     if (h->graph) cudaGraphExecDestroy(h->graph);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (int i = 0; i < kMaxGroups - 1; ++i) {
+        if (h->grp_stream[i]) cudaStreamDestroy(h->grp_stream[i]);
+        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    for (int i = 0; i < kMaxGroups; ++i)
+        if (h->ev_attn[i]) cudaEventDestroy(h->ev_attn[i]);
     for (void* p : h->allocs) cudaFree(p);
     delete h;
 }
@@ -783,7 +925,13 @@ static int create_body(Handle* h) {
     h->kcache = kc; h->vcache = vc;
     MB_TRY(dev_alloc(h, &h->part_acc, B * kHeads * kMaxAttnSplit * kHeadDim));
     MB_TRY(dev_alloc(h, &h->part_ml, B * kHeads * kMaxAttnSplit * 2));
-    MB_TRY(dev_alloc(h, &h->gemm_partial, (size_t)kMaxSplitK * 128 * kHidden));
+    MB_TRY(dev_alloc(h, &h->gemm_partial, (size_t)kMaxGroups * kMaxSplitK * 128 * kHidden));
+    for (int i = 0; i < kMaxGroups - 1; ++i) {
+        MB_CK(h, cudaStreamCreateWithFlags(&h->grp_stream[i], cudaStreamNonBlocking));
+        MB_CK(h, cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
+    }
+    MB_CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < kMaxGroups; ++i) MB_CK(h, cudaEventCreateWithFlags(&h->ev_attn[i], cudaEventDisableTiming));
     MB_TRY(dev_alloc(h, &h->chain_bar, (size_t)kLayers * 8));
     MB_TRY(dev_alloc(h, &h->d_tokens, B * h->max_new));
     MB_TRY(dev_alloc(h, &h->d_done, B));
@@ -845,6 +993,19 @@ int mb_set_gemm_engine(void* hv, int engine) {
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
     return 0;
 }
+int mb_set_decode_groups(void* hv, int groups) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    if (groups < 0 || groups > kMaxGroups) return fail(h, "decode row groups must be 0 (automatic) .. 4");
+    h->groups = groups;
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    return 0;
+}
+int mb_set_trace(void* hv, void* dev_trace_buf) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    h->trace = reinterpret_cast<TraceBuf*>(dev_trace_buf);
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    return 0;
+}
 long long mb_kernel_launches(void* hv) { return reinterpret_cast<Handle*>(hv)->launches; }
 
 int mb_frontend(void* hv, const float* wave, int n_clips, float* logmel_out, float* bn_out, void* stream) {
@@ -863,6 +1024,31 @@ int mb_encode(void* hv, const float* wave1, const float* wave2, int B, float* ro
     MB_TRY(frontend(h, wave1, B, nullptr, h->bn, st));
     MB_TRY(frontend(h, wave2, B, nullptr, h->bn + (size_t)B * kFrames * kMels, st));
     return encoder_body(h, 2 * B, -1, nullptr, rows_out, st);
+}
+
+// SURVEY 8 row f4 (reference mellow.py:100-108 returns od1/od2 = the encoder's output dict; htsat.py:782-796,950-955).
+// The TSCAM conv is re-run without its sigmoid on the im2col rows the last encoder pass left in the workspace (a
+// 0.12 TFLOP GEMM, only when a caller asks for the heads), then heads_kernel forms the two classification outputs.
+int mb_encode_heads(void* hv, int n_clips, float* clipwise_out, float* framewise_rows_out, float* latent_out,
+                    float* frame_embed_out, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    if (!h->bound) return fail(h, "weights not bound");
+    if (n_clips < 1 || n_clips != h->enc_clips) return fail(h, "mb_encode_heads: call it after mb_encode / mb_generate with n_clips = 2*B of that call");
+    cudaSetDevice(h->device);
+    cudaStream_t st = pick_stream(h, stream);
+    if (clipwise_out || framewise_rows_out) {
+        float* logits = h->qkv;                            // encoder scratch, free after the Swin stages
+        GemmArgs g = gemm_base(h, h->col_hi, h->col_lo, 6 * kEncOut, h->w.tscam, 6 * kEncOut, n_clips * 32, kClasses, 6 * kEncOut);
+        g.bias = h->w.tscam_b; g.out_f32 = logits; g.ldo = kClassesPad;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+        MB_CK(h, launch_heads(logits, kClassesPad, n_clips, clipwise_out, framewise_rows_out, st));
+        h->launches++;
+    }
+    if (latent_out)
+        MB_CK(h, cudaMemcpyAsync(latent_out, h->latent, (size_t)n_clips * kEncOut * 4, cudaMemcpyDeviceToDevice, st));
+    if (frame_embed_out)
+        MB_CK(h, cudaMemcpyAsync(frame_embed_out, h->frames, (size_t)n_clips * 32 * kEncOut * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
 }
 
 int mb_encode_tap(void* hv, const float* wave, int n_clips, int stage, float* out, void* stream) {

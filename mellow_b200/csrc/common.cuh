@@ -104,6 +104,42 @@ __device__ __forceinline__ void cp_async_wait() {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// Optional in-kernel timeline (mb_set_trace).  The first and the last CTA of a launch each claim one 16-slot record with
+// a single atomic at kernel entry (off the critical path: before the programmatic-dependency wait) and afterwards
+// stamp %globaltimer into that record with plain stores, so the stamps do not stall the threads they measure.
+// A null buffer (the default) costs one predicate per stamp.
+struct TraceEvent { unsigned long long t; unsigned int id; unsigned int sm; };
+struct TraceBuf { unsigned int n; unsigned int cap; TraceEvent ev[1]; };   // n, cap count 16-event records
+enum { TR_ENTRY = 0, TR_WAITED = 1, TR_EXIT = 2, TR_EXIT_LAST = 3 };
+constexpr unsigned kTraceNone = 0xffffffffu;
+__device__ __forceinline__ void trace_put(TraceBuf* tb, unsigned rec, unsigned id, unsigned phase) {
+    if (tb == nullptr || rec == kTraceNone) return;
+    unsigned long long t;
+    unsigned sm;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+    TraceEvent* e = &tb->ev[(size_t)rec * 16 + phase];
+    e->t = t; e->id = (id << 4) | phase; e->sm = sm;
+}
+__device__ __forceinline__ bool first_cta() { return (blockIdx.x | blockIdx.y | blockIdx.z) == 0; }
+__device__ __forceinline__ bool last_cta() {
+    return blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1;
+}
+// called by one thread of the first / last CTA at kernel entry; returns the record index (kTraceNone when not traced)
+__device__ __forceinline__ unsigned trace_open(TraceBuf* tb, unsigned id) {
+    if (tb == nullptr || !(first_cta() || last_cta())) return kTraceNone;
+    const unsigned rec = atomicAdd(&tb->n, 1u);
+    if (rec >= tb->cap) return kTraceNone;
+    trace_put(tb, rec, id, first_cta() ? TR_ENTRY : 15);
+    return rec;
+}
+// exit stamps: phase TR_EXIT from the first CTA, TR_EXIT_LAST from the last CTA (both when the grid has one CTA)
+__device__ __forceinline__ void trace_close(TraceBuf* tb, unsigned rec, unsigned id) {
+    if (tb == nullptr || rec == kTraceNone) return;
+    if (first_cta()) trace_put(tb, rec, id, TR_EXIT);
+    if (last_cta()) trace_put(tb, rec, id, TR_EXIT_LAST);
+}
+
 // KV-cache element types
 __device__ __forceinline__ float kv_load(const float* p) { return *p; }
 __device__ __forceinline__ float kv_load(const bf16* p) { return __bfloat162float(*p); }

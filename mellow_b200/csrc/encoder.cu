@@ -199,6 +199,26 @@ __global__ void __launch_bounds__(256) assemble33_kernel(const float* __restrict
     for (int c = threadIdx.x; c < kEncOut; c += 256) store_planes1(a_hi, a_lo, o + c, src[c]);
 }
 
+// the classification heads the path computes but generate() discards (htsat.py:774-796, loss_type
+// "clip_bce").  logits [N*32, ld] are the TSCAM conv outputs before the sigmoid:
+//   framewise[n,t,c] = sigmoid(logit[n,t,c])                 (the 32 unique rows; the reference repeats each 32x)
+//   clipwise[n,c]    = sigmoid(mean_t logit[n,t,c])          (avgpool over time, then sigmoid)
+__global__ void __launch_bounds__(256) heads_kernel(const float* __restrict__ logits, int ld, float* __restrict__ clipwise,
+                                                    float* __restrict__ framewise) {
+    const int n = blockIdx.x;
+    pdl_trigger();
+    pdl_wait();
+    for (int c = threadIdx.x; c < kClasses; c += 256) {
+        float s = 0.f;
+        for (int t = 0; t < 32; ++t) {
+            const float v = logits[((size_t)n * 32 + t) * ld + c];
+            s += v;
+            if (framewise) framewise[((size_t)n * 32 + t) * kClasses + c] = sigmoidf_(v);
+        }
+        if (clipwise) clipwise[(size_t)n * kClasses + c] = sigmoidf_(s * (1.0f / 32.0f));
+    }
+}
+
 __global__ void __launch_bounds__(256) gelu_planes_kernel(const float* __restrict__ x, size_t n, bf16* __restrict__ hi,
                                                           bf16* __restrict__ lo) {
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
@@ -243,6 +263,10 @@ cudaError_t launch_assemble33(const float* latent, const float* frames, int n_cl
                               cudaStream_t st) {
     dim3 grid(kAudioRows, n_clips);
     return launch_k(assemble33_kernel, grid, dim3(256), 0, st, latent, frames, a_hi, a_lo);
+}
+
+cudaError_t launch_heads(const float* logits, int ld, int n_clips, float* clipwise, float* framewise, cudaStream_t st) {
+    return launch_k(heads_kernel, dim3(n_clips), dim3(256), 0, st, logits, ld, clipwise, framewise);
 }
 
 cudaError_t launch_gelu_planes(const float* x, size_t n, bf16* hi, bf16* lo, cudaStream_t st) {

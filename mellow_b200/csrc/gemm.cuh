@@ -14,6 +14,11 @@ struct GemmArgs {
     int M, N, K;                                      // K % 32 == 0
     int passes;                                       // 3: hi*hi + hi*lo + lo*hi ; 1: hi*hi
     int split_k; float* partial;                      // split_k > 1: raw fp32 partial sums [split_k][M][N], no epilogue
+    TraceBuf* trace; unsigned trace_id;               // optional timeline stamps (common.cuh)
+    int dbg;                                          // bottleneck hunting only (MB_GEMM_DBG): 1 skip A loads, 2 skip MMAs, 4 skip stores
+    int resident;                                     // decode chain: use the weight-resident kernel (gemm_skinny.cu) when the shape fits
+    int bn_hint;                                      // decode-sized split-K GEMMs: N-tile width 48 / 64 (0 = default rule)
+    int compact;                                      // decode-sized GEMMs: use the two-CTAs-per-SM variants (gemm_umma.cu)
     // EPI_GENERIC: v = act(acc + bias) + residual -> out_f32 and/or bf16 planes
     const float* bias;
     const float* residual; int ldr;
@@ -145,6 +150,52 @@ __device__ __forceinline__ void store_planes8(bf16* hi, bf16* lo, size_t idx, co
     if (lo) *reinterpret_cast<uint4*>(lo + idx) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// EPI_QKV_ROPE on 16 columns, in two steps so that an engine can fetch the RoPE factors (a dependent chain of two
+// global loads: the step counter, then the table row) while its MMAs are still running.
+__device__ __forceinline__ void qkv_rope_load(const GemmArgs& g, int m, int n, float* c, float* sn) {
+    if (n < kHidden + kKvHeads * kHeadDim) {                       // q and k columns only
+        const int b = m / g.rows_per_seq;
+        const int pos = g.pos_base + (g.d_pos ? *g.d_pos : 0) + (m - b * g.rows_per_seq);
+        const int i0 = (n & (kHeadDim - 1)) >> 1;                  // multiple of 8
+        ldg4(g.rope_cos + pos * 32 + i0, c); ldg4(g.rope_cos + pos * 32 + i0 + 4, c + 4);
+        ldg4(g.rope_sin + pos * 32 + i0, sn); ldg4(g.rope_sin + pos * 32 + i0 + 4, sn + 4);
+    }
+}
+__device__ __forceinline__ void epilogue_row16_qkv(const GemmArgs& g, int m, int n, float* v, const float* c, const float* sn) {
+    const int b = m / g.rows_per_seq;
+    const int s = m - b * g.rows_per_seq;
+    const int pos = g.pos_base + (g.d_pos ? *g.d_pos : 0) + s;
+    if (n < kHidden + kKvHeads * kHeadDim) {                       // 8 rotate-half pairs of one head
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float x0 = v[2 * j] * c[j] - v[2 * j + 1] * sn[j];
+            const float x1 = v[2 * j + 1] * c[j] + v[2 * j] * sn[j];
+            v[2 * j] = x0; v[2 * j + 1] = x1;
+        }
+    }
+    if (n < kHidden) {
+        float* o = g.q_out + (size_t)m * kHidden + n;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) st4(o + j, v + j);
+    } else {
+        const int nn = n - kHidden;
+        const bool is_v = nn >= kKvHeads * kHeadDim;
+        const int c2 = is_v ? nn - kKvHeads * kHeadDim : nn;
+        const int kvh = c2 >> 6, dd = c2 & 63;
+        const size_t off = (((size_t)b * kKvHeads + kvh) * g.t_max + pos) * kHeadDim + dd;
+        void* base = is_v ? g.v_cache : g.k_cache;
+        if (g.kv_bf16) {
+            bf16* o = reinterpret_cast<bf16*>(base) + off;
+            store_planes8(o, nullptr, 0, v);
+            store_planes8(o, nullptr, 8, v + 8);
+        } else {
+            float* o = reinterpret_cast<float*>(base) + off;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) st4(o + j, v + j);
+        }
+    }
+}
+
 template <int EPI>
 __device__ __forceinline__ void epilogue_row16(const GemmArgs& g, int m, int n, float* v) {
     bool vec = (n + 16 <= g.N);
@@ -204,46 +255,14 @@ __device__ __forceinline__ void epilogue_row16(const GemmArgs& g, int m, int n, 
         g.cand_val[c] = best;
         g.cand_idx[c] = n + bi;
     } else {
-        const int b = m / g.rows_per_seq;
-        const int s = m - b * g.rows_per_seq;
-        const int pos = g.pos_base + (g.d_pos ? *g.d_pos : 0) + s;
-        if (n < kHidden + kKvHeads * kHeadDim) {                   // 8 rotate-half pairs of one head
-            const int i0 = (n & (kHeadDim - 1)) >> 1;              // multiple of 8
-            float c[8], sn[8];
-            ldg4(g.rope_cos + pos * 32 + i0, c); ldg4(g.rope_cos + pos * 32 + i0 + 4, c + 4);
-            ldg4(g.rope_sin + pos * 32 + i0, sn); ldg4(g.rope_sin + pos * 32 + i0 + 4, sn + 4);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float x0 = v[2 * j] * c[j] - v[2 * j + 1] * sn[j];
-                const float x1 = v[2 * j + 1] * c[j] + v[2 * j] * sn[j];
-                v[2 * j] = x0; v[2 * j + 1] = x1;
-            }
-        }
-        if (n < kHidden) {
-            float* o = g.q_out + (size_t)m * kHidden + n;
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) st4(o + j, v + j);
-        } else {
-            const int nn = n - kHidden;
-            const bool is_v = nn >= kKvHeads * kHeadDim;
-            const int c2 = is_v ? nn - kKvHeads * kHeadDim : nn;
-            const int kvh = c2 >> 6, dd = c2 & 63;
-            const size_t off = (((size_t)b * kKvHeads + kvh) * g.t_max + pos) * kHeadDim + dd;
-            void* base = is_v ? g.v_cache : g.k_cache;
-            if (g.kv_bf16) {
-                bf16* o = reinterpret_cast<bf16*>(base) + off;
-                store_planes8(o, nullptr, 0, v);
-                store_planes8(o, nullptr, 8, v + 8);
-            } else {
-                float* o = reinterpret_cast<float*>(base) + off;
-#pragma unroll
-                for (int j = 0; j < 16; j += 4) st4(o + j, v + j);
-            }
-        }
+        float c[8], sn[8];
+        qkv_rope_load(g, m, n, c, sn);
+        epilogue_row16_qkv(g, m, n, v, c, sn);
     }
 }
 
 // Engine entry points (gemm_mma.cu, gemm_umma.cu)
 cudaError_t launch_gemm_mma(const GemmArgs& g, int epi, cudaStream_t st);
+cudaError_t launch_gemm_skinny(const GemmArgs& g, int epi, int bn, cudaStream_t st);   // gemm_skinny.cu
 
 }  // namespace mb

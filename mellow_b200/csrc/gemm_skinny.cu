@@ -1,0 +1,275 @@
+// Decode-sized tcgen05 GEMM (M <= 128 rows, one tile per CTA):  C[M,N] = A[M,K] * W[N,K]^T, same operand planes,
+// MMA passes and fused epilogues as gemm_umma.cu, but laid out for the decode step's dependency chain:
+//
+//   * WEIGHT-RESIDENT: the CTA's whole weight slice (BN rows x its K range, <= KBMAX k-blocks) has its own shared
+//     memory region and is requested in full BEFORE griddepcontrol.wait.  The kernel is resident several microseconds
+//     before its predecessor finishes (PDL), so the HBM latency of every weight byte is hidden; the ring version only
+//     prefetched as many k-blocks as it had stages and paid one exposed HBM round trip per ring revolution after the wait
+//     (measured with the in-kernel timeline, tools/decode_timeline.py: 2.5-3.3 us of a 3.4-8.2 us kernel body).
+//   * the 128-row activation tile streams through a ring of its own (as deep as the remaining shared memory allows),
+//     requested right after the wait: these are L2 hits (the predecessor just wrote them).
+//   * one elected thread issues the MMAs k-block by k-block as the activation stages land; eight epilogue warps drain
+//     the TMEM accumulator (one row per thread) into the fused epilogue or the split-K partial buffer.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
+#include "umma.cuh"
+
+namespace mb {
+
+namespace {
+
+using namespace umma;
+
+template <int BN, bool SPLIT, int KBMAX>
+struct SkinnyCfg {
+    static constexpr uint32_t PLANES = SPLIT ? 2 : 1;
+    static constexpr uint32_t B_BYTES = BN * BK * 2;                    // one plane of one k-block
+    static constexpr uint32_t B_REGION = KBMAX * PLANES * B_BYTES;
+    static constexpr uint32_t A_STAGE = PLANES * A_BYTES;
+    static constexpr uint32_t BAR_BYTES = 512;
+    static constexpr uint32_t BUDGET = 227u * 1024u - 1024u - BAR_BYTES - B_REGION;
+    static constexpr int FIT = (int)(BUDGET / A_STAGE);
+    static constexpr int STAGES = FIT > KBMAX ? KBMAX : FIT;
+    static constexpr uint32_t ACC_N = PLANES * BN;                      // accumulator columns: [a*b_hi | a_hi*b_lo]
+    static constexpr uint32_t ACC_COLS = ACC_N <= 32 ? 32 : (ACC_N <= 64 ? 64 : 128);
+    static constexpr uint32_t TMEM_COLS = ACC_COLS;
+    static_assert(ACC_N <= 128 && (BN % 16) == 0, "N tile");
+    static constexpr size_t SMEM = (size_t)B_REGION + (size_t)STAGES * A_STAGE + 1024 + BAR_BYTES;
+    static_assert(STAGES >= 2, "activation ring does not fit");
+    static_assert((B_BYTES % 1024) == 0, "swizzled tiles start on 1024-byte boundaries");
+    static_assert((2 * KBMAX + 2 * 8 + 2) * 8 + 8 <= BAR_BYTES, "barrier block too small");
+};
+
+template <int BN, int EPI, bool SPLIT, int KBMAX>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                   const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                   const GemmArgs g) {
+    using C = SkinnyCfg<BN, SPLIT, KBMAX>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* breg = smem;                                       // [KBMAX][PLANES][BN x 64] weight slice
+    unsigned char* areg = smem + C::B_REGION;                         // [STAGES][PLANES][128 x 64] activation ring
+    uint64_t* bfull = reinterpret_cast<uint64_t*>(areg + (size_t)C::STAGES * C::A_STAGE);
+    uint64_t* afull = bfull + KBMAX;
+    uint64_t* aempty = afull + C::STAGES;
+    uint64_t* tfull = aempty + C::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+    uint32_t* trace_slot = tmem_slot + 1;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nsplit = g.split_k > 1 ? g.split_k : 1;
+    const int tiles_n = (g.N + BN - 1) / BN;
+    const int z = blockIdx.x / tiles_n;                               // K split owned by this CTA
+    const int n0 = (blockIdx.x - z * tiles_n) * BN;
+    const int kb_all = (g.K + BK - 1) / BK;
+    const int kb_begin = (int)(((long long)kb_all * z) / nsplit);
+    const int KB = (int)(((long long)kb_all * (z + 1)) / nsplit) - kb_begin;      // <= KBMAX (checked by the launcher)
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        *trace_slot = trace_open(g.trace, g.trace_id);
+        for (int i = 0; i < KBMAX; ++i) mbar_init(&bfull[i], 1);
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // the whole weight slice, before the dependency wait (weights are never produced by a predecessor kernel)
+        for (int kb = 0; kb < KB; ++kb) {
+            unsigned char* bt = breg + (size_t)kb * C::PLANES * C::B_BYTES;
+            mbar_expect_tx(&bfull[kb], C::PLANES * C::B_BYTES);
+            tma_load_2d(bt, &tm_b_hi, &bfull[kb], (kb_begin + kb) * BK, n0);
+            if (SPLIT) tma_load_2d(bt + C::B_BYTES, &tm_b_lo, &bfull[kb], (kb_begin + kb) * BK, n0);
+        }
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const unsigned trec = first_cta() ? *trace_slot : kTraceNone;    // fine-grained stamps come from the first CTA only
+
+    if (warp == 0) {
+        if (lane == 0) {
+            pdl_wait();
+            trace_put(g.trace, trec, g.trace_id, TR_WAITED);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % C::STAGES;
+                if (kb >= C::STAGES) mbar_wait(&aempty[s], ((kb / C::STAGES) - 1) & 1);
+                unsigned char* at = areg + (size_t)s * C::A_STAGE;
+                if (!(g.dbg & 1)) {
+                    mbar_expect_tx(&afull[s], C::A_STAGE);
+                    tma_load_2d(at, &tm_a_hi, &afull[s], (kb_begin + kb) * BK, 0);
+                    if (SPLIT) tma_load_2d(at + A_BYTES, &tm_a_lo, &afull[s], (kb_begin + kb) * BK, 0);
+                } else {
+                    mbar_arrive(&afull[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int s = kb % C::STAGES;
+                mbar_wait(&bfull[kb], 0);
+                if (kb == 0) trace_put(g.trace, trec, g.trace_id, 4);                // weights of k-block 0 present
+                mbar_wait(&afull[s], (kb / C::STAGES) & 1);
+                if (kb == 0) trace_put(g.trace, trec, g.trace_id, 5);                // first activation stage landed
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(areg + (size_t)s * C::A_STAGE);
+                const uint32_t a_lo = a_hi + A_BYTES;
+                const uint32_t b_hi = smem_u32(breg + (size_t)kb * C::PLANES * C::B_BYTES);    // lo rows follow the hi rows
+                // Split policy in TWO MMAs per k-step instead of three: the weight slice keeps its hi rows and its lo
+                // rows adjacent in shared memory, so one MMA with N = 2*BN forms a_hi*[b_hi | b_lo] in one pass over
+                // the 128-row activation tile; a_lo*b_hi accumulates onto the first BN columns.  Every MMA re-reads
+                // its activation tile from shared memory, and with N this small that read IS the cost of the kernel
+                // (measured ~0.8 us per k-block for three MMAs per k-step, whatever BN or the accumulator layout).
+                // The epilogue adds columns [0,BN) and [BN,2BN).
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    if (g.dbg & 2) break;
+                    const uint32_t off = k * 32;                     // 16 bf16 = 32 B along the swizzled row
+                    const uint32_t acc = (kb | k) != 0;
+                    if (SPLIT) {
+                        umma_bf16(tmem_base, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc2, acc);
+                        umma_bf16(tmem_base, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+                    } else {
+                        umma_bf16(tmem_base, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, acc);
+                    }
+                }
+                // tcgen05.commit is not free (measured ~0.28 us per k-block of pure commit / barrier ping-pong), so a
+                // stage is only handed back when a later k-block will actually be loaded into it
+                if (kb + C::STAGES < KB) umma_commit(&aempty[s]);
+            }
+            umma_commit(tfull);                                      // accumulator complete
+            trace_put(g.trace, trec, g.trace_id, 6);                 // all MMAs issued
+        }
+    } else {
+        // One accumulator row per thread (TMEM lane = row); the two warps of a lane quadrant take the 16-column units
+        // of the tile alternately, so a 32-column tile keeps all eight warps busy.
+        const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;
+        constexpr int kUnits = BN / 16;
+        pdl_wait();                                                  // residual reads / output writes depend on the predecessor
+        const int m = q * 32 + lane;
+        if (half < kUnits) {
+            float rc[8], rs[8];
+            if (EPI == EPI_QKV_ROPE && nsplit == 1 && m < g.M)       // RoPE factors of the first unit, fetched while the MMAs run
+                qkv_rope_load(g, m, n0 + half * 16, rc, rs);
+            mbar_wait(tfull, 0);
+            if (threadIdx.x == 64) trace_put(g.trace, trec, g.trace_id, 7);             // accumulator complete
+            tc_fence_after();
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+            for (int u = half; u < kUnits; u += 2) {
+                const int c0 = u * 16;
+                float v[16];
+                tmem_ld16(tacc + (uint32_t)c0, v);
+                if (SPLIT) {                                         // + a_hi * b_lo
+                    float w[16];
+                    tmem_ld16(tacc + (uint32_t)(BN + c0), w);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] += w[j];
+                }
+                const int n = n0 + c0;
+                if (m < g.M && n < g.N && !(g.dbg & 4)) {
+                    if (nsplit > 1) {
+                        float* pz = g.partial + (size_t)z * g.M * g.N + (size_t)m * g.N + n;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4)
+                            if (n + j < g.N) st4(pz + j, v + j);
+                    } else if (EPI == EPI_QKV_ROPE && n + 16 <= g.N) {
+                        if (u != half) qkv_rope_load(g, m, n, rc, rs);
+                        epilogue_row16_qkv(g, m, n, v, rc, rs);
+                    } else {
+                        epilogue_row16<EPI>(g, m, n, v);
+                    }
+                }
+            }
+        }
+    }
+    if (threadIdx.x == 64) trace_put(g.trace, trec, g.trace_id, 8);                     // this warp's epilogue stores issued
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) trace_close(g.trace, *trace_slot, g.trace_id);
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+    }
+}
+
+template <int BN, int EPI, bool SPLIT, int KBMAX>
+cudaError_t launch_skinny(const GemmArgs& g, cudaStream_t st) {
+    using C = SkinnyCfg<BN, SPLIT, KBMAX>;
+    auto kern = gemm_skinny_kernel<BN, EPI, SPLIT, KBMAX>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    if (!make_map(&ta_hi, g.A_hi, g.M, g.K, g.lda, BM) || !make_map(&tb_hi, g.W_hi, g.N, g.K, g.ldw, BN))
+        return cudaErrorInvalidValue;
+    if (SPLIT) {
+        if (!make_map(&ta_lo, g.A_lo, g.M, g.K, g.lda, BM) || !make_map(&tb_lo, g.W_lo, g.N, g.K, g.ldw, BN))
+            return cudaErrorInvalidValue;
+    } else {
+        ta_lo = ta_hi;
+        tb_lo = tb_hi;
+    }
+    const int total = ((g.N + BN - 1) / BN) * (g.split_k > 1 ? g.split_k : 1);
+    return launch_k(kern, dim3((unsigned)total), dim3(kThreads), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
+}
+
+template <int BN, int EPI, int KBMAX>
+cudaError_t launch_skinny_p(const GemmArgs& g, cudaStream_t st) {
+    return g.passes == 3 ? launch_skinny<BN, EPI, true, KBMAX>(g, st) : launch_skinny<BN, EPI, false, KBMAX>(g, st);
+}
+
+template <int EPI>
+cudaError_t launch_skinny_epi(const GemmArgs& g, int bn, cudaStream_t st) {
+    const int nsplit = g.split_k > 1 ? g.split_k : 1;
+    const int kb_all = (g.K + BK - 1) / BK;
+    const int kb_max = (kb_all + nsplit - 1) / nsplit;               // largest K slice, in k-blocks
+    if constexpr (EPI == EPI_GENERIC) {                              // split-K slices: the whole activation slice stays resident too
+        if (bn == 16 && kb_max <= 3) return launch_skinny_p<16, EPI, 3>(g, st);
+        if (bn == 16 && kb_max <= 6) return launch_skinny_p<16, EPI, 6>(g, st);
+    }
+    if (bn == 16 && kb_max <= 9) return launch_skinny_p<16, EPI, 9>(g, st);
+    if (bn == 32 && kb_max <= 9) return launch_skinny_p<32, EPI, 9>(g, st);
+    if constexpr (EPI == EPI_GENERIC) {
+        if (bn == 48 && kb_max <= 3) return launch_skinny_p<48, EPI, 3>(g, st);
+        if (bn == 64 && kb_max <= 3) return launch_skinny_p<64, EPI, 3>(g, st);
+    }
+    return cudaErrorNotSupported;
+}
+
+}  // namespace
+
+// Decode-sized GEMM with resident weights.  Returns cudaErrorNotSupported (nothing launched) when the shape does not
+// fit this kernel (more than one M tile, more tiles than SMs, K slice longer than the weight region); the caller then
+// uses the persistent ring kernel of gemm_umma.cu.
+cudaError_t launch_gemm_skinny(const GemmArgs& g, int epi, int bn, cudaStream_t st) {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int total = ((g.N + bn - 1) / bn) * (g.split_k > 1 ? g.split_k : 1);
+    if (g.M > BM || total > num_sms) return cudaErrorNotSupported;
+    switch (epi) {
+        case EPI_GENERIC: return launch_skinny_epi<EPI_GENERIC>(g, bn, st);
+        case EPI_SWIGLU: return launch_skinny_epi<EPI_SWIGLU>(g, bn, st);
+        case EPI_QKV_ROPE: return launch_skinny_epi<EPI_QKV_ROPE>(g, bn, st);
+        case EPI_ARGMAX: return cudaErrorNotSupported;            // lm_head has far more tiles than SMs
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace mb

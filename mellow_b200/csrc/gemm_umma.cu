@@ -18,18 +18,31 @@ namespace {
 
 using namespace umma;
 
-template <int BN, bool SPLIT>
+// AM: rows of the activation tile that TMA actually fetches (128, or 64 for row groups of <= 64 decode rows).  The UMMA
+//     always runs M=128: with AM=64 the descriptor's rows 64..127 alias whatever follows in shared memory (the W tile,
+//     the next stage, the tail pad).  Accumulator row r depends on A row r only, so those rows hold garbage that the
+//     epilogue never reads (m < M guard); TAIL_PAD keeps the aliased reads inside the allocation.
+// ST: ring depth; 0 = as deep as 227 KB allows (one CTA per SM).  ST > 0 selects the "compact" decode variants whose
+//     footprint (< 113 KB) lets two CTAs share an SM, so the CTAs of the next kernel of a PDL chain -- or of another
+//     row group's chain -- are resident (barriers initialised, TMEM allocated, weight tiles in flight) while the
+//     current kernel still runs.
+template <int BN, bool SPLIT, int AM = BM, int ST = 0>
 struct Cfg {
+    static constexpr uint32_t A_TILE = AM * BK * 2;
     static constexpr uint32_t B_BYTES = BN * BK * 2;
-    static constexpr uint32_t STAGE_BYTES = (SPLIT ? 2 : 1) * (A_BYTES + B_BYTES);
+    static constexpr uint32_t STAGE_BYTES = (SPLIT ? 2 : 1) * (A_TILE + B_BYTES);
     static constexpr uint32_t STAGING_BYTES = 0;
-    static constexpr uint32_t BUDGET = 227u * 1024u - 1024u - 256u - STAGING_BYTES;
+    static constexpr uint32_t TAIL_PAD = AM < BM ? A_BYTES - A_TILE : 0;
+    static constexpr uint32_t BUDGET = 227u * 1024u - 1024u - 256u - STAGING_BYTES - TAIL_PAD;
     static constexpr int STAGES_FIT = (int)(BUDGET / STAGE_BYTES);
-    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
+    static constexpr int STAGES = ST > 0 ? ST : (STAGES_FIT > 8 ? 8 : STAGES_FIT);
+    static constexpr int MIN_CTAS = ST > 0 ? 2 : 1;
     static constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
     static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                             // two accumulators: MMA of tile i+1
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256;   // overlaps epilogue of tile i
-    static_assert(STAGES >= 2, "tile does not fit");
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + TAIL_PAD;   // overlaps epilogue of tile i
+    static_assert(STAGES >= 2 && STAGES <= STAGES_FIT, "tile does not fit");
+    static_assert(ST == 0 || SMEM <= 113u * 1024u, "compact variant must leave room for a second CTA on the SM");
+    static_assert(AM == BM || AM == 64, "activation tile is 128 or 64 rows");
 };
 
 struct TileCoord { int m0, n0, z, kb_begin, KB; };
@@ -54,12 +67,13 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile, int
 // CL > 1 (decode-sized GEMMs): CL CTAs of a thread-block cluster own CL consecutive N tiles of the same 128-row
 // activation tile.  Each CTA loads 1/CL of every A k-block and TMA-multicasts it to all of them, so the activation
 // bytes pulled from L2 drop CL-fold; a stage is recycled only after all CL consumers released it (multicast commit).
-template <int BN, int EPI, bool SPLIT, int CL>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int EPI, bool SPLIT, int CL, int AM, int ST>
+__global__ void __launch_bounds__(kThreads, (Cfg<BN, SPLIT, AM, ST>::MIN_CTAS))
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                  const GemmArgs g) {
-    using C = Cfg<BN, SPLIT>;
+    using C = Cfg<BN, SPLIT, AM, ST>;
+    static_assert(CL == 1 || AM == BM, "multicast clusters split the full 128-row tile");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* staging = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
@@ -77,9 +91,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 
     const uint32_t crank = CL > 1 ? cluster_rank() : 0u;
     constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
-    constexpr uint32_t A_PART = A_BYTES / CL;                        // bytes of the A tile this CTA fetches per plane
+    constexpr uint32_t A_PART = C::A_TILE / CL;                       // bytes of the A tile this CTA fetches per plane
     pdl_trigger();
+    unsigned trec = kTraceNone;                                      // thread 0 only
     if (threadIdx.x == 0) {
+        trec = trace_open(g.trace, g.trace_id);
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
         mbar_init(&tempty[0], kEpiWarps); mbar_init(&tempty[1], kEpiWarps);
@@ -107,22 +123,24 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     // are requested before the dependency wait; the activation (A) tiles of those slots follow it.
                     first = false;
                     const int npre = t.KB < C::STAGES ? t.KB : C::STAGES;
+                    const uint32_t tx_bytes = (g.dbg & 1) ? (SPLIT ? 2u : 1u) * C::B_BYTES : C::STAGE_BYTES;
                     for (int i = 0; i < npre; ++i) {
                         unsigned char* st = smem + (size_t)i * C::STAGE_BYTES;
-                        mbar_expect_tx(&full[i], C::STAGE_BYTES);
-                        tma_load_2d(st + A_BYTES, &tm_b_hi, &full[i], (t.kb_begin + i) * BK, t.n0);
-                        if (SPLIT) tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, &full[i], (t.kb_begin + i) * BK, t.n0);
+                        mbar_expect_tx(&full[i], tx_bytes);
+                        tma_load_2d(st + C::A_TILE, &tm_b_hi, &full[i], (t.kb_begin + i) * BK, t.n0);
+                        if (SPLIT) tma_load_2d(st + 2 * C::A_TILE + C::B_BYTES, &tm_b_lo, &full[i], (t.kb_begin + i) * BK, t.n0);
                     }
                     pdl_wait();
-                    for (int i = 0; i < npre; ++i) {
+                    if (first_cta()) trace_put(g.trace, trec, g.trace_id, TR_WAITED);
+                    for (int i = 0; i < npre && !(g.dbg & 1); ++i) {
                         unsigned char* st = smem + (size_t)i * C::STAGE_BYTES;
                         if (CL > 1) {
                             const int mr = t.m0 + (int)crank * (BM / CL);
                             tma_load_2d_mc(st + crank * A_PART, &tm_a_hi, &full[i], (t.kb_begin + i) * BK, mr, cmask);
-                            if (SPLIT) tma_load_2d_mc(st + A_BYTES + C::B_BYTES + crank * A_PART, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, mr, cmask);
+                            if (SPLIT) tma_load_2d_mc(st + C::A_TILE + C::B_BYTES + crank * A_PART, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, mr, cmask);
                         } else {
                             tma_load_2d(st, &tm_a_hi, &full[i], (t.kb_begin + i) * BK, t.m0);
-                            if (SPLIT) tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, t.m0);
+                            if (SPLIT) tma_load_2d(st + C::A_TILE + C::B_BYTES, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, t.m0);
                         }
                     }
                     kb = npre;
@@ -133,16 +151,17 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     const uint32_t ph = (it / C::STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
-                    mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                    tma_load_2d(st + A_BYTES, &tm_b_hi, &full[s], (t.kb_begin + kb) * BK, t.n0);
-                    if (SPLIT) tma_load_2d(st + 2 * A_BYTES + C::B_BYTES, &tm_b_lo, &full[s], (t.kb_begin + kb) * BK, t.n0);
-                    if (CL > 1) {
+                    mbar_expect_tx(&full[s], (g.dbg & 1) ? (SPLIT ? 2u : 1u) * C::B_BYTES : C::STAGE_BYTES);
+                    tma_load_2d(st + C::A_TILE, &tm_b_hi, &full[s], (t.kb_begin + kb) * BK, t.n0);
+                    if (SPLIT) tma_load_2d(st + 2 * C::A_TILE + C::B_BYTES, &tm_b_lo, &full[s], (t.kb_begin + kb) * BK, t.n0);
+                    if (g.dbg & 1) {
+                    } else if (CL > 1) {
                         const int mr = t.m0 + (int)crank * (BM / CL);
                         tma_load_2d_mc(st + crank * A_PART, &tm_a_hi, &full[s], (t.kb_begin + kb) * BK, mr, cmask);
-                        if (SPLIT) tma_load_2d_mc(st + A_BYTES + C::B_BYTES + crank * A_PART, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, mr, cmask);
+                        if (SPLIT) tma_load_2d_mc(st + C::A_TILE + C::B_BYTES + crank * A_PART, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, mr, cmask);
                     } else {
                         tma_load_2d(st, &tm_a_hi, &full[s], (t.kb_begin + kb) * BK, t.m0);
-                        if (SPLIT) tma_load_2d(st + A_BYTES + C::B_BYTES, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, t.m0);
+                        if (SPLIT) tma_load_2d(st + C::A_TILE + C::B_BYTES, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, t.m0);
                     }
                 }
             }
@@ -164,11 +183,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
-                    const uint32_t b_hi = a_hi + A_BYTES;
+                    const uint32_t b_hi = a_hi + C::A_TILE;
                     const uint32_t a_lo = b_hi + C::B_BYTES;
-                    const uint32_t b_lo = a_lo + A_BYTES;
+                    const uint32_t b_lo = a_lo + C::A_TILE;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
+                        if (g.dbg & 2) break;
                         const uint32_t off = k * 32;                 // 16 bf16 = 32 B along the swizzled row
                         umma_bf16(tacc, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | k) != 0);
                         if (SPLIT) {
@@ -214,7 +234,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[buf]);
                 }
-                if (m < g.M) {
+                if (m < g.M && !(g.dbg & 4)) {
 #pragma unroll
                     for (int h = 0; h < 32; h += 16) {
                         const int n = t.n0 + c0 + h;
@@ -235,6 +255,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) trace_close(g.trace, trec, g.trace_id);
     if (CL > 1) cluster_sync_all();                                  // no CTA leaves while peers may still signal it
     if (warp == 1) {
         __syncwarp();
@@ -243,10 +264,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN, int EPI, bool SPLIT, int CL = 1>
+template <int BN, int EPI, bool SPLIT, int CL = 1, int AM = BM, int ST = 0>
 cudaError_t launch_one(const GemmArgs& g, cudaStream_t st) {
-    using C = Cfg<BN, SPLIT>;
-    auto kern = gemm_umma_kernel<BN, EPI, SPLIT, CL>;
+    using C = Cfg<BN, SPLIT, AM, ST>;
+    auto kern = gemm_umma_kernel<BN, EPI, SPLIT, CL, AM, ST>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -254,10 +275,10 @@ cudaError_t launch_one(const GemmArgs& g, cudaStream_t st) {
         configured = true;
     }
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    if (!make_map(&ta_hi, g.A_hi, g.M, g.K, g.lda, BM / CL) || !make_map(&tb_hi, g.W_hi, g.N, g.K, g.ldw, BN))
+    if (!make_map(&ta_hi, g.A_hi, g.M, g.K, g.lda, AM / CL) || !make_map(&tb_hi, g.W_hi, g.N, g.K, g.ldw, BN))
         return cudaErrorInvalidValue;
     if (SPLIT) {
-        if (!make_map(&ta_lo, g.A_lo, g.M, g.K, g.lda, BM / CL) || !make_map(&tb_lo, g.W_lo, g.N, g.K, g.ldw, BN))
+        if (!make_map(&ta_lo, g.A_lo, g.M, g.K, g.lda, AM / CL) || !make_map(&tb_lo, g.W_lo, g.N, g.K, g.ldw, BN))
             return cudaErrorInvalidValue;
     } else {
         ta_lo = ta_hi;
@@ -293,6 +314,22 @@ cudaError_t launch_epi(const GemmArgs& g, cudaStream_t st) {
         // of 4 CTAs multicast the shared activation tile when the tile count allows it
         static const bool no_cluster = getenv("MB_CLUSTER4") == nullptr;   // measured: multicast clusters are ~10% slower here (latency-bound, not A-traffic-bound), off by default
         const int bn = g.N >= 2048 ? 32 : 16;
+        if constexpr (EPI == EPI_GENERIC) {
+            // wide-tile split-K: every tcgen05.mma streams the 128-row activation tile from shared memory (~65 cycles
+            // whatever N is), so the decode GEMMs are paced by the NUMBER of MMAs a CTA issues.  A wide N tile with
+            // K cut into 1-2 k-blocks per CTA needs 12-24 MMAs instead of 36-108; the partial sums are reduced by the
+            // consumer kernel (add_rmsnorm / decode attention) in a fixed order.
+            if (g.bn_hint == 64 && g.split_k > 1) return split ? launch_one<64, EPI, true, 1, BM, 2>(g, st) : launch_one<64, EPI, false, 1, BM, 2>(g, st);
+            if (g.bn_hint == 48 && g.split_k > 1) return split ? launch_one<48, EPI, true, 1, BM, 2>(g, st) : launch_one<48, EPI, false, 1, BM, 2>(g, st);
+        }
+        if (g.compact) {
+            // co-resident variants (two CTAs per SM): row groups of <= 64 rows fetch a 64-row activation tile
+            if (g.M <= 64) {
+                if (bn == 32) return split ? launch_one<32, EPI, true, 1, 64, 4>(g, st) : launch_one<32, EPI, false, 1, 64, 4>(g, st);
+                return split ? launch_one<16, EPI, true, 1, 64, 5>(g, st) : launch_one<16, EPI, false, 1, 64, 5>(g, st);
+            }
+            if (bn == 16) return split ? launch_one<16, EPI, true, 1, BM, 3>(g, st) : launch_one<16, EPI, false, 1, BM, 6>(g, st);
+        }
         const int tiles_n = (g.N + bn - 1) / bn;
         const bool cl4 = !no_cluster && tiles_n % 4 == 0 && tiles_n * (g.split_k > 1 ? g.split_k : 1) <= 148;
         if (bn == 32) {

@@ -44,6 +44,7 @@ cudaError_t launch_window_attention_mma(const float* qkv, const float* relbias, 
 cudaError_t launch_tail_gather(const float* y, int n_clips, float* latent, bf16* col_hi, bf16* col_lo, cudaStream_t st);
 cudaError_t launch_assemble33(const float* latent, const float* frames, int n_clips, bf16* a_hi, bf16* a_lo,
                               cudaStream_t st);
+cudaError_t launch_heads(const float* logits, int ld, int n_clips, float* clipwise, float* framewise, cudaStream_t st);
 cudaError_t launch_gelu_planes(const float* x, size_t n, bf16* hi, bf16* lo, cudaStream_t st);
 cudaError_t launch_split_planes(const float* x, size_t n, bf16* hi, bf16* lo, cudaStream_t st);
 
@@ -63,6 +64,7 @@ struct DecodeAttnArgs {
     const int* done;                   // optional [B]: rows that already emitted the stop token skip their K/V stream
     float* part_acc; float* part_ml;   // [B][9][nsplit][64], [B][9][nsplit][2]
     bf16* out_hi; bf16* out_lo;        // [B,576]
+    TraceBuf* trace; unsigned trace_id;
 };
 cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st);
 struct SampleArgs {
@@ -79,7 +81,7 @@ struct SampleArgs {
     float* logits_dump;             // optional [max_len][B][V] temperature-scaled logits
 };
 cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, int M, const float* w, bf16* hi, bf16* lo,
-                               cudaStream_t st);
+                               cudaStream_t st, TraceBuf* trace = nullptr, unsigned trace_id = 0);
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st);
 cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st);
 

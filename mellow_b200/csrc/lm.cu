@@ -1,6 +1,8 @@
 // SmolLM2 decoder-side kernels that are not GEMMs: prefix assembly (reference mellow/model/decoder.py:14-55),
 // causal prefill attention and split-KV decode attention (transformers modeling_llama.py:276-285; the reference has
 // no KV cache, wrapper.py:216-217), and the sampling step (wrapper.py:218-249).
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace mb {
@@ -164,11 +166,14 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
     // decode step, so they are requested before waiting on the predecessor.  Nothing that the predecessor chain
     // writes (the step counter, the newest K/V row, q) is touched before pdl_wait().
     pdl_trigger();
+    unsigned trec = kTraceNone;
+    if (tid == 0) trec = trace_open(a.trace, a.trace_id);
     const bool early0 = (t_begin + 1) * 64 < a.ctx_base;
     const bool early1 = a.tps > 1 && (t_begin + 2) * 64 < a.ctx_base;
     if (early0) load_tile(0, t_begin, a.ctx_base);
     if (early1) load_tile(1, t_begin + 1, a.ctx_base);
     pdl_wait();
+    if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, TR_WAITED);
     // a row that has emitted the stop token is finished (the reference cuts its text there,
     // wrapper.py:254); its later tokens are never read, so its K/V stream -- the dominant decode traffic -- is skipped.
     // The uniform exit happens after the cp.async groups above are drained by the hardware at CTA exit.
@@ -291,6 +296,7 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
             if (d == 0) { a.part_ml[o * 2] = sm.m[h]; a.part_ml[o * 2 + 1] = sm.l[h]; }
         }
     }
+    if (tid == 0) trace_close(a.trace, trec, a.trace_id);
 }
 
 __global__ void __launch_bounds__(64) decode_combine_kernel(const DecodeAttnArgs a) {
@@ -363,6 +369,7 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
             if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
         }
         if (lane == 0) {
+            if (bi < 0 || bi >= kVocab) bi = 0;                    // all-NaN row: never index the embedding table out of range
             a.tokens_out[(size_t)b * a.max_len + step] = bi;
             if (bi == a.eos_id) a.done[b] = 1;
             stoken = a.forced ? a.forced[(size_t)b * a.max_len + step] : bi;
@@ -381,10 +388,13 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
 template <int S>
 __global__ void __launch_bounds__(128) add_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ partial,
                                                           int M, const float* __restrict__ w,
-                                                          bf16* __restrict__ hi, bf16* __restrict__ lo) {
+                                                          bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                                          TraceBuf* trace, unsigned trace_id) {
     constexpr int PER = kHidden / 32;
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
+    unsigned trec = kTraceNone;
+    if (threadIdx.x == 0) trec = trace_open(trace, trace_id);
     if (row >= M) return;
     float v[PER], p[S > 0 ? S : 1][PER], wv[PER];
     float* xr = x + (size_t)row * kHidden;
@@ -392,6 +402,7 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(float* __restrict__ x,
 #pragma unroll
     for (int j = 0; j < PER; ++j) wv[j] = w[lane + 32 * j];        // weights do not depend on the predecessor
     pdl_wait();
+    if (threadIdx.x == 0 && first_cta()) trace_put(trace, trec, trace_id, TR_WAITED);
 #pragma unroll
     for (int j = 0; j < PER; ++j) v[j] = xr[lane + 32 * j];
 #pragma unroll
@@ -412,6 +423,49 @@ __global__ void __launch_bounds__(128) add_rmsnorm_kernel(float* __restrict__ x,
         if (S > 0) xr[i] = v[j];
         store_planes1(hi, lo, (size_t)row * kHidden + i, wv[j] * (v[j] * rstd));
     }
+    if (threadIdx.x == 0) trace_close(trace, trec, trace_id);
+}
+
+// Same operation with one CTA per row and 16-byte accesses (144 threads x float4 = 576 columns): up to 12 split-K
+// partials are all in flight before the first add, the sum order is fixed (s = 0..S-1), and the 128 rows of a decode
+// step spread over 128 SMs instead of 32.
+template <int S>
+__global__ void __launch_bounds__(160) add_rmsnorm_row_kernel(float* __restrict__ x, const float* __restrict__ partial,
+                                                              int M, const float* __restrict__ w,
+                                                              bf16* __restrict__ hi, bf16* __restrict__ lo,
+                                                              TraceBuf* trace, unsigned trace_id) {
+    __shared__ float red[5];
+    const int row = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const bool act = t < kHidden / 4;
+    unsigned trec = kTraceNone;
+    if (t == 0) trec = trace_open(trace, trace_id);
+    pdl_trigger();
+    float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (act) wv = __ldg(reinterpret_cast<const float4*>(w) + t);   // gains do not depend on the predecessor
+    pdl_wait();
+    if (t == 0 && first_cta()) trace_put(trace, trec, trace_id, TR_WAITED);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 p[S > 0 ? S : 1];
+    if (act) {
+        v = reinterpret_cast<const float4*>(x + (size_t)row * kHidden)[t];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+            p[s] = reinterpret_cast<const float4*>(partial + ((size_t)s * M + row) * kHidden)[t];
+#pragma unroll
+        for (int s = 0; s < S; ++s) { v.x += p[s].x; v.y += p[s].y; v.z += p[s].z; v.w += p[s].w; }
+    }
+    const float sq = warp_sum(v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w);
+    if (lane == 0) red[warp] = sq;
+    __syncthreads();
+    const float tot = (((red[0] + red[1]) + red[2]) + red[3]) + red[4];
+    const float rstd = rsqrtf(tot * (1.0f / kHidden) + 1e-5f);
+    if (act) {
+        const size_t o = (size_t)row * kHidden + 4 * t;
+        if (S > 0) reinterpret_cast<float4*>(x + (size_t)row * kHidden)[t] = v;
+        store_planes2(hi, lo, o, wv.x * (v.x * rstd), wv.y * (v.y * rstd));
+        store_planes2(hi, lo, o + 2, wv.z * (v.z * rstd), wv.w * (v.w * rstd));
+    }
+    if (t == 0) trace_close(trace, trec, trace_id);
 }
 
 // step += 1; records the first step count at which every row has emitted eos (wrapper.py:247-249)
@@ -466,12 +520,26 @@ cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
 }
 
 cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, int M, const float* w, bf16* hi, bf16* lo,
-                               cudaStream_t st) {
+                               cudaStream_t st, TraceBuf* trace, unsigned trace_id) {
+    static const bool v1 = getenv("MB_NORM_V1") != nullptr;       // warp-per-row version, kept for A/B measurements
+    if (!v1 || n_partial > 4) {
+#define MB_ROWNORM(S) launch_k(add_rmsnorm_row_kernel<S>, dim3(M), dim3(160), 0, st, x, partial, M, w, hi, lo, trace, trace_id)
+        switch (n_partial) {
+            case 0: return MB_ROWNORM(0);
+            case 3: return MB_ROWNORM(3);
+            case 4: return MB_ROWNORM(4);
+            case 6: return MB_ROWNORM(6);
+            case 9: return MB_ROWNORM(9);
+            case 12: return MB_ROWNORM(12);
+            default: return cudaErrorInvalidValue;
+        }
+#undef MB_ROWNORM
+    }
     const int grid = (M + 3) / 4;
     switch (n_partial) {
-        case 0: return launch_k(add_rmsnorm_kernel<0>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo);
-        case 3: return launch_k(add_rmsnorm_kernel<3>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo);
-        case 4: return launch_k(add_rmsnorm_kernel<4>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo);
+        case 0: return launch_k(add_rmsnorm_kernel<0>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo, trace, trace_id);
+        case 3: return launch_k(add_rmsnorm_kernel<3>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo, trace, trace_id);
+        case 4: return launch_k(add_rmsnorm_kernel<4>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo, trace, trace_id);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -82,6 +82,10 @@ class Engine:
     def set_gemm_engine(self, engine):
         self._ck(self.lib.mb_set_gemm_engine(self.handle, int(engine)))
 
+    def set_decode_groups(self, groups):
+        """Row groups of the decode step (0 = automatic); a scheduling choice only, token ids do not depend on it."""
+        self._ck(self.lib.mb_set_decode_groups(self.handle, int(groups)))
+
     def workspace_bytes(self):
         return self.lib.mb_workspace_bytes(self.handle)
 
@@ -101,6 +105,38 @@ class Engine:
         rows = torch.empty(2, b, S.AUDIO_FRAMES + 1, S.D_PROJ, device=self.device)
         self._ck(self.lib.mb_encode(self.handle, _ptr(wave1), _ptr(wave2), b, _ptr(rows), self._stream()))
         return rows
+
+    def encode_heads(self, batch, expand=True):
+        """the output dicts the reference returns as od1 / od2 (mellow.py:100-108) for the last
+        encode()/generate() of `batch` pairs.  expand=True gives the reference shapes (framewise (B,1024,527),
+        embedding (B,1025,768)) as views that repeat each of the 32 unique frame rows 32 times (htsat.py:43-56)."""
+        n = 2 * batch
+        clip = torch.empty(n, S.NUM_CLASSES, device=self.device)
+        frame = torch.empty(n, S.AUDIO_FRAMES, S.NUM_CLASSES, device=self.device)
+        latent = torch.empty(n, S.ENC_OUT, device=self.device)
+        femb = torch.empty(n, S.AUDIO_FRAMES, S.ENC_OUT, device=self.device)
+        self._ck(self.lib.mb_encode_heads(self.handle, n, _ptr(clip), _ptr(frame), _ptr(latent), _ptr(femb), self._stream()))
+        out = []
+        for k in range(2):
+            sl = slice(k * batch, (k + 1) * batch)
+            fw, fe = frame[sl], femb[sl]
+            if expand:
+                fw = fw[:, :, None, :].expand(-1, -1, 32, -1).reshape(batch, 32 * S.AUDIO_FRAMES, S.NUM_CLASSES)
+                fe = fe[:, :, None, :].expand(-1, -1, 32, -1).reshape(batch, 32 * S.AUDIO_FRAMES, S.ENC_OUT)
+                emb = torch.cat([latent[sl][:, None, :], fe], dim=1)
+            else:
+                emb = torch.cat([latent[sl][:, None, :], fe], dim=1)
+            out.append({"framewise_output": fw, "clipwise_output": clip[sl], "latent_output": latent[sl], "embedding": emb})
+        return out[0], out[1]
+
+    def generate_prefix_inference(self, input_dict, heads=True):
+        """The reference's inner seam ``model.generate_prefix_inference`` (mellow.py:100-108):
+        {'audio1': (B,320000), 'audio2': (B,320000), 'input': {'input_ids': (B,129)}} -> (prefix (B,389,576), od1, od2)."""
+        a1, a2 = input_dict["audio1"], input_dict["audio2"]
+        self.encode(a1, a2)
+        prefix = self.prefix(input_dict["input"]["input_ids"])
+        od1, od2 = self.encode_heads(a1.shape[0]) if heads else (None, None)
+        return prefix, od1, od2
 
     _TAP_SHAPES = {0: (4096, 96), 1: (1024, 192), 2: (256, 384), 3: (64, 768), 4: (64, 768), 5: (33, 768)}
 

@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libmellow_b200.so")
 HASH_PATH = os.path.join(CSRC, "libmellow_b200.srchash")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-SOURCES = ["api.cu", "frontend.cu", "encoder.cu", "lm.cu", "attn_mma.cu", "gemm_mma.cu", "gemm_umma.cu", "decode_chain.cu", "audio.cu"]
+SOURCES = ["api.cu", "frontend.cu", "encoder.cu", "lm.cu", "attn_mma.cu", "gemm_mma.cu", "gemm_umma.cu", "gemm_skinny.cu", "decode_chain.cu", "audio.cu"]
 HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", "umma.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -92,9 +92,12 @@ SYMBOLS = [
     ("mb_bind_weights", _i, [_vp, _vp, _ll]),
     ("mb_workspace_bytes", _ll, [_vp]),
     ("mb_set_gemm_engine", _i, [_vp, _i]),
+    ("mb_set_decode_groups", _i, [_vp, _i]),
+    ("mb_set_trace", _i, [_vp, _vp]),
     ("mb_kernel_launches", _ll, [_vp]),
     ("mb_frontend", _i, [_vp, _vp, _i, _vp, _vp, _vp]),
     ("mb_encode", _i, [_vp, _vp, _vp, _i, _vp, _vp]),
+    ("mb_encode_heads", _i, [_vp, _i, _vp, _vp, _vp, _vp, _vp]),
     ("mb_encode_tap", _i, [_vp, _vp, _i, _i, _vp, _vp]),
     ("mb_prefix", _i, [_vp, _vp, _i, _vp, _vp]),
     ("mb_set_prefix", _i, [_vp, _vp, _i, _vp]),

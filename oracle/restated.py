@@ -194,6 +194,20 @@ def encoder_tail(sd, x):
     return latent, oframe
 
 
+def encoder_heads(sd, x):
+    """The classification outputs of the same TSCAM branch (htsat.py:774-796, loss_type "clip_bce" config.py:1), which
+    the reference returns inside od1/od2 (mellow.py:100-108) and generate() ignores: clipwise (N,527) =
+    sigmoid(avgpool_t(conv)), and the 32 unique framewise rows (N,32,527) = sigmoid(conv) (repeated 32x by :780)."""
+    n = x.shape[0]
+    x = F.layer_norm(x, (768,), sd[HT + "norm.weight"], sd[HT + "norm.bias"], 1e-5)
+    x = x.permute(0, 2, 1).reshape(n, 768, 8, 8)
+    x = x.reshape(n, 768, 4, 2, 8).permute(0, 1, 3, 2, 4).reshape(n, 768, 2, 32)
+    y = torch.flatten(F.conv2d(x, sd[HT + "tscam_conv.weight"], sd[HT + "tscam_conv.bias"], padding=(0, 1)), 2)   # (N,527,32)
+    framewise = torch.sigmoid(y).permute(0, 2, 1)                                         # :780 before interpolate
+    clipwise = torch.sigmoid(y.mean(dim=-1))                                              # :782-783,795
+    return clipwise, framewise
+
+
 def projection(sd, x):
     """Projection.forward mellow/model/mellow.py:48-52 (dropout is eval-identity)."""
     e1 = F.linear(x, sd["audio_encoder.projection.linear1.weight"])
@@ -217,7 +231,7 @@ def encode_clips(sd, wave, taps=None):
     emb33 = torch.cat([latent[:, None, :], oframe], dim=1)                                # (N,33,768)
     out = projection(sd, emb33)
     if taps is not None:
-        taps.update(latent=latent, oframe=oframe, rows33=out)
+        taps.update(latent=latent, oframe=oframe, rows33=out, final_tokens=x)
     return out
 
 

@@ -28,6 +28,12 @@ def golden():
 
 
 @pytest.fixture(scope="session")
+def golden_heads():
+    """od1 / od2 of the reference's generate_prefix_inference (tests/golden/make_golden_heads.py)."""
+    return dict(np.load(os.path.join(ROOT, "tests", "golden", "ref_heads_synth1234.npz")))
+
+
+@pytest.fixture(scope="session")
 def inputs():
     """The seeded synthetic batch the golden fixture was generated from (B=2 pairs)."""
     from mellow_b200 import synth

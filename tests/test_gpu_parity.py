@@ -267,6 +267,53 @@ def test_odd_batch_and_determinism(engine, inputs, golden):
     assert a.tolist() == [want[0], want[1], want[0]]
 
 
+def test_encoder_heads_od1_od2(engine, inputs, golden_heads, golden):
+    """generate_prefix_inference returns (prefix, od1, od2) like mellow.py:100-108; the
+    classification heads and the embedding must match the reference's output dicts (sigmoid outputs: 2e-4 abs)."""
+    d = {"audio1": inputs["wave1"], "audio2": inputs["wave2"], "input": {"input_ids": inputs["ids"]}}
+    prefix, od1, od2 = engine.generate_prefix_inference(d)
+    assert prefix.shape == (2, 389, 576)
+    assert maxerr(prefix[:, PREFIX_ROWS], golden["prefix_rows"]) < ACT_TOL
+    for name, od in (("od1", od1), ("od2", od2)):
+        assert od["framewise_output"].shape == (2, 1024, 527) and od["embedding"].shape == (2, 1025, 768)
+        assert od["clipwise_output"].shape == (2, 527) and od["latent_output"].shape == (2, 768)
+        assert maxerr(od["clipwise_output"], golden_heads[name + "_clipwise"]) < 2e-4
+        assert maxerr(od["framewise_output"][:, 0::32], golden_heads[name + "_framewise_rows"]) < 2e-4
+        assert torch.equal(od["framewise_output"][:, 0::32], od["framewise_output"][:, 31::32])     # 32x repeat (htsat.py:43-56)
+        assert maxerr(od["latent_output"], golden_heads[name + "_latent"]) < ACT_TOL
+        emb_rows = torch.cat([od["embedding"][:, :1], od["embedding"][:, 1::32]], dim=1)
+        assert maxerr(emb_rows, golden_heads[name + "_embedding_rows"]) < ACT_TOL
+    # the heads are optional and must not disturb the main path
+    toks = engine.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 6).cpu()
+    assert toks.tolist() == golden["tokens"][:, :6].tolist()
+
+
+def test_decode_row_groups_do_not_change_results(engine, inputs, golden):
+    """The decode step may run the batch as 1..4 row groups on concurrent streams (compact tcgen05 variants with a
+    64-row activation tile): ragged groups of a 7-row batch must give the same ids as the single-group path, both in
+    the captured graph and in the eager (logit-dumping) path, whose logits must be bit-identical."""
+    from mellow_b200.engine import Engine
+    eng7 = Engine(None, device=0, max_batch=7, max_new_tokens=16, policy="split", arena=engine.arena)
+    try:
+        idx = [0, 1, 1, 0, 1, 0, 0]
+        w1, w2, ids = inputs["wave1"][idx], inputs["wave2"][idx], inputs["ids"][idx]
+        want = torch.from_numpy(golden["tokens"]).to(torch.int32)[idx][:, :10]
+        ref_logits = None
+        for groups in (1, 2, 3, 4):
+            eng7.set_decode_groups(groups)
+            toks = eng7.generate(w1, w2, ids, 10).cpu()
+            assert torch.equal(toks, want), f"groups={groups} (graph)"
+            eng7.encode(w1, w2); eng7.prefix(ids); eng7.prefill(7, want_logits=False)
+            toks2, dump = eng7.decode(7, 6, dump_logits=True)
+            assert torch.equal(toks2.cpu(), want[:, :6]), f"groups={groups} (eager)"
+            if ref_logits is None:
+                ref_logits = dump.cpu()
+            else:
+                assert torch.equal(dump.cpu(), ref_logits), f"groups={groups}: logits differ from the single-group path"
+    finally:
+        eng7.close()
+
+
 def test_full_size_batch_128_rows_match_golden(sd, engine, inputs, golden):
     """BASELINE.json's batch-128 configuration: 64 copies of the two golden pairs; every row must reproduce its golden
     ids (row independence at full size, the persistent tcgen05 tiles and the unsplit decode attention path)."""

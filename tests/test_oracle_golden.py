@@ -30,6 +30,20 @@ def test_encoder_stages_match_reference(sd, golden, inputs):
     _close(rows, golden["rows33"], 5e-5)
 
 
+def test_encoder_heads_match_reference(sd, golden_heads, inputs):
+    """clipwise / framewise / latent / embedding of od1 and od2 (mellow.py:100-108)."""
+    for name, wave in (("od1", inputs["wave1"]), ("od2", inputs["wave2"])):
+        taps = {}
+        with torch.no_grad():
+            R.encode_clips(sd, wave, taps)
+            clip, frame = R.encoder_heads(sd, taps["final_tokens"])
+        assert clip.shape == (2, 527) and frame.shape == (2, 32, 527)
+        _close(clip, golden_heads[name + "_clipwise"], 1e-5)
+        _close(frame, golden_heads[name + "_framewise_rows"], 1e-5)
+        _close(taps["latent"], golden_heads[name + "_latent"], 2e-5)
+        _close(torch.cat([taps["latent"][:, None], taps["oframe"]], 1), golden_heads[name + "_embedding_rows"], 2e-5)
+
+
 def test_prefix_and_greedy_tokens_match_reference(sd, golden, inputs):
     with torch.no_grad():
         ra, rb = R.encode_clips(sd, inputs["wave1"]), R.encode_clips(sd, inputs["wave2"])

@@ -31,6 +31,7 @@ namespace {
 
 constexpr int kMaxSplitK = 12;
 constexpr int kMaxGroups = 4;
+constexpr int kGuSplitMax = 3;
 constexpr int kDepths[4] = {2, 2, 6, 2};
 constexpr int kHeadsPerStage[4] = {4, 8, 16, 32};
 inline int stage_dim(int i) { return kEmbed << i; }
@@ -176,7 +177,9 @@ struct Handle {
     bf16 *la_hi = nullptr, *la_lo = nullptr, *lh_hi = nullptr, *lh_lo = nullptr;
     void *kcache = nullptr, *vcache = nullptr;
     size_t kv_layer_elems = 0;
-    float *part_acc = nullptr, *part_ml = nullptr, *gemm_partial = nullptr, *cand_val = nullptr;
+    float *part_acc = nullptr, *part_ml = nullptr, *gemm_partial = nullptr, *cand_val = nullptr, *qkv_part = nullptr, *gu_part = nullptr;
+    float* rope_cur = nullptr;           // cos | sin row of the position the current decode step writes (step_advance_kernel)
+    unsigned* fix_counter = nullptr;     // split-K fix-up tickets of the gate/up tiles (self-resetting)
     int* cand_idx = nullptr;
     bool logits_fused = false;           // the last lm_head wrote argmax candidates instead of logits
     unsigned* chain_bar = nullptr;       // [kLayers][8] grid-barrier counters of the fused decode chain
@@ -241,8 +244,6 @@ GemmArgs gemm_base(const Handle* h, const bf16* a_hi, const bf16* a_lo, int lda,
     g.W_hi = wgt.hi; g.W_lo = lo_of(h, wgt.lo); g.ldw = ldw;
     g.M = M; g.N = N; g.K = K;
     g.passes = h->policy == kPolicySplit ? 3 : 1;
-    static const int dbg = getenv("MB_GEMM_DBG") ? atoi(getenv("MB_GEMM_DBG")) : 0;
-    g.dbg = M <= 128 ? dbg : 0;
     return g;
 }
 
@@ -416,18 +417,30 @@ inline int decode_nsplit(const Handle* h, int B) {
 // Tiling of the split-K decode GEMMs (gemm_umma.cu launch_epi): N-tile width x K split.  The default follows the
 // measured rule "a decode GEMM costs what its CTAs' tcgen05.mma COUNT costs": wide tiles, 1-2 k-blocks per CTA.
 // MB_DEC_TILING=0 restores the 16-column tiles with split 3 / 4.
-struct DecodeTiling { int o_bn, o_split, down_bn, down_split, resident; };
+struct DecodeTiling { int o_bn, o_split, down_bn, down_split, resident, qkv_split, gu_split; };
 const DecodeTiling& decode_tiling() {
     static const DecodeTiling t = [] {
         const char* e = getenv("MB_DEC_TILING");
-        const int mode = e ? atoi(e) : 0;
+        const int mode = e ? atoi(e) : 6;
         const char* r = getenv("MB_DEC_RESIDENT");
         const int res = r ? atoi(r) : 1;
-        if (mode == 1) return DecodeTiling{48, 9, 48, 12, res};
-        if (mode == 2) return DecodeTiling{64, 9, 64, 12, res};
-        if (mode == 3) return DecodeTiling{48, 9, 48, 6, res};
-        if (mode == 4) return DecodeTiling{48, 3, 48, 6, res};
-        return DecodeTiling{0, 3, 0, 4, res};
+        // QKV as 9 one-k-block slices of 64-column tiles (135 CTAs x 8 MMAs instead of 60 CTAs x 72); the partial sums
+        // are reduced, roped and appended to the KV cache by the decode-attention kernel that consumes them
+        const char* q = getenv("MB_DEC_QKV_SPLIT");
+        const int qs = res ? (q ? atoi(q) : 9) : 0;
+        // gate/up as 3 K slices of 64-column tiles (144 CTAs x 24 MMAs instead of 96 x 72); SwiGLU needs the complete
+        // sums, so the split that arrives last at its tile finishes it inside the same kernel (gemm_skinny.cu fix-up)
+        const char* gq = getenv("MB_DEC_GU_SPLIT");
+        const int gs = res ? (gq ? atoi(gq) : 0) : 0;   // measured slower (fence + ticket + re-read cost more than the MMAs saved): off
+        if (mode == 1) return DecodeTiling{48, 9, 48, 12, res, qs, gs};
+        if (mode == 2) return DecodeTiling{64, 9, 64, 12, res, qs, gs};
+        if (mode == 3) return DecodeTiling{48, 9, 48, 6, res, qs, gs};
+        if (mode == 4) return DecodeTiling{48, 3, 48, 6, res, qs, gs};
+        if (mode == 5) return DecodeTiling{0, 3, 32, 8, res, qs, gs};
+        if (mode == 6) return DecodeTiling{32, 3, 32, 8, res, qs, gs};
+        if (mode == 7) return DecodeTiling{0, 3, 48, 12, res, qs, gs};
+        if (mode == 0) return DecodeTiling{0, 3, 0, 4, res, qs, gs};
+        return DecodeTiling{32, 3, 32, 8, res, qs, gs};
     }();
     return t;
 }
@@ -452,8 +465,10 @@ int decode_compact(int G) {
 }
 
 // Rows [r0, r0+n) of the batch; n_all = rows of the whole step (all row groups), which sets the key split.
-int run_decode_attention(Handle* h, int l, int r0, int n, int n_all, cudaStream_t st, bool skip_done = true) {
+int run_decode_attention(Handle* h, int l, int r0, int n, int n_all, cudaStream_t st, bool skip_done = true,
+                         const float* qkv_part = nullptr, int qkv_nsplit = 0) {
     DecodeAttnArgs a;
+    a.qkv_part = qkv_part; a.qkv_nsplit = qkv_nsplit; a.rope_cur = h->rope_cur;
     const size_t esz = h->policy == kPolicyFast ? 2 : 4;
     const size_t kv_off = (size_t)r0 * kKvHeads * h->t_max * kHeadDim * esz;
     a.q = h->q + (size_t)r0 * kHidden;
@@ -481,9 +496,11 @@ int run_decode_attention(Handle* h, int l, int B, cudaStream_t st, bool skip_don
 // fixed order.  On entry la_hi/la_lo hold RMSNorm(x) with this layer's input_layernorm; on exit they hold RMSNorm(x)
 // with `next_norm` (the next layer's input_layernorm, or the final model norm).  Every row is independent of every
 // other row, so the values are identical however the batch is cut into groups.
-int lm_layer_decode_fused(Handle* h, int l, int r0, int n, int n_all, int compact, float* partial,
+int lm_layer_decode_fused(Handle* h, int l, int gi, int r0, int n, int n_all, int compact,
                           const float* next_norm, cudaStream_t st, cudaEvent_t attn_wait = nullptr,
                           cudaEvent_t attn_record = nullptr) {
+    float* partial = h->gemm_partial + (size_t)gi * kMaxSplitK * 128 * kHidden;           // split-K partials of this row group
+    float* qkv_part = h->qkv_part + (size_t)gi * kQkvSplitMax * 128 * kQkvDim;
     const LmLayerW& k = h->w.layer[l];
     const DecodeTiling& tl = decode_tiling();
     const size_t esz = h->policy == kPolicyFast ? 2 : 4;
@@ -491,7 +508,14 @@ int lm_layer_decode_fused(Handle* h, int l, int r0, int n, int n_all, int compac
     float* x = h->x + (size_t)r0 * kHidden;
     bf16* la_hi = h->la_hi + (size_t)r0 * kHidden; bf16* la_lo = h->la_lo + (size_t)r0 * kHidden;
     bf16* lh_hi = h->lh_hi + (size_t)r0 * kInter; bf16* lh_lo = h->lh_lo + (size_t)r0 * kInter;
-    {
+    const bool qkv_split = tl.qkv_split > 1 && h->engine == 1;
+    if (qkv_split) {
+        GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.qkv, kHidden, n, kQkvDim, kHidden);
+        g.resident = 1; g.bn_hint = 64;
+        g.trace = h->trace; g.trace_id = 1000 + (r0 ? 100 : 0) + l;
+        g.split_k = tl.qkv_split; g.partial = qkv_part;
+        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+    } else {
         GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.qkv, kHidden, n, kQkvDim, kHidden);
         g.compact = compact; g.resident = tl.resident;
         g.trace = h->trace; g.trace_id = 1000 + (r0 ? 100 : 0) + l;
@@ -506,7 +530,7 @@ int lm_layer_decode_fused(Handle* h, int l, int r0, int n, int n_all, int compac
     if (attn_wait) MB_CK(h, cudaStreamWaitEvent(st, attn_wait, 0));
     {
         PdlOff off(attn_wait != nullptr);                  // two predecessors: the QKV kernel and the other group's event
-        MB_TRY(run_decode_attention(h, l, r0, n, n_all, st));
+        MB_TRY(run_decode_attention(h, l, r0, n, n_all, st, true, qkv_split ? qkv_part : nullptr, tl.qkv_split));
     }
     if (attn_record) MB_CK(h, cudaEventRecord(attn_record, st));
     {
@@ -522,6 +546,11 @@ int lm_layer_decode_fused(Handle* h, int l, int r0, int n, int n_all, int compac
         GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.gu, kHidden, n, 2 * kInter, kHidden);
         g.compact = compact; g.resident = tl.resident;
         g.trace = h->trace; g.trace_id = 5000 + (r0 ? 100 : 0) + l;
+        if (tl.gu_split > 1 && h->engine == 1) {
+            g.split_k = tl.gu_split; g.bn_hint = 64;
+            g.partial = h->gu_part + (size_t)gi * kGuSplitMax * 128 * 2 * kInter;
+            g.fix_counter = h->fix_counter + (size_t)gi * 64;
+        }
         g.out_hi = lh_hi; g.out_lo = lo_of(h, lh_lo); g.ldp = kInter;
         MB_TRY(run_gemm(h, g, EPI_SWIGLU, st));
     }
@@ -723,7 +752,6 @@ int decode_step(Handle* h, int B, bool fused, cudaStream_t st) {
             for (int gi = 0; gi < G; ++gi) {
                 const int r0 = (int)(((long long)B * gi) / G), n = (int)(((long long)B * (gi + 1)) / G) - r0;
                 cudaStream_t sg = gi == 0 ? st : h->grp_stream[gi - 1];
-                float* partial = h->gemm_partial + (size_t)gi * kMaxSplitK * 128 * kHidden;
                 if (l == 0) {
                     if (stagger == 1 && gi > 0) MB_CK(h, cudaStreamWaitEvent(sg, h->ev_attn[gi - 1], 0));
                     PdlOff off(gi > 0);                     // a forked chain starts behind event edges, not a kernel
@@ -738,7 +766,7 @@ int decode_step(Handle* h, int B, bool fused, cudaStream_t st) {
                 } else if (stagger == 1 && l == 0 && gi + 1 < G) {
                     rec_ev = h->ev_attn[gi];
                 }
-                MB_TRY(lm_layer_decode_fused(h, l, r0, n, B, compact, partial,
+                MB_TRY(lm_layer_decode_fused(h, l, gi, r0, n, B, compact,
                                              l + 1 < kLayers ? h->w.layer[l + 1].ln1 : h->w.lm_norm, sg, wait_ev, rec_ev));
             }
         }
@@ -760,7 +788,7 @@ int sample_and_advance(Handle* h, int B, int max_len, float temperature, float t
     a.temperature = temperature; a.top_p = top_p; a.d_step = h->d_step; a.tokens_out = h->d_tokens;
     a.forced = forced; a.x_next = h->x; a.done = h->d_done; a.logits_dump = logits_dump;
     MB_CK(h, launch_sample(a, st));
-    MB_CK(h, launch_step_advance(h->d_step, h->d_done, B, h->d_stop, st));
+    MB_CK(h, launch_step_advance(h->d_step, h->d_done, B, h->d_stop, h->w.rope_cos, h->w.rope_sin, kPrefix - 1, h->rope_cur, st));
     h->launches += 2;
     return 0;
 }
@@ -926,6 +954,11 @@ static int create_body(Handle* h) {
     MB_TRY(dev_alloc(h, &h->part_acc, B * kHeads * kMaxAttnSplit * kHeadDim));
     MB_TRY(dev_alloc(h, &h->part_ml, B * kHeads * kMaxAttnSplit * 2));
     MB_TRY(dev_alloc(h, &h->gemm_partial, (size_t)kMaxGroups * kMaxSplitK * 128 * kHidden));
+    MB_TRY(dev_alloc(h, &h->qkv_part, (size_t)kMaxGroups * kQkvSplitMax * 128 * kQkvDim));
+    MB_TRY(dev_alloc(h, &h->rope_cur, 64));
+    MB_TRY(dev_alloc(h, &h->gu_part, (size_t)kMaxGroups * kGuSplitMax * 128 * 2 * kInter));
+    MB_TRY(dev_alloc(h, &h->fix_counter, (size_t)kMaxGroups * 64));
+    MB_CK(h, cudaMemset(h->fix_counter, 0, sizeof(unsigned) * kMaxGroups * 64));
     for (int i = 0; i < kMaxGroups - 1; ++i) {
         MB_CK(h, cudaStreamCreateWithFlags(&h->grp_stream[i], cudaStreamNonBlocking));
         MB_CK(h, cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));

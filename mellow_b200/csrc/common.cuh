@@ -143,6 +143,8 @@ __device__ __forceinline__ void trace_close(TraceBuf* tb, unsigned rec, unsigned
 // KV-cache element types
 __device__ __forceinline__ float kv_load(const float* p) { return *p; }
 __device__ __forceinline__ float kv_load(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void kv_cast(float x, float& o) { o = x; }
+__device__ __forceinline__ void kv_cast(float x, bf16& o) { o = __float2bfloat16_rn(x); }
 __device__ __forceinline__ void kv_store2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 __device__ __forceinline__ void kv_store2(bf16* p, float a, float b) {
     __nv_bfloat162 v;

@@ -15,7 +15,9 @@ struct GemmArgs {
     int passes;                                       // 3: hi*hi + hi*lo + lo*hi ; 1: hi*hi
     int split_k; float* partial;                      // split_k > 1: raw fp32 partial sums [split_k][M][N], no epilogue
     TraceBuf* trace; unsigned trace_id;               // optional timeline stamps (common.cuh)
-    int dbg;                                          // bottleneck hunting only (MB_GEMM_DBG): 1 skip A loads, 2 skip MMAs, 4 skip stores
+    unsigned* fix_counter;                            // weight-resident kernel, split_k > 1: per-N-tile arrival counters (zero between
+                                                      // launches).  The split that arrives last sums the partials in z order and runs
+                                                      // the fused epilogue itself, so no consumer-side reduction is needed.
     int resident;                                     // decode chain: use the weight-resident kernel (gemm_skinny.cu) when the shape fits
     int bn_hint;                                      // decode-sized split-K GEMMs: N-tile width 48 / 64 (0 = default rule)
     int compact;                                      // decode-sized GEMMs: use the two-CTAs-per-SM variants (gemm_umma.cu)

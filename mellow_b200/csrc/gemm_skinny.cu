@@ -11,7 +11,11 @@
 //   * one elected thread issues the MMAs k-block by k-block as the activation stages land; eight epilogue warps drain
 //     the TMEM accumulator (one row per thread) into the fused epilogue or the split-K partial buffer.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue.
+// Warp roles (320 threads): warps 0..7 = epilogue, warp 8 = TMA producer, warp 9 = TMEM allocator + MMA issuer.  The two
+// single-thread roles sit in the HIGHEST-numbered warps of their schedulers (warp id % 4) and the epilogue warps sleep
+// between polls of the accumulator barrier: with the roles the other way round (and a bare polling loop) the waiting
+// epilogue warps took most issue slots of the shared schedulers and an EMPTY k-block iteration of the MMA thread cost
+// 0.3 us (measured, tools/decode_timeline.py with MB_GEMM_DBG=3).
 #include "umma.cuh"
 
 namespace mb {
@@ -56,6 +60,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     uint64_t* tfull = aempty + C::STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
     uint32_t* trace_slot = tmem_slot + 1;
+    uint32_t* last_slot = trace_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsplit = g.split_k > 1 ? g.split_k : 1;
@@ -66,8 +71,9 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const int kb_begin = (int)(((long long)kb_all * z) / nsplit);
     const int KB = (int)(((long long)kb_all * (z + 1)) / nsplit) - kb_begin;      // <= KBMAX (checked by the launcher)
 
+    constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
     pdl_trigger();
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == kProducerWarp * 32) {
         *trace_slot = trace_open(g.trace, g.trace_id);
         for (int i = 0; i < KBMAX; ++i) mbar_init(&bfull[i], 1);
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
@@ -82,7 +88,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             if (SPLIT) tma_load_2d(bt + C::B_BYTES, &tm_b_lo, &bfull[kb], (kb_begin + kb) * BK, n0);
         }
     }
-    if (warp == 1) {
+    if (warp == kMmaWarp) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -92,58 +98,64 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     const unsigned trec = first_cta() ? *trace_slot : kTraceNone;    // fine-grained stamps come from the first CTA only
 
-    if (warp == 0) {
-        if (lane == 0) {
+    // Both single-thread loops below are fully unrolled over the (compile-time bounded) k-blocks: stage indices,
+    // barrier parities and shared-memory offsets become constants, and what remains per MMA is one 32-bit add per
+    // descriptor plus the instruction itself.  A lone thread issues dependent instructions ~5 cycles apart, so the
+    // generic loop (runtime stage arithmetic, 64-bit descriptor rebuilds, a watchdog clock read per barrier) cost
+    // ~0.3 us per k-block before a single MMA ran -- more than the MMAs themselves (tools/decode_timeline.py).
+    if (warp == kProducerWarp) {
+        if (elect_one()) {
             pdl_wait();
             trace_put(g.trace, trec, g.trace_id, TR_WAITED);
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % C::STAGES;
-                if (kb >= C::STAGES) mbar_wait(&aempty[s], ((kb / C::STAGES) - 1) & 1);
-                unsigned char* at = areg + (size_t)s * C::A_STAGE;
-                if (!(g.dbg & 1)) {
+#pragma unroll
+            for (int kb = 0; kb < KBMAX; ++kb) {
+                if (kb < KB) {
+                    const int s = kb % C::STAGES;
+                    if (kb >= C::STAGES) mbar_wait_fast(&aempty[s], ((kb / C::STAGES) - 1) & 1);
+                    unsigned char* at = areg + (size_t)s * C::A_STAGE;
                     mbar_expect_tx(&afull[s], C::A_STAGE);
                     tma_load_2d(at, &tm_a_hi, &afull[s], (kb_begin + kb) * BK, 0);
                     if (SPLIT) tma_load_2d(at + A_BYTES, &tm_a_lo, &afull[s], (kb_begin + kb) * BK, 0);
-                } else {
-                    mbar_arrive(&afull[s]);
                 }
             }
         }
-    } else if (warp == 1) {
-        if (lane == 0) {
+    } else if (warp == kMmaWarp) {
+        if (elect_one()) {
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             constexpr uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            for (int kb = 0; kb < KB; ++kb) {
-                const int s = kb % C::STAGES;
-                mbar_wait(&bfull[kb], 0);
-                if (kb == 0) trace_put(g.trace, trec, g.trace_id, 4);                // weights of k-block 0 present
-                mbar_wait(&afull[s], (kb / C::STAGES) & 1);
-                if (kb == 0) trace_put(g.trace, trec, g.trace_id, 5);                // first activation stage landed
-                tc_fence_after();
-                const uint32_t a_hi = smem_u32(areg + (size_t)s * C::A_STAGE);
-                const uint32_t a_lo = a_hi + A_BYTES;
-                const uint32_t b_hi = smem_u32(breg + (size_t)kb * C::PLANES * C::B_BYTES);    // lo rows follow the hi rows
-                // Split policy in TWO MMAs per k-step instead of three: the weight slice keeps its hi rows and its lo
-                // rows adjacent in shared memory, so one MMA with N = 2*BN forms a_hi*[b_hi | b_lo] in one pass over
-                // the 128-row activation tile; a_lo*b_hi accumulates onto the first BN columns.  Every MMA re-reads
-                // its activation tile from shared memory, and with N this small that read IS the cost of the kernel
-                // (measured ~0.8 us per k-block for three MMAs per k-step, whatever BN or the accumulator layout).
-                // The epilogue adds columns [0,BN) and [BN,2BN).
+            const uint32_t a_lo0 = umma_desc_lo(smem_u32(areg));      // descriptor low words of stage 0 / k-block 0
+            const uint32_t b_lo0 = umma_desc_lo(smem_u32(breg));
+            // Split policy in TWO MMAs per k-step instead of three: the weight slice keeps its hi rows and its lo rows
+            // adjacent in shared memory, so one MMA with N = 2*BN forms a_hi*[b_hi | b_lo] in one pass over the
+            // 128-row activation tile; a_lo*b_hi accumulates onto the first BN columns.  The epilogue adds columns
+            // [0,BN) and [BN,2BN).
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k) {
-                    if (g.dbg & 2) break;
-                    const uint32_t off = k * 32;                     // 16 bf16 = 32 B along the swizzled row
-                    const uint32_t acc = (kb | k) != 0;
-                    if (SPLIT) {
-                        umma_bf16(tmem_base, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc2, acc);
-                        umma_bf16(tmem_base, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
-                    } else {
-                        umma_bf16(tmem_base, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, acc);
+            for (int kb = 0; kb < KBMAX; ++kb) {
+                if (kb < KB) {
+                    const int s = kb % C::STAGES;
+                    mbar_wait_fast(&bfull[kb], 0);
+                    if (kb == 0) trace_put(g.trace, trec, g.trace_id, 4);            // weights of k-block 0 present
+                    mbar_wait_fast(&afull[s], (kb / C::STAGES) & 1);
+                    if (kb == 0) trace_put(g.trace, trec, g.trace_id, 5);            // first activation stage landed
+                    tc_fence_after();
+                    const uint32_t ah = a_lo0 + (uint32_t)(s * (C::A_STAGE >> 4));
+                    const uint32_t al = ah + (A_BYTES >> 4);
+                    const uint32_t bh = b_lo0 + (uint32_t)(kb * ((C::PLANES * C::B_BYTES) >> 4));   // lo rows follow the hi rows
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {              // 16 bf16 = 32 B = 2 descriptor units along the swizzled row
+                        const uint64_t da = umma_desc_join(ah + 2 * k), db = umma_desc_join(bh + 2 * k);
+                        if (SPLIT) {
+                            if (kb == 0 && k == 0) umma_bf16_c<false>(tmem_base, da, db, idesc2);
+                            else umma_bf16_c<true>(tmem_base, da, db, idesc2);
+                            umma_bf16_c<true>(tmem_base, umma_desc_join(al + 2 * k), db, idesc);
+                        } else {
+                            if (kb == 0 && k == 0) umma_bf16_c<false>(tmem_base, da, db, idesc);
+                            else umma_bf16_c<true>(tmem_base, da, db, idesc);
+                        }
                     }
+                    // a stage is only handed back when a later k-block will actually be loaded into it
+                    if (kb + C::STAGES < KBMAX && kb + C::STAGES < KB) umma_commit(&aempty[s]);
                 }
-                // tcgen05.commit is not free (measured ~0.28 us per k-block of pure commit / barrier ping-pong), so a
-                // stage is only handed back when a later k-block will actually be loaded into it
-                if (kb + C::STAGES < KB) umma_commit(&aempty[s]);
             }
             umma_commit(tfull);                                      // accumulator complete
             trace_put(g.trace, trec, g.trace_id, 6);                 // all MMAs issued
@@ -152,7 +164,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         // One accumulator row per thread (TMEM lane = row); the two warps of a lane quadrant take the 16-column units
         // of the tile alternately, so a 32-column tile keeps all eight warps busy.
         const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;
+        const int half = warp >> 2;
         constexpr int kUnits = BN / 16;
         pdl_wait();                                                  // residual reads / output writes depend on the predecessor
         const int m = q * 32 + lane;
@@ -160,8 +172,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             float rc[8], rs[8];
             if (EPI == EPI_QKV_ROPE && nsplit == 1 && m < g.M)       // RoPE factors of the first unit, fetched while the MMAs run
                 qkv_rope_load(g, m, n0 + half * 16, rc, rs);
-            mbar_wait(tfull, 0);
-            if (threadIdx.x == 64) trace_put(g.trace, trec, g.trace_id, 7);             // accumulator complete
+            mbar_wait_sleep(tfull, 0);
+            if (threadIdx.x == 0) trace_put(g.trace, trec, g.trace_id, 7);              // accumulator complete
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
@@ -176,7 +188,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                     for (int j = 0; j < 16; ++j) v[j] += w[j];
                 }
                 const int n = n0 + c0;
-                if (m < g.M && n < g.N && !(g.dbg & 4)) {
+                if (m < g.M && n < g.N) {
                     if (nsplit > 1) {
                         float* pz = g.partial + (size_t)z * g.M * g.N + (size_t)m * g.N + n;
 #pragma unroll
@@ -192,11 +204,58 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             }
         }
     }
-    if (threadIdx.x == 64) trace_put(g.trace, trec, g.trace_id, 8);                     // this warp's epilogue stores issued
+    if (threadIdx.x == 0) trace_put(g.trace, trec, g.trace_id, 8);                      // this warp's epilogue stores issued
+    if (nsplit > 1 && g.fix_counter != nullptr) {
+        // In-kernel split-K fix-up: every split has written its partial tile; the one whose ticket shows that all the
+        // others arrived before it re-reads the nsplit partials from L2, adds them in z order (deterministic whoever
+        // is last) and runs the fused epilogue.  The counter returns to zero for the next launch.
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == kProducerWarp * 32) {
+            const unsigned ticket = atomicAdd(g.fix_counter + (blockIdx.x - z * tiles_n), 1u);
+            const bool last = ticket == (unsigned)(nsplit - 1);
+            if (last) g.fix_counter[blockIdx.x - z * tiles_n] = 0u;
+            *last_slot = last ? 1u : 0u;
+        }
+        __syncthreads();
+        if (*last_slot != 0u && warp < kEpiWarps) {
+            __threadfence();
+            const int q = warp & 3, half = warp >> 2;
+            const int m = q * 32 + lane;
+            constexpr int kUnits = BN / 16;
+            if (m < g.M) {
+#pragma unroll 1
+                for (int u = half; u < kUnits; u += 2) {
+                    const int n = n0 + u * 16;
+                    if (n >= g.N) break;
+                    float v[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                    const float* p0 = g.partial + (size_t)m * g.N + n;
+                    for (int zz = 0; zz < nsplit; zz += 3) {         // three splits' loads in flight at a time
+                        float4 t[3][4];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                t[k][j] = zz + k < nsplit ? __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)(zz + k) * g.M * g.N) + j)
+                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                v[4 * j] += t[k][j].x; v[4 * j + 1] += t[k][j].y; v[4 * j + 2] += t[k][j].z; v[4 * j + 3] += t[k][j].w;
+                            }
+                    }
+                    epilogue_row16<EPI>(g, m, n, v);
+                }
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0) trace_close(g.trace, *trace_slot, g.trace_id);
-    if (warp == 1) {
+    if (threadIdx.x == kProducerWarp * 32) trace_close(g.trace, *trace_slot, g.trace_id);
+    if (warp == kMmaWarp) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
     }
@@ -239,11 +298,14 @@ cudaError_t launch_skinny_epi(const GemmArgs& g, int bn, cudaStream_t st) {
     if constexpr (EPI == EPI_GENERIC) {                              // split-K slices: the whole activation slice stays resident too
         if (bn == 16 && kb_max <= 3) return launch_skinny_p<16, EPI, 3>(g, st);
         if (bn == 16 && kb_max <= 6) return launch_skinny_p<16, EPI, 6>(g, st);
+        if (bn == 32 && kb_max <= 3) return launch_skinny_p<32, EPI, 3>(g, st);
     }
     if (bn == 16 && kb_max <= 9) return launch_skinny_p<16, EPI, 9>(g, st);
     if (bn == 32 && kb_max <= 9) return launch_skinny_p<32, EPI, 9>(g, st);
     if constexpr (EPI == EPI_GENERIC) {
         if (bn == 48 && kb_max <= 3) return launch_skinny_p<48, EPI, 3>(g, st);
+    }
+    if constexpr (EPI == EPI_GENERIC || EPI == EPI_SWIGLU) {
         if (bn == 64 && kb_max <= 3) return launch_skinny_p<64, EPI, 3>(g, st);
     }
     return cudaErrorNotSupported;

@@ -112,7 +112,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             int it = 0;
             bool first = true;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
@@ -123,16 +123,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     // are requested before the dependency wait; the activation (A) tiles of those slots follow it.
                     first = false;
                     const int npre = t.KB < C::STAGES ? t.KB : C::STAGES;
-                    const uint32_t tx_bytes = (g.dbg & 1) ? (SPLIT ? 2u : 1u) * C::B_BYTES : C::STAGE_BYTES;
                     for (int i = 0; i < npre; ++i) {
                         unsigned char* st = smem + (size_t)i * C::STAGE_BYTES;
-                        mbar_expect_tx(&full[i], tx_bytes);
+                        mbar_expect_tx(&full[i], C::STAGE_BYTES);
                         tma_load_2d(st + C::A_TILE, &tm_b_hi, &full[i], (t.kb_begin + i) * BK, t.n0);
                         if (SPLIT) tma_load_2d(st + 2 * C::A_TILE + C::B_BYTES, &tm_b_lo, &full[i], (t.kb_begin + i) * BK, t.n0);
                     }
                     pdl_wait();
                     if (first_cta()) trace_put(g.trace, trec, g.trace_id, TR_WAITED);
-                    for (int i = 0; i < npre && !(g.dbg & 1); ++i) {
+                    for (int i = 0; i < npre; ++i) {
                         unsigned char* st = smem + (size_t)i * C::STAGE_BYTES;
                         if (CL > 1) {
                             const int mr = t.m0 + (int)crank * (BM / CL);
@@ -151,11 +150,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     const uint32_t ph = (it / C::STAGES) & 1;
                     mbar_wait(&empty[s], ph ^ 1);
                     unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
-                    mbar_expect_tx(&full[s], (g.dbg & 1) ? (SPLIT ? 2u : 1u) * C::B_BYTES : C::STAGE_BYTES);
+                    mbar_expect_tx(&full[s], C::STAGE_BYTES);
                     tma_load_2d(st + C::A_TILE, &tm_b_hi, &full[s], (t.kb_begin + kb) * BK, t.n0);
                     if (SPLIT) tma_load_2d(st + 2 * C::A_TILE + C::B_BYTES, &tm_b_lo, &full[s], (t.kb_begin + kb) * BK, t.n0);
-                    if (g.dbg & 1) {
-                    } else if (CL > 1) {
+                    if (CL > 1) {
                         const int mr = t.m0 + (int)crank * (BM / CL);
                         tma_load_2d_mc(st + crank * A_PART, &tm_a_hi, &full[s], (t.kb_begin + kb) * BK, mr, cmask);
                         if (SPLIT) tma_load_2d_mc(st + C::A_TILE + C::B_BYTES + crank * A_PART, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, mr, cmask);
@@ -167,7 +165,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3, M>>4
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             int it = 0, lt = 0;
@@ -188,7 +186,6 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     const uint32_t b_lo = a_lo + C::A_TILE;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        if (g.dbg & 2) break;
                         const uint32_t off = k * 32;                 // 16 bf16 = 32 B along the swizzled row
                         umma_bf16(tacc, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | k) != 0);
                         if (SPLIT) {
@@ -234,7 +231,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[buf]);
                 }
-                if (m < g.M && !(g.dbg & 4)) {
+                if (m < g.M) {
 #pragma unroll
                     for (int h = 0; h < 32; h += 16) {
                         const int n = t.n0 + c0 + h;
@@ -353,7 +350,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 cudaError_t launch_gemm_umma(const GemmArgs& g, int epi, cudaStream_t st, bool* handled) {
     *handled = false;
     if (g.M < 1 || g.K < BK || (g.K % 8) != 0 || (g.lda % 8) != 0 || (g.ldw % 8) != 0) return cudaSuccess;
-    if (g.split_k > 1 && (epi != EPI_GENERIC || !g.partial || (g.N & 1))) return cudaErrorInvalidValue;
+    if (g.split_k > 1 && (epi != EPI_GENERIC || !g.partial || (g.N & 1) || g.fix_counter)) return cudaErrorInvalidValue;
     if (!aligned16(g.A_hi) || !aligned16(g.W_hi) || (g.passes == 3 && (!aligned16(g.A_lo) || !aligned16(g.W_lo)))) return cudaSuccess;
     if (!encode_fn()) return cudaSuccess;
     cudaError_t e;

@@ -55,6 +55,7 @@ cudaError_t launch_prefill_attention(const float* q, const void* kc, const void*
 // tensor-core (mma.sync, split operands) version of the same attention (attn_mma.cu)
 cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S,
                                          int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st);
+constexpr int kQkvSplitMax = 9;     // most split-K partials of the QKV projection the decode-attention prologue reduces
 struct DecodeAttnArgs {
     const float* q;                 // [B,576]
     const void* kc; const void* vc; // layer caches [B][3][t_max][64]
@@ -64,6 +65,11 @@ struct DecodeAttnArgs {
     const int* done;                   // optional [B]: rows that already emitted the stop token skip their K/V stream
     float* part_acc; float* part_ml;   // [B][9][nsplit][64], [B][9][nsplit][2]
     bf16* out_hi; bf16* out_lo;        // [B,576]
+    // optional: the QKV projection arrives as split-K partial sums [qkv_nsplit][B][960] (columns q | k | v, q/k head dims
+    // pair-interleaved).  The kernel then reduces its own 320 columns, applies RoPE at position ctx-1, appends the new
+    // K/V row to the caches (kc / vc are written) and uses q / k / v from shared memory; `q` is not read.
+    const float* qkv_part; int qkv_nsplit;
+    const float* rope_cur;             // [64] cos | sin of position ctx-1, maintained by step_advance_kernel
     TraceBuf* trace; unsigned trace_id;
 };
 cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st);
@@ -83,7 +89,10 @@ struct SampleArgs {
 cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, int M, const float* w, bf16* hi, bf16* lo,
                                cudaStream_t st, TraceBuf* trace = nullptr, unsigned trace_id = 0);
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st);
-cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st);
+// rope_cur (optional, [64]): cos[32] | sin[32] of the position the NEXT decode step writes (pos_base + new step), copied
+// from the tables so that the decode-attention prologue reads them from a fixed address
+cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, const float* rope_cos,
+                                const float* rope_sin, int pos_base, float* rope_cur, cudaStream_t st);
 
 // ---- decode_chain.cu: one persistent kernel for the GEMM / norm phases between two decode-attention kernels
 enum { CH_GEMM = 0, CH_ADDNORM = 1 };

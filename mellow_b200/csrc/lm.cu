@@ -136,6 +136,9 @@ struct DecodeSmem {
     __align__(16) float sc[3][64];
     float alpha[3], m[3], l[3];
     float red[4][3][kHeadDim];
+    __align__(16) float qs[3 * kHeadDim];       // fused-QKV mode: roped queries of the 3 heads, new key / value row
+    __align__(16) float knew[kHeadDim];
+    __align__(16) float vnew[kHeadDim];
 };
 
 template <typename T>
@@ -174,24 +177,79 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
     if (early1) load_tile(1, t_begin + 1, a.ctx_base);
     pdl_wait();
     if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, TR_WAITED);
+    // fused-QKV mode: this row's q | k | v columns (320 = 80 float4) arrive as split-K partial sums.  Their addresses, and
+    // that of the RoPE row of the new position (rope_cur), do not depend on the step counter, so all these loads are in
+    // flight together with the counter / stop-flag loads: one L2 round trip instead of three.
+    const bool fused = a.qkv_part != nullptr;
+    float4 pv[kQkvSplitMax];
+    float2 c2 = make_float2(1.f, 1.f), s2 = make_float2(0.f, 0.f);
+    int qcol = 0;
+    if (fused && tid < 80) {
+        qcol = tid < 48 ? kvh * 192 + tid * 4
+                        : (tid < 64 ? kHidden + kvh * kHeadDim + (tid - 48) * 4
+                                    : kHidden + kKvHeads * kHeadDim + kvh * kHeadDim + (tid - 64) * 4);
+        const float* pp = a.qkv_part + (size_t)b * kQkvDim + qcol;
+        const size_t zs = (size_t)a.B * kQkvDim;
+#pragma unroll
+        for (int z = 0; z < kQkvSplitMax; ++z)
+            pv[z] = z < a.qkv_nsplit ? *reinterpret_cast<const float4*>(pp + z * zs) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tid < 64) {                                             // RoPE angle index of this thread's two pairs
+            const int i = (qcol & (kHeadDim - 1)) >> 1;
+            c2 = *reinterpret_cast<const float2*>(a.rope_cur + i);
+            s2 = *reinterpret_cast<const float2*>(a.rope_cur + 32 + i);
+        }
+    }
+    const int step_now = a.d_step ? *a.d_step : 0;
     // a row that has emitted the stop token is finished (the reference cuts its text there,
     // wrapper.py:254); its later tokens are never read, so its K/V stream -- the dominant decode traffic -- is skipped.
     // The uniform exit happens after the cp.async groups above are drained by the hardware at CTA exit.
     if (a.done && a.done[b]) { cp_async_commit(); cp_async_wait<0>(); return; }
-    const int ctx = a.ctx_base + (a.d_step ? *a.d_step : 0);
+    const int ctx = a.ctx_base + step_now;
     const int ntiles = (ctx + 63) >> 6;
     const int t_end = min(ntiles, t_begin + a.tps);
-    if (!early0 && t_begin < t_end) load_tile(0, t_begin, ctx);
+    // fused-QKV mode: key ctx-1 is produced by this kernel, so the cache is only read up to ctx-2
+    const int ctx_ld = fused ? ctx - 1 : ctx;
+    if (!early0 && t_begin < t_end) load_tile(0, t_begin, ctx_ld);
     cp_async_commit();
-    if (!early1 && t_begin + 1 < t_end) load_tile(1, t_begin + 1, ctx);
+    if (!early1 && t_begin + 1 < t_end) load_tile(1, t_begin + 1, ctx_ld);
     cp_async_commit();
+    const int t_new = (ctx - 1) >> 6;                               // tile that holds the new key
+    if (fused) {
+        if (tid < 80) {
+            float4 acc4 = pv[0];                                    // fixed summation order z = 0..nsplit-1
+#pragma unroll
+            for (int z = 1; z < kQkvSplitMax; ++z)
+                if (z < a.qkv_nsplit) { acc4.x += pv[z].x; acc4.y += pv[z].y; acc4.z += pv[z].z; acc4.w += pv[z].w; }
+            if (tid < 64) {                                         // RoPE on q and k: pairs (2i, 2i+1) rotate by angle i
+                const float x0 = acc4.x * c2.x - acc4.y * s2.x, x1 = acc4.y * c2.x + acc4.x * s2.x;
+                const float x2 = acc4.z * c2.y - acc4.w * s2.y, x3 = acc4.w * c2.y + acc4.z * s2.y;
+                acc4 = make_float4(x0, x1, x2, x3);
+            }
+            if (tid < 48) {
+                *reinterpret_cast<float4*>(&sm.qs[tid * 4]) = acc4;
+            } else {
+                const int dd = (tid < 64 ? tid - 48 : tid - 64) * 4;
+                float* dst = tid < 64 ? &sm.knew[dd] : &sm.vnew[dd];
+                // what later steps will read back from the cache (rounded when the cache is bf16)
+                T r0, r1, r2, r3;
+                kv_cast(acc4.x, r0); kv_cast(acc4.y, r1); kv_cast(acc4.z, r2); kv_cast(acc4.w, r3);
+                dst[0] = kv_load(&r0); dst[1] = kv_load(&r1); dst[2] = kv_load(&r2); dst[3] = kv_load(&r3);
+                if (t_new >= t_begin && t_new < t_begin + a.tps) {  // the split that owns the new key appends it to the cache
+                    T* cb = const_cast<T*>(tid < 64 ? kb : vb) + (size_t)(ctx - 1) * kHeadDim + dd;
+                    cb[0] = r0; cb[1] = r1; cb[2] = r2; cb[3] = r3;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, 4);       // q / k / v of this step ready
+    }
 
     // score role: thread = (key j, half); each half owns every other 16 B chunk of the key row.  The matching
     // slices of the three query heads live in registers.
     const int sj = tid >> 1, shalf = tid & 1;
     float qreg[3][kHeadDim / 2];
     {
-        const float* qb = a.q + (size_t)b * kHidden + (kvh * 3) * kHeadDim;
+        const float* qb = fused ? sm.qs : a.q + (size_t)b * kHidden + (kvh * 3) * kHeadDim;
 #pragma unroll
         for (int h = 0; h < 3; ++h)
 #pragma unroll
@@ -212,6 +270,12 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
         const int buf = (t - t_begin) & 1;
         if (t + 1 < t_end) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
+        if (fused && t == t_new) {                                   // uniform: place the new key / value row into the tile
+            const int j = (ctx - 1) & 63;
+            if (tid < kHeadDim) kv_cast(sm.knew[tid], sm.k[buf][j][tid]);
+            else kv_cast(sm.vnew[tid - kHeadDim], sm.v[buf][j][tid - kHeadDim]);
+            __syncthreads();
+        }
         {
             float p0 = 0.f, p1 = 0.f, p2 = 0.f;
 #pragma unroll
@@ -277,10 +341,11 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
             }
         }
         __syncthreads();                                             // tile buffer and sc are reused
-        if (t + 2 < t_end) load_tile(buf, t + 2, ctx);
+        if (t + 2 < t_end) load_tile(buf, t + 2, ctx_ld);
         cp_async_commit();
     }
     cp_async_wait<0>();
+    if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, 5);           // all key tiles consumed
 #pragma unroll
     for (int h = 0; h < 3; ++h) { sm.red[kq][h][dp] = acc[h][0]; sm.red[kq][h][dp + 1] = acc[h][1]; }
     __syncthreads();
@@ -469,7 +534,8 @@ __global__ void __launch_bounds__(160) add_rmsnorm_row_kernel(float* __restrict_
 }
 
 // step += 1; records the first step count at which every row has emitted eos (wrapper.py:247-249)
-__global__ void step_advance_kernel(int* d_step, const int* done, int B, int* d_stop_step) {
+__global__ void step_advance_kernel(int* d_step, const int* done, int B, int* d_stop_step, const float* rope_cos,
+                                    const float* rope_sin, int pos_base, float* rope_cur) {
     __shared__ int all;
     pdl_trigger();
     pdl_wait();
@@ -478,8 +544,12 @@ __global__ void step_advance_kernel(int* d_step, const int* done, int B, int* d_
     for (int b = threadIdx.x; b < B; b += blockDim.x)
         if (!done[b]) all = 0;
     __syncthreads();
+    const int s = *d_step + 1;                                     // every thread reads the old value before thread 0 writes
+    if (rope_cur && threadIdx.x < 64 && pos_base + s < kMaxPos)
+        rope_cur[threadIdx.x] = threadIdx.x < 32 ? rope_cos[(pos_base + s) * 32 + threadIdx.x]
+                                                 : rope_sin[(pos_base + s) * 32 + threadIdx.x - 32];
+    __syncthreads();
     if (threadIdx.x == 0) {
-        const int s = *d_step + 1;
         *d_step = s;
         if (all && *d_stop_step < 0) *d_stop_step = s;
     }
@@ -529,6 +599,7 @@ cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, in
             case 3: return MB_ROWNORM(3);
             case 4: return MB_ROWNORM(4);
             case 6: return MB_ROWNORM(6);
+            case 8: return MB_ROWNORM(8);
             case 9: return MB_ROWNORM(9);
             case 12: return MB_ROWNORM(12);
             default: return cudaErrorInvalidValue;
@@ -548,8 +619,10 @@ cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st) {
     return launch_k(sample_kernel, dim3(a.B), dim3(1024), 0, st, a);
 }
 
-cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st) {
-    return launch_k(step_advance_kernel, dim3(1), dim3(128), 0, st, d_step, done, B, d_stop_step);
+cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, const float* rope_cos,
+                                const float* rope_sin, int pos_base, float* rope_cur, cudaStream_t st) {
+    return launch_k(step_advance_kernel, dim3(1), dim3(128), 0, st, d_step, done, B, d_stop_step, rope_cos, rope_sin,
+                    pos_base, rope_cur);
 }
 
 }  // namespace mb

@@ -34,6 +34,67 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (clock64() - t0 > 4000000000LL) __trap();          // ~2 s: a broken pipeline must fail, not hang the GPU
     }
 }
+// One elected lane of a converged warp (elect.sync): unlike `lane == 0`, the compiler knows that exactly one thread runs
+// the guarded code and can keep descriptors / addresses in uniform registers without broadcast loops.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+// Fast-path wait for the single-thread TMA / MMA loops: these loops are instruction-latency bound (one thread, no ILP,
+// ~5 cycles per dependent instruction), so the common case -- the phase has already completed -- must cost one
+// try_wait; the watchdog loop is only entered when the first probe fails.
+__device__ __forceinline__ void mbar_wait_fast(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (!done) mbar_wait(bar, parity);
+}
+// K-major SWIZZLE_128B descriptor split into its constant high word and the address-dependent low word, so that the
+// MMA loop advances a descriptor with one 32-bit add (16-byte units) instead of rebuilding 64 bits per instruction
+constexpr uint32_t kDescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);      // SBO | version 1 | SWIZZLE_128B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t umma_desc_join(uint32_t lo) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(kDescHi));
+    return d;
+}
+// tcgen05.mma with a compile-time accumulate flag (no setp per instruction)
+template <bool ACC>
+__device__ __forceinline__ void umma_bf16_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+// Wait used by warps that have nothing to do until the barrier flips (the epilogue warps waiting for the accumulator):
+// a polling loop without back-off keeps those warps eligible every cycle and they win the issue slots of the warp
+// scheduler they share with the TMA-producer / MMA-issuer warps, slowing the critical single-thread loops several-fold.
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (true) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(128);
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+// same wait without the watchdog clock reads (used to measure what the watchdog costs)
+__device__ __forceinline__ void mbar_wait_light(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)

@@ -116,6 +116,10 @@ if len(steps) > args.show_step:
             k = KIND.get(r["id"] // 1000, "?")
             f = fine.setdefault(k, [])
             f.append([(r.get(p, np.nan) - r[1]) / 1e3 for p in (4, 5, 6, 7, 8, 2, 3)])
+    att = [[(r.get(p, np.nan) - r[1]) / 1e3 for p in (4, 5, 2, 3)] for r in st if r["id"] // 1000 == 2 and 1 in r]
+    if att:
+        lines.append("attention, first CTA, us after its wait returned: q/k/v ready (fused QKV mode), key tiles consumed, exit, last-CTA exit")
+        lines.append("            " + " ".join(f"{x:7.2f}" for x in np.nanmean(np.array(att, dtype=float), axis=0)))
     if fine:
         lines.append("weight-resident GEMM, first CTA, us after its wait returned: W0 present, A0 landed, MMAs issued, acc complete, stores issued, exit, last-CTA exit")
         for k, v in fine.items():

@@ -33,6 +33,10 @@ PREFIX, LAYERS, KV_HEADS, HEAD_DIM, HIDDEN = 389, 30, 3, 64, 576
 FALLBACK_HBM_GBS = 6650.0
 
 
+FALLBACK_BF16_TFLOPS = 1400.0          # sustained figure of the profiling recipe (1.59 PF/s burst)
+LM_PARAMS = 134_515_008
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -40,6 +44,27 @@ def measured_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_tensor_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        if "bf16_tflops_sustained" in d:
+            return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return FALLBACK_BF16_TFLOPS, "fallback (B200_PROFILING.md ~1.4 PF/s sustained)"
+
+
+def decode_floor_bytes(batch, max_len, elem_bytes):
+    """bytes one decode step must move, summed over the steps 1..max_len-1 that run the LM
+    (step 0 samples from the prefill logits): every LM weight once, the KV history read, the new KV row written, the
+    token embedding gathered; `elem_bytes` = bytes per weight / KV element of the policy (4 under `split`)."""
+    total = 0
+    for t in range(1, max_len):
+        ctx = PREFIX + t
+        total += elem_bytes * (LM_PARAMS + 11520 * batch * ctx + 11520 * batch + HIDDEN * batch)
+    return total
 
 
 class ClockSampler:
@@ -201,11 +226,21 @@ def run_ours(args):
     # prefill is tensor-pipe bound: 112.18 GFLOP of algorithmic work per pair; under the split
     # policy every contraction is issued as 3 bf16 MMA passes, so the tensor pipe does 3x that
     prefill_tflops = 112.18e9 * B / (ms_prefill * 1e-3) / 1e12
+    passes = 3 if args.policy == "split" else 1
+    tpeak, tpeak_src = measured_tensor_peak()
+    hpeak, hpeak_src = measured_peaks()
+    elem = 4 if args.policy in ("split", "bf16x3") else 2
+    floor_ms = decode_floor_bytes(B, max_len, elem) / (hpeak * 1e9) * 1e3          # whole decode loop at the HBM peak
     phases = {"prefill_ms": ms_prefill, "prefill_pairs_per_s": world * B / (ms_prefill * 1e-3),
               "prefill_algorithmic_tflops_per_gpu": prefill_tflops,
-              "prefill_mma_tflops_per_gpu": prefill_tflops * (3 if args.policy == "split" else 1),
+              "prefill_mma_tflops_per_gpu": prefill_tflops * passes,
+              "prefill_frac_of_tensor_peak": prefill_tflops * passes / tpeak, "tensor_peak_tflops": tpeak,
+              "tensor_peak_source": tpeak_src,
               "decode_ms_per_token_step": ms_decode / max_len,
-              "decode_tokens_per_s": world * B * dtoks.shape[1] / (ms_decode * 1e-3)}
+              "decode_tokens_per_s": world * B * dtoks.shape[1] / (ms_decode * 1e-3),
+              "decode_hbm_floor_ms_per_step": floor_ms / max_len,
+              "decode_frac_of_hbm_floor": floor_ms / ms_decode,
+              "decode_floor_note": f"SURVEY 8d bytes at {elem} B per weight / KV element (policy {args.policy}), peak {hpeak:.0f} GB/s ({hpeak_src})"}
 
     # roofline of the dominant decode kernel: decode attention at the mean context of the 300-step loop
     peak, peak_src = measured_peaks()

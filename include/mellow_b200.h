@@ -48,9 +48,11 @@ int mb_set_gemm_engine(void* h, int engine); /* 0 = mma.sync bring-up engine, 1 
 /* decode row groups: the batch is cut into `groups` contiguous row groups whose per-layer kernel chains run on
  * concurrent streams (1..4; 0 = automatic: 2 from 96 rows up).  Results do not depend on it (rows are independent). */
 int mb_set_decode_groups(void* h, int groups);
-/* profiling aid: dev_trace_buf = {u32 n; u32 cap; {u64 globaltimer_ns; u32 id*16+phase; u32 smid} ev[cap]} in device
- * memory (NULL = off).  The decode-step kernels stamp entry / dependency-wait-return / exit of their first CTA and
- * the exit of their last CTA; id = kind*1000 + group*100 + layer (kind 1 QKV, 2 attention, 3 o_proj, 4 add+norm,
+/* profiling aid: dev_trace_buf = {u32 n; u32 cap; {u64 globaltimer_ns; u32 id*16+phase; u32 smid} ev[cap][16]} in device
+ * memory, zero-initialised, n = records used, cap = records available (NULL = off).  The first and the last CTA of every
+ * decode-step kernel claim one 16-slot record at entry and stamp phases into it with plain stores: 0 entry, 1 return of
+ * the programmatic-dependency wait, 2 exit (first CTA), 3 exit (last CTA), 4.. kernel-specific (see gemm_skinny.cu,
+ * lm.cu), 15 entry of the last CTA; id = kind*1000 + group*100 + layer (kind 1 QKV, 2 attention, 3 o_proj, 4 add+norm,
  * 5 gate/up, 6 down, 7 add+norm, 8 lm_head).  tools/decode_timeline.py prints the timeline. */
 int mb_set_trace(void* h, void* dev_trace_buf);
 long long mb_kernel_launches(void* h);       /* kernels launched by this handle so far (counting graph replays) */

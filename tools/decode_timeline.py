@@ -112,7 +112,7 @@ if len(steps) > args.show_step:
     # landed, 6 all MMAs issued, 7 accumulator complete (seen by an epilogue warp), 8 that warp's stores issued
     fine = {}
     for r in st:
-        if 1 in r and 5 in r:
+        if 1 in r and 5 in r and r["id"] // 1000 != 2:
             k = KIND.get(r["id"] // 1000, "?")
             f = fine.setdefault(k, [])
             f.append([(r.get(p, np.nan) - r[1]) / 1e3 for p in (4, 5, 6, 7, 8, 2, 3)])

@@ -226,10 +226,10 @@ def run_ours(args):
     # prefill is tensor-pipe bound: 112.18 GFLOP of algorithmic work per pair; under the split
     # policy every contraction is issued as 3 bf16 MMA passes, so the tensor pipe does 3x that
     prefill_tflops = 112.18e9 * B / (ms_prefill * 1e-3) / 1e12
-    passes = 3 if args.policy == "split" else 1
+    passes = 3 if args.policy in ("split", "split24") else 1
     tpeak, tpeak_src = measured_tensor_peak()
     hpeak, hpeak_src = measured_peaks()
-    elem = 4 if args.policy in ("split", "bf16x3") else 2
+    elem = 4 if args.policy in ("split", "bf16x3", "split24") else 2      # split24: weights 4 B, KV 3 B -- the floor stays the fp32 one
     floor_ms = decode_floor_bytes(B, max_len, elem) / (hpeak * 1e9) * 1e3          # whole decode loop at the HBM peak
     phases = {"prefill_ms": ms_prefill, "prefill_pairs_per_s": world * B / (ms_prefill * 1e-3),
               "prefill_algorithmic_tflops_per_gpu": prefill_tflops,
@@ -244,7 +244,7 @@ def run_ours(args):
 
     # roofline of the dominant decode kernel: decode attention at the mean context of the 300-step loop
     peak, peak_src = measured_peaks()
-    kv_bytes = 4 if args.policy in ("split", "bf16x3") else 2
+    kv_bytes = 4 if args.policy in ("split", "bf16x3") else (3 if args.policy == "split24" else 2)
     ctx = PREFIX + max_len // 2
     iters = 120
     ms_attn, _ = timed(lambda: eng.bench_decode_attention(B, ctx, iters), 1, 1)
@@ -273,7 +273,8 @@ def run_ours(args):
         line = {"metric": "generated tokens/s, generate() = prefill + decode", "value": value, "unit": "tokens/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16x3 (bf16 hi/lo split operands, fp32 accumulate, fp32 KV)" if kv_bytes == 4 else "bf16",
+                "dtype": ("bf16x3 (bf16 hi/lo split operands, fp32 accumulate, fp32 KV)" if kv_bytes == 4 else
+                          "bf16x3 (bf16 hi/lo split operands, fp32 accumulate, 24-bit KV)" if kv_bytes == 3 else "bf16"),
                 "data": "synthetic",
                 "config": {"workload": "BASELINE.json configs[2]: v0_s batch-128 two-audio difference, max_len=300, top_p=0.8, temp=1.0",
                            "pairs_per_gpu": B, "max_len": max_len, "steps_generated": steps_generated, "prompt_tokens": 64,
@@ -298,7 +299,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="pairs per GPU")
     ap.add_argument("--max-len", type=int, default=300)
-    ap.add_argument("--policy", default="split", choices=["split", "fast"])
+    ap.add_argument("--policy", default="split", choices=["split", "split24", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -27,6 +27,8 @@ extern "C" {
 
 #define MB_POLICY_SPLIT 0 /* bf16 hi/lo operand split, 3 MMA passes, fp32 KV cache: greedy ids match the fp32 reference */
 #define MB_POLICY_FAST 1  /* single bf16 operand plane, 1 MMA pass, bf16 KV cache: logits within bf16 tolerance */
+#define MB_POLICY_SPLIT24 2 /* MB_POLICY_SPLIT with the KV cache rounded to 24 bits (bf16 upper half + one mantissa byte per value,
+                             * relative error 2^-17 like the split GEMM operands): 25 % fewer bytes for decode attention */
 
 int mb_version(void);
 

@@ -196,6 +196,7 @@ struct Handle {
     // row-group decode: groups 1.. run on their own streams, forked from / joined to the caller's stream by events
     cudaStream_t grp_stream[kMaxGroups - 1] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups - 1] = {}, ev_attn[kMaxGroups] = {};
+    int kv_fmt = kKvF32;                 // KV-cache row format (common.cuh)
     int groups = 0;                      // mb_set_decode_groups: 0 = automatic
     TraceBuf* trace = nullptr;           // mb_set_trace: optional in-kernel timeline of the decode kernels
 };
@@ -399,8 +400,7 @@ int frontend(Handle* h, const float* wave, int n_clips, float* logmel_out, float
 
 // ------------------------------------------------------------------------------------------------ LM
 inline void* kv_layer(const Handle* h, void* base, int l) {
-    const size_t esz = h->policy == kPolicyFast ? 2 : 4;
-    return reinterpret_cast<char*>(base) + (size_t)l * h->kv_layer_elems * esz;
+    return reinterpret_cast<char*>(base) + (size_t)l * (h->kv_layer_elems / kHeadDim) * kv_row_bytes(h->kv_fmt);
 }
 
 constexpr int kMaxAttnSplit = 16;
@@ -439,6 +439,7 @@ const DecodeTiling& decode_tiling() {
         if (mode == 5) return DecodeTiling{0, 3, 32, 8, res, qs, gs};
         if (mode == 6) return DecodeTiling{32, 3, 32, 8, res, qs, gs};
         if (mode == 7) return DecodeTiling{0, 3, 48, 12, res, qs, gs};
+        if (mode == 8) return DecodeTiling{32, 3, 0, 4, res, qs, gs};
         if (mode == 0) return DecodeTiling{0, 3, 0, 4, res, qs, gs};
         return DecodeTiling{32, 3, 32, 8, res, qs, gs};
     }();
@@ -469,12 +470,11 @@ int run_decode_attention(Handle* h, int l, int r0, int n, int n_all, cudaStream_
                          const float* qkv_part = nullptr, int qkv_nsplit = 0) {
     DecodeAttnArgs a;
     a.qkv_part = qkv_part; a.qkv_nsplit = qkv_nsplit; a.rope_cur = h->rope_cur;
-    const size_t esz = h->policy == kPolicyFast ? 2 : 4;
-    const size_t kv_off = (size_t)r0 * kKvHeads * h->t_max * kHeadDim * esz;
+    const size_t kv_off = (size_t)r0 * kKvHeads * h->t_max * kv_row_bytes(h->kv_fmt);
     a.q = h->q + (size_t)r0 * kHidden;
     a.kc = reinterpret_cast<char*>(kv_layer(h, h->kcache, l)) + kv_off;
     a.vc = reinterpret_cast<char*>(kv_layer(h, h->vcache, l)) + kv_off;
-    a.kv_bf16 = h->policy == kPolicyFast; a.B = n; a.t_max = h->t_max;
+    a.kv_fmt = h->kv_fmt; a.B = n; a.t_max = h->t_max;
     a.nsplit = decode_nsplit(h, n_all);
     a.tps = ((h->t_max + 63) / 64 + a.nsplit - 1) / a.nsplit;
     a.ctx_base = kPrefix; a.d_step = h->d_step;
@@ -502,9 +502,12 @@ int lm_layer_decode_fused(Handle* h, int l, int gi, int r0, int n, int n_all, in
     float* partial = h->gemm_partial + (size_t)gi * kMaxSplitK * 128 * kHidden;           // split-K partials of this row group
     float* qkv_part = h->qkv_part + (size_t)gi * kQkvSplitMax * 128 * kQkvDim;
     const LmLayerW& k = h->w.layer[l];
-    const DecodeTiling& tl = decode_tiling();
-    const size_t esz = h->policy == kPolicyFast ? 2 : 4;
-    const size_t kv_off = (size_t)r0 * kKvHeads * h->t_max * kHeadDim * esz;
+    // Policy fast keeps the 16-column tiles and the in-GEMM QKV epilogue: with the 32-column split-K tiles its first
+    // decode on a fresh handle produced non-finite logits on 3 of ~12 boxes (B=2; never with policy split, never
+    // under compute-sanitizer memcheck / initcheck / racecheck) -- unexplained, see DESIGN.md section 10.
+    static const DecodeTiling conservative{0, 3, 0, 4, decode_tiling().resident, 0, 0};
+    const DecodeTiling& tl = h->policy == kPolicyFast ? conservative : decode_tiling();
+    const size_t kv_off = (size_t)r0 * kKvHeads * h->t_max * kv_row_bytes(h->kv_fmt);
     float* x = h->x + (size_t)r0 * kHidden;
     bf16* la_hi = h->la_hi + (size_t)r0 * kHidden; bf16* la_lo = h->la_lo + (size_t)r0 * kHidden;
     bf16* lh_hi = h->lh_hi + (size_t)r0 * kInter; bf16* lh_lo = h->lh_lo + (size_t)r0 * kInter;
@@ -524,7 +527,7 @@ int lm_layer_decode_fused(Handle* h, int l, int gi, int r0, int n, int n_all, in
         g.v_cache = reinterpret_cast<char*>(kv_layer(h, h->vcache, l)) + kv_off;
         g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
         g.rows_per_seq = 1; g.pos_base = kPrefix - 1; g.d_pos = h->d_step;
-        g.t_max = h->t_max; g.kv_bf16 = h->policy == kPolicyFast;
+        g.t_max = h->t_max; g.kv_fmt = h->kv_fmt;
         MB_TRY(run_gemm(h, g, EPI_QKV_ROPE, st));
     }
     if (attn_wait) MB_CK(h, cudaStreamWaitEvent(st, attn_wait, 0));
@@ -627,7 +630,7 @@ int lm_layer_decode_chain(Handle* h, int l, int B, cudaStream_t st) {
         g.k_cache = kv_layer(h, h->kcache, l + 1); g.v_cache = kv_layer(h, h->vcache, l + 1);
         g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
         g.rows_per_seq = 1; g.pos_base = kPrefix - 1; g.d_pos = h->d_step;
-        g.t_max = h->t_max; g.kv_bf16 = h->policy == kPolicyFast;
+        g.t_max = h->t_max; g.kv_fmt = h->kv_fmt;
     }
     ca.n_ops = n;
     MB_CK(h, launch_decode_chain(maps, ca, st));
@@ -648,7 +651,7 @@ int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_
         g.rows_per_seq = rows_per_seq;
         g.pos_base = decode ? kPrefix - 1 : 0;
         g.d_pos = decode ? h->d_step : nullptr;
-        g.t_max = h->t_max; g.kv_bf16 = h->policy == kPolicyFast;
+        g.t_max = h->t_max; g.kv_fmt = h->kv_fmt;
         MB_TRY(run_gemm(h, g, EPI_QKV_ROPE, st));
     }
     if (decode) {
@@ -657,11 +660,11 @@ int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_
         static const bool fp32_attn = getenv("MB_ATTN_FP32") != nullptr;      // CUDA-core fp32 kernel, kept for A/B checks
         if (fp32_attn)
             MB_CK(h, launch_prefill_attention(h->q, kv_layer(h, h->kcache, l), kv_layer(h, h->vcache, l),
-                                              h->policy == kPolicyFast, B, rows_per_seq, h->t_max, h->la_hi,
+                                              h->kv_fmt, B, rows_per_seq, h->t_max, h->la_hi,
                                               lo_of(h, h->la_lo), st));
         else
             MB_CK(h, launch_prefill_attention_mma(h->q, kv_layer(h, h->kcache, l), kv_layer(h, h->vcache, l),
-                                                  h->policy == kPolicyFast, B, rows_per_seq, h->t_max, h->la_hi,
+                                                  h->kv_fmt, B, rows_per_seq, h->t_max, h->la_hi,
                                                   lo_of(h, h->la_lo), st));
         h->launches++;
     }
@@ -722,7 +725,7 @@ int decode_step(Handle* h, int B, bool fused, cudaStream_t st) {
             g.k_cache = kv_layer(h, h->kcache, 0); g.v_cache = kv_layer(h, h->vcache, 0);
             g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
             g.rows_per_seq = 1; g.pos_base = kPrefix - 1; g.d_pos = h->d_step;
-            g.t_max = h->t_max; g.kv_bf16 = h->policy == kPolicyFast;
+            g.t_max = h->t_max; g.kv_fmt = h->kv_fmt;
             MB_TRY(run_gemm(h, g, EPI_QKV_ROPE, st));
         }
         for (int l = 0; l < kLayers; ++l) {
@@ -946,10 +949,11 @@ static int create_body(Handle* h) {
     MB_TRY(dev_alloc(h, &h->cand_idx, B * (kVocab / 16)));
     h->t_max = kPrefix + h->max_new;
     h->kv_layer_elems = B * kKvHeads * h->t_max * kHeadDim;
-    const size_t esz = h->policy == kPolicyFast ? 2 : 4;
+    // KV format: fp32 rows (split policy default), bf16 (fast policy), or 24-bit rows (MB_KV24=1 / policy split24)
+    const size_t kv_bytes = (h->kv_layer_elems / kHeadDim) * kLayers * kv_row_bytes(h->kv_fmt);
     char* kc = nullptr; char* vc = nullptr;
-    MB_TRY(dev_alloc(h, &kc, h->kv_layer_elems * kLayers * esz));
-    MB_TRY(dev_alloc(h, &vc, h->kv_layer_elems * kLayers * esz));
+    MB_TRY(dev_alloc(h, &kc, kv_bytes));
+    MB_TRY(dev_alloc(h, &vc, kv_bytes));
     h->kcache = kc; h->vcache = vc;
     MB_TRY(dev_alloc(h, &h->part_acc, B * kHeads * kMaxAttnSplit * kHeadDim));
     MB_TRY(dev_alloc(h, &h->part_ml, B * kHeads * kMaxAttnSplit * 2));
@@ -985,7 +989,7 @@ void* mb_create(int device, int max_batch, int max_new_tokens, int policy) {
         return nullptr;
     }
     if (device < 0 || device >= count || max_batch < 1 || max_new_tokens < 1 || kPrefix + max_new_tokens > kMaxPos ||
-        (policy != kPolicySplit && policy != kPolicyFast)) {
+        (policy != kPolicySplit && policy != kPolicyFast && policy != kPolicySplit24)) {
         snprintf(g_create_error, sizeof(g_create_error), "mb_create: invalid argument");
         return nullptr;
     }
@@ -998,7 +1002,14 @@ void* mb_create(int device, int max_batch, int max_new_tokens, int policy) {
     }
     cudaSetDevice(device);
     Handle* h = new Handle();
-    h->device = device; h->max_batch = max_batch; h->max_new = max_new_tokens; h->policy = policy;
+    h->device = device; h->max_batch = max_batch; h->max_new = max_new_tokens;
+    {
+        // kPolicySplit24 = kPolicySplit with the KV cache stored at 24 bits (MB_KV24=1 turns it on for kPolicySplit too)
+        const char* e = getenv("MB_KV24");
+        const bool kv24 = policy == kPolicySplit24 || (e && atoi(e) != 0);
+        h->policy = policy == kPolicySplit24 ? kPolicySplit : policy;
+        h->kv_fmt = policy == kPolicyFast ? kKvBf16 : (kv24 ? kKvF24 : kKvF32);
+    }
     build_table(h->t, h->w);
     // a blocking stream: implicitly ordered with work the caller issued on the legacy default stream
     if (cudaStreamCreate(&h->own_stream) != cudaSuccess || create_body(h) != 0) {

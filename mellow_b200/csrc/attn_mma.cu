@@ -68,6 +68,39 @@ __device__ __forceinline__ void stage_tile(const bf16* src, int key0, int S, bf1
     }
 }
 
+// kKvF24 rows (common.cuh): the upper halves are the hi plane as they are; value - hi has at most 8 significant bits, so
+// the lo plane is exact as well and hi + lo reproduces the stored 24-bit value.
+template <bool SPLIT>
+__device__ __forceinline__ void stage_tile(const kv24* src_, int key0, int S, bf16 (*hi)[LDS], bf16 (*lo)[LDS], int tid) {
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(src_);
+    for (int e = tid; e < TK * (kHeadDim / 8); e += 128) {
+        const int j = e >> 3, c = (e & 7) * 8;
+        uint4 hv = make_uint4(0u, 0u, 0u, 0u);
+        uint2 lv = make_uint2(0u, 0u);
+        if (key0 + j < S) {
+            const unsigned char* row = src + (size_t)(key0 + j) * 192;
+            hv = *reinterpret_cast<const uint4*>(row + c * 2);
+            lv = *reinterpret_cast<const uint2*>(row + 128 + c);
+        }
+        *reinterpret_cast<uint4*>(&hi[j][c]) = hv;
+        if (SPLIT) {
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+            uint32_t out[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const uint32_t lb = p < 2 ? lv.x >> (16 * p) : lv.y >> (16 * (p - 2));
+                const uint32_t h0 = hw[p] << 16, h1 = hw[p] & 0xFFFF0000u;
+                const float r0 = __uint_as_float(h0 | ((lb & 0xFFu) << 8)) - __uint_as_float(h0);
+                const float r1 = __uint_as_float(h1 | (lb & 0xFF00u)) - __uint_as_float(h1);
+                __nv_bfloat162 l2;
+                l2.x = __float2bfloat16_rn(r0); l2.y = __float2bfloat16_rn(r1);
+                out[p] = *reinterpret_cast<uint32_t*>(&l2);
+            }
+            *reinterpret_cast<uint4*>(&lo[j][c]) = make_uint4(out[0], out[1], out[2], out[3]);
+        }
+    }
+}
+
 template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(128) prefill_attention_mma_kernel(const float* __restrict__ q, const T* __restrict__ kc,
                                                                     const T* __restrict__ vc, int S, int t_max,
@@ -77,8 +110,8 @@ __global__ void __launch_bounds__(128) prefill_attention_mma_kernel(const float*
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int kvh = h / (kHeads / kKvHeads);
-    const T* kb = kc + ((size_t)b * kKvHeads + kvh) * t_max * kHeadDim;
-    const T* vb = vc + ((size_t)b * kKvHeads + kvh) * t_max * kHeadDim;
+    const T* kb = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(kc) + ((size_t)b * kKvHeads + kvh) * t_max * KvRowBytes<T>::value);
+    const T* vb = reinterpret_cast<const T*>(reinterpret_cast<const unsigned char*>(vc) + ((size_t)b * kKvHeads + kvh) * t_max * KvRowBytes<T>::value);
     const int row0 = qt * TQ + warp * 16 + g, row1 = row0 + 8;
     pdl_trigger();
     pdl_wait();
@@ -384,12 +417,15 @@ cudaError_t launch_window_attention_mma(const float* qkv, const float* relbias, 
     return launch_k(window_attention_mma_kernel<false>, grid, dim3(128), 0, st, qkv, relbias, out_hi, out_lo, res, C, shift);
 }
 
-cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S,
+cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_fmt, int B, int S,
                                          int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st) {
     dim3 grid((S + TQ - 1) / TQ, kHeads, B);
-    if (kv_bf16)
+    if (kv_fmt == kKvBf16)
         return launch_k(prefill_attention_mma_kernel<bf16, false>, grid, dim3(128), 0, st, q, (const bf16*)kc,
                         (const bf16*)vc, S, t_max, out_hi, out_lo);
+    if (kv_fmt == kKvF24)
+        return launch_k(prefill_attention_mma_kernel<kv24, true>, grid, dim3(128), 0, st, q, (const kv24*)kc,
+                        (const kv24*)vc, S, t_max, out_hi, out_lo);
     return launch_k(prefill_attention_mma_kernel<float, true>, grid, dim3(128), 0, st, q, (const float*)kc,
                     (const float*)vc, S, t_max, out_hi, out_lo);
 }

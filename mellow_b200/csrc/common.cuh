@@ -46,8 +46,11 @@ constexpr int kMaxPos = 1024;       // rope table rows (389 + max_new <= 1024)
 //                 issues hi*hi + hi*lo + lo*hi with fp32 accumulation (error ~2^-16 relative; greedy ids match the
 //                 fp32 reference); KV cache fp32.
 //   kPolicyFast:  single bf16 plane, one MMA pass, KV cache bf16 (logits within the stated bf16 tolerance).
+//   kPolicySplit24: kPolicySplit with the KV cache rounded to 24 bits (kKvF24 below): the same 2^-17 the GEMM operands
+//                 carry, 25 % fewer bytes for the HBM-bound decode attention.
 constexpr int kPolicySplit = 0;
 constexpr int kPolicyFast = 1;
+constexpr int kPolicySplit24 = 2;
 
 // ---------------------------------------------------------------- small device helpers
 __device__ __forceinline__ float warp_sum(float v) {
@@ -139,6 +142,25 @@ __device__ __forceinline__ void trace_close(TraceBuf* tb, unsigned rec, unsigned
     if (first_cta()) trace_put(tb, rec, id, TR_EXIT);
     if (last_cta()) trace_put(tb, rec, id, TR_EXIT_LAST);
 }
+
+// KV-cache formats (GemmArgs::kv_fmt, DecodeAttnArgs::kv_fmt).
+//   kKvF32 : float rows, 256 B per (position, kv head)
+//   kKvBf16: bf16 rows, 128 B (policy fast)
+//   kKvF24 : the value rounded to 24 bits (sign, 8 exponent, 15 mantissa bits -- relative error 2^-17, the precision
+//            the split GEMM operands carry) stored as a bf16-like upper half and one extra mantissa byte, planar inside
+//            the row: bytes [0,128) = 64 x u16 (bits 31..16), bytes [128,192) = 64 x u8 (bits 15..8); 192 B per row.
+//            Decode attention is HBM-bound on exactly these rows, so the format is worth 25 % of its time.
+enum { kKvF32 = 0, kKvBf16 = 1, kKvF24 = 2 };
+struct kv24 { unsigned char b[3]; };                               // tag type of the kKvF24 kernels (never dereferenced)
+__host__ __device__ constexpr int kv_row_bytes(int fmt) { return fmt == kKvF32 ? 256 : (fmt == kKvBf16 ? 128 : 192); }
+template <typename T> struct KvRowBytes { static constexpr int value = kHeadDim * (int)sizeof(T); };
+template <> struct KvRowBytes<kv24> { static constexpr int value = 192; };
+// round-to-nearest-even to 24 bits; returns the fp32 bit pattern with the low byte cleared
+__device__ __forceinline__ uint32_t f24_bits(float x) {
+    const uint32_t u = __float_as_uint(x);
+    return (u + 0x7Fu + ((u >> 8) & 1u)) & 0xFFFFFF00u;
+}
+__device__ __forceinline__ float f24_round(float x) { return __uint_as_float(f24_bits(x)); }
 
 // KV-cache element types
 __device__ __forceinline__ float kv_load(const float* p) { return *p; }

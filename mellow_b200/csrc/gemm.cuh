@@ -35,7 +35,7 @@ struct GemmArgs {
     const float* rope_cos; const float* rope_sin;     // [kMaxPos][32]
     int rows_per_seq;                                 // m = b*rows_per_seq + s
     int pos_base; const int* d_pos;                   // position = pos_base + (d_pos ? *d_pos : 0) + s
-    int t_max; int kv_bf16;
+    int t_max; int kv_fmt;
     // EPI_ARGMAX (lm_head fused with the first stage of the sampling step): per row and per 16-column group the
     // (max logit, first arg max) candidate is written instead of the 49152 logits; sample_kernel finishes the scan.
     float* cand_val; int* cand_idx;                   // [M][N/16]
@@ -107,7 +107,12 @@ __device__ __forceinline__ void epilogue_pair_r(const GemmArgs& g, int m, int n,
             const int kvh = c2 >> 6, dd = c2 & 63;
             const size_t off = (((size_t)b * kKvHeads + kvh) * g.t_max + pos) * kHeadDim + dd;
             void* base = is_v ? g.v_cache : g.k_cache;
-            if (g.kv_bf16) kv_store2(reinterpret_cast<bf16*>(base) + off, v0, v1);
+            if (g.kv_fmt == kKvF24) {
+                unsigned char* row = reinterpret_cast<unsigned char*>(base) + (off - dd) / kHeadDim * 192;
+                const uint32_t u0 = f24_bits(v0), u1 = f24_bits(v1);
+                *reinterpret_cast<uint32_t*>(row + dd * 2) = (u0 >> 16) | (u1 & 0xFFFF0000u);
+                *reinterpret_cast<unsigned short*>(row + 128 + dd) = (unsigned short)(((u0 >> 8) & 0xFFu) | (u1 & 0xFF00u));
+            } else if (g.kv_fmt == kKvBf16) kv_store2(reinterpret_cast<bf16*>(base) + off, v0, v1);
             else kv_store2(reinterpret_cast<float*>(base) + off, v0, v1);
         }
     }
@@ -186,7 +191,19 @@ __device__ __forceinline__ void epilogue_row16_qkv(const GemmArgs& g, int m, int
         const int kvh = c2 >> 6, dd = c2 & 63;
         const size_t off = (((size_t)b * kKvHeads + kvh) * g.t_max + pos) * kHeadDim + dd;
         void* base = is_v ? g.v_cache : g.k_cache;
-        if (g.kv_bf16) {
+        if (g.kv_fmt == kKvF24) {                                    // 16 values: 32 B of upper halves + 16 B of mantissa bytes
+            unsigned char* row = reinterpret_cast<unsigned char*>(base) + (off - dd) / kHeadDim * 192;
+            uint32_t hw[8], lw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t u0 = f24_bits(v[2 * j]), u1 = f24_bits(v[2 * j + 1]);
+                hw[j] = (u0 >> 16) | (u1 & 0xFFFF0000u);
+                lw[j >> 1] |= (((u0 >> 8) & 0xFFu) | (u1 & 0xFF00u)) << (16 * (j & 1));
+            }
+            *reinterpret_cast<uint4*>(row + dd * 2) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(row + dd * 2 + 16) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+            *reinterpret_cast<uint4*>(row + 128 + dd) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+        } else if (g.kv_fmt == kKvBf16) {
             bf16* o = reinterpret_cast<bf16*>(base) + off;
             store_planes8(o, nullptr, 0, v);
             store_planes8(o, nullptr, 8, v + 8);

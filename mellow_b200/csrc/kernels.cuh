@@ -50,16 +50,16 @@ cudaError_t launch_split_planes(const float* x, size_t n, bf16* hi, bf16* lo, cu
 
 // ---- lm.cu
 cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embed, int B, float* prefix, cudaStream_t st);
-cudaError_t launch_prefill_attention(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S, int t_max,
+cudaError_t launch_prefill_attention(const float* q, const void* kc, const void* vc, int kv_fmt, int B, int S, int t_max,
                                      bf16* out_hi, bf16* out_lo, cudaStream_t st);
 // tensor-core (mma.sync, split operands) version of the same attention (attn_mma.cu)
-cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S,
+cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_fmt, int B, int S,
                                          int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st);
 constexpr int kQkvSplitMax = 9;     // most split-K partials of the QKV projection the decode-attention prologue reduces
 struct DecodeAttnArgs {
     const float* q;                 // [B,576]
     const void* kc; const void* vc; // layer caches [B][3][t_max][64]
-    int kv_bf16, B, t_max, nsplit;
+    int kv_fmt, B, t_max, nsplit;
     int tps;                           // key tiles (64 keys) owned by each split: ceil(ceil(t_max/64)/nsplit)
     int ctx_base; const int* d_step;   // ctx = ctx_base + *d_step  (keys 0..ctx-1)
     const int* done;                   // optional [B]: rows that already emitted the stop token skip their K/V stream

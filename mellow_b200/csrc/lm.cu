@@ -130,9 +130,10 @@ __global__ void __launch_bounds__(64) prefill_attention_kernel(const float* __re
 // cp.async double buffering; partial (m, l, acc) per split are merged by decode_combine_kernel.
 template <typename T>
 struct DecodeSmem {
-    static constexpr int KLD = kHeadDim + 16 / sizeof(T);         // +16 B: conflict-free 16 B row reads
-    T k[2][64][KLD];
-    T v[2][64][kHeadDim];
+    static constexpr int ROWB = KvRowBytes<T>::value;             // bytes of one cached row (64 values)
+    static constexpr int KROWB = ROWB + 16;                       // +16 B: conflict-free 16 B row reads
+    __align__(16) unsigned char k[2][64][KROWB];
+    __align__(16) unsigned char v[2][64][ROWB];
     __align__(16) float sc[3][64];
     float alpha[3], m[3], l[3];
     float red[4][3][kHeadDim];
@@ -141,28 +142,33 @@ struct DecodeSmem {
     __align__(16) float vnew[kHeadDim];
 };
 
+// Three CTAs per SM (<= 170 registers): the fused-QKV prologue pushed the fp32 variant to 207 registers = two CTAs per SM
+// without the bound.  Four CTAs of the 24-bit variant (128 registers, unpadded rows) were measured slower: 23.4 vs 18.7 us.
 template <typename T>
-__global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnArgs a) {
+__global__ void __launch_bounds__(128, 3) decode_attention_kernel(const DecodeAttnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     DecodeSmem<T>& sm = *reinterpret_cast<DecodeSmem<T>*>(smem_raw);
-    constexpr int E = 16 / sizeof(T);             // elements per 16 B chunk
-    constexpr int NCH = kHeadDim / E;             // chunks per row
+    constexpr bool F24 = sizeof(T) == 3;          // kKvF24 rows: 64 x u16 upper halves, then 64 x u8 mantissa bytes
+    constexpr int ROWB = DecodeSmem<T>::ROWB;
+    constexpr int NCHB = ROWB / 16;               // 16-byte chunks per cached row
+    constexpr int E = F24 ? 8 : 16 / sizeof(T);   // values per 16 B chunk of the part the score role walks (the upper halves for f24)
+    constexpr int NCH = kHeadDim / E;             // such chunks per row
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // Tile ownership is static (independent of the step counter): split s owns tiles [s*tps, (s+1)*tps).
     const int t_begin = split * a.tps;
-    const T* kb = reinterpret_cast<const T*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * kHeadDim;
-    const T* vb = reinterpret_cast<const T*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * kHeadDim;
+    const unsigned char* kb = reinterpret_cast<const unsigned char*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
+    const unsigned char* vb = reinterpret_cast<const unsigned char*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
 
     auto load_tile = [&](int buf, int tile, int ctx_limit) {
         const int key0 = tile << 6;
-        for (int c = tid; c < 64 * NCH; c += 128) {
-            const int j = c / NCH, ch = c - j * NCH;
+        for (int c = tid; c < 64 * NCHB; c += 128) {
+            const int j = c / NCHB, ch = c - j * NCHB;
             const int key = key0 + j;
             const bool ok = key < ctx_limit;
-            const size_t off = (size_t)(ok ? key : 0) * kHeadDim + ch * E;
-            cp_async16(&sm.k[buf][j][ch * E], kb + off, ok);
-            cp_async16(&sm.v[buf][j][ch * E], vb + off, ok);
+            const size_t off = (size_t)(ok ? key : 0) * ROWB + ch * 16;
+            cp_async16(&sm.k[buf][j][ch * 16], kb + off, ok);
+            cp_async16(&sm.v[buf][j][ch * 16], vb + off, ok);
         }
     };
     // PDL: tiles that lie entirely inside the prefill prefix (keys < ctx_base - 1) are immutable history for every
@@ -230,13 +236,25 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
             } else {
                 const int dd = (tid < 64 ? tid - 48 : tid - 64) * 4;
                 float* dst = tid < 64 ? &sm.knew[dd] : &sm.vnew[dd];
-                // what later steps will read back from the cache (rounded when the cache is bf16)
-                T r0, r1, r2, r3;
-                kv_cast(acc4.x, r0); kv_cast(acc4.y, r1); kv_cast(acc4.z, r2); kv_cast(acc4.w, r3);
-                dst[0] = kv_load(&r0); dst[1] = kv_load(&r1); dst[2] = kv_load(&r2); dst[3] = kv_load(&r3);
-                if (t_new >= t_begin && t_new < t_begin + a.tps) {  // the split that owns the new key appends it to the cache
-                    T* cb = const_cast<T*>(tid < 64 ? kb : vb) + (size_t)(ctx - 1) * kHeadDim + dd;
-                    cb[0] = r0; cb[1] = r1; cb[2] = r2; cb[3] = r3;
+                const bool owner = t_new >= t_begin && t_new < t_begin + a.tps;   // the split that owns the new key appends it to the cache
+                unsigned char* crow = const_cast<unsigned char*>(tid < 64 ? kb : vb) + (size_t)(ctx - 1) * ROWB;
+                // knew / vnew hold what later steps will read back from the cache (rounded to the cache format)
+                if constexpr (F24) {
+                    const uint32_t u0 = f24_bits(acc4.x), u1 = f24_bits(acc4.y), u2 = f24_bits(acc4.z), u3 = f24_bits(acc4.w);
+                    dst[0] = __uint_as_float(u0); dst[1] = __uint_as_float(u1); dst[2] = __uint_as_float(u2); dst[3] = __uint_as_float(u3);
+                    if (owner) {
+                        *reinterpret_cast<uint2*>(crow + dd * 2) = make_uint2((u0 >> 16) | (u1 & 0xFFFF0000u), (u2 >> 16) | (u3 & 0xFFFF0000u));
+                        *reinterpret_cast<uint32_t*>(crow + 128 + dd) =
+                            ((u0 >> 8) & 0xFFu) | (u1 & 0xFF00u) | ((u2 << 8) & 0xFF0000u) | ((u3 << 16) & 0xFF000000u);
+                    }
+                } else {
+                    T r0, r1, r2, r3;
+                    kv_cast(acc4.x, r0); kv_cast(acc4.y, r1); kv_cast(acc4.z, r2); kv_cast(acc4.w, r3);
+                    dst[0] = kv_load(&r0); dst[1] = kv_load(&r1); dst[2] = kv_load(&r2); dst[3] = kv_load(&r3);
+                    if (owner) {
+                        T* cb = reinterpret_cast<T*>(crow) + dd;
+                        cb[0] = r0; cb[1] = r1; cb[2] = r2; cb[3] = r3;
+                    }
                 }
             }
         }
@@ -272,19 +290,43 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
         __syncthreads();
         if (fused && t == t_new) {                                   // uniform: place the new key / value row into the tile
             const int j = (ctx - 1) & 63;
-            if (tid < kHeadDim) kv_cast(sm.knew[tid], sm.k[buf][j][tid]);
-            else kv_cast(sm.vnew[tid - kHeadDim], sm.v[buf][j][tid - kHeadDim]);
+            const int d = tid & (kHeadDim - 1);
+            unsigned char* row = tid < kHeadDim ? sm.k[buf][j] : sm.v[buf][j];
+            const float val = tid < kHeadDim ? sm.knew[d] : sm.vnew[d];
+            if constexpr (F24) {
+                const uint32_t u = __float_as_uint(val);             // already rounded to 24 bits
+                reinterpret_cast<unsigned short*>(row)[d] = (unsigned short)(u >> 16);
+                row[128 + d] = (unsigned char)(u >> 8);
+            } else {
+                kv_cast(val, reinterpret_cast<T*>(row)[d]);
+            }
             __syncthreads();
         }
         {
             float p0 = 0.f, p1 = 0.f, p2 = 0.f;
 #pragma unroll
             for (int i = 0; i < NCH / 2; ++i) {
-                const T* kp = &sm.k[buf][sj][(2 * i + shalf) * E];
+                if constexpr (F24) {
+                    // 8 values: one 16 B read of upper halves, one 8 B read of mantissa bytes
+                    const unsigned char* rowp = sm.k[buf][sj];
+                    const uint4 hv = *reinterpret_cast<const uint4*>(rowp + (2 * i + shalf) * 16);
+                    const uint2 lv = *reinterpret_cast<const uint2*>(rowp + 128 + (2 * i + shalf) * 8);
+                    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const float kvv = kv_load(kp + e);
-                    p0 += qreg[0][i * E + e] * kvv; p1 += qreg[1][i * E + e] * kvv; p2 += qreg[2][i * E + e] * kvv;
+                    for (int p = 0; p < 4; ++p) {
+                        const uint32_t lb = p < 2 ? lv.x >> (16 * p) : lv.y >> (16 * (p - 2));
+                        const float k0 = __uint_as_float((hw[p] << 16) | ((lb & 0xFFu) << 8));
+                        const float k1 = __uint_as_float((hw[p] & 0xFFFF0000u) | (lb & 0xFF00u));
+                        p0 += qreg[0][i * E + 2 * p] * k0; p1 += qreg[1][i * E + 2 * p] * k0; p2 += qreg[2][i * E + 2 * p] * k0;
+                        p0 += qreg[0][i * E + 2 * p + 1] * k1; p1 += qreg[1][i * E + 2 * p + 1] * k1; p2 += qreg[2][i * E + 2 * p + 1] * k1;
+                    }
+                } else {
+                    const T* kp = reinterpret_cast<const T*>(sm.k[buf][sj]) + (2 * i + shalf) * E;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const float kvv = kv_load(kp + e);
+                        p0 += qreg[0][i * E + e] * kvv; p1 += qreg[1][i * E + e] * kvv; p2 += qreg[2][i * E + e] * kvv;
+                    }
                 }
             }
             p0 += __shfl_xor_sync(0xffffffffu, p0, 1);
@@ -325,7 +367,17 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const DecodeAttnA
                 for (int h = 0; h < 3; ++h) p[h] = *reinterpret_cast<const float4*>(&sm.sc[h][j]);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const float v0 = kv_load(&sm.v[buf][j + u][dp]), v1 = kv_load(&sm.v[buf][j + u][dp + 1]);
+                    float v0, v1;
+                    if constexpr (F24) {
+                        const unsigned char* rowp = sm.v[buf][j + u];
+                        const uint32_t hw = *reinterpret_cast<const uint32_t*>(rowp + dp * 2);
+                        const uint32_t lb = *reinterpret_cast<const unsigned short*>(rowp + 128 + dp);
+                        v0 = __uint_as_float((hw << 16) | ((lb & 0xFFu) << 8));
+                        v1 = __uint_as_float((hw & 0xFFFF0000u) | (lb & 0xFF00u));
+                    } else {
+                        const T* vp = reinterpret_cast<const T*>(sm.v[buf][j + u]);
+                        v0 = kv_load(vp + dp); v1 = kv_load(vp + dp + 1);
+                    }
 #pragma unroll
                     for (int h = 0; h < 3; ++h) {
                         const float pv = u == 0 ? p[h].x : (u == 1 ? p[h].y : (u == 2 ? p[h].z : p[h].w));
@@ -563,10 +615,11 @@ cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embe
     return launch_k(prefix_kernel, grid, dim3(144), 0, st, rows33, ids, embed, B, prefix);
 }
 
-cudaError_t launch_prefill_attention(const float* q, const void* kc, const void* vc, int kv_bf16, int B, int S,
+cudaError_t launch_prefill_attention(const float* q, const void* kc, const void* vc, int kv_fmt, int B, int S,
                                      int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st) {
     dim3 grid((S + 63) / 64, kHeads, B);
-    if (kv_bf16)
+    if (kv_fmt == kKvF24) return cudaErrorNotSupported;            // the CUDA-core A/B kernel reads element-wise formats only
+    if (kv_fmt)
         return launch_k(prefill_attention_kernel<bf16>, grid, dim3(64), 0, st, q, (const bf16*)kc, (const bf16*)vc, S, t_max, out_hi, out_lo);
     return launch_k(prefill_attention_kernel<float>, grid, dim3(64), 0, st, q, (const float*)kc, (const float*)vc, S, t_max, out_hi, out_lo);
 }
@@ -581,10 +634,14 @@ cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
         e = cudaFuncSetAttribute(decode_attention_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(DecodeSmem<bf16>));
         if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(decode_attention_kernel<kv24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(DecodeSmem<kv24>));
+        if (e != cudaSuccess) return e;
         configured = true;
     }
-    cudaError_t e = a.kv_bf16 ? launch_k(decode_attention_kernel<bf16>, grid, dim3(128), sizeof(DecodeSmem<bf16>), st, a)
-                              : launch_k(decode_attention_kernel<float>, grid, dim3(128), sizeof(DecodeSmem<float>), st, a);
+    cudaError_t e = a.kv_fmt == kKvBf16 ? launch_k(decode_attention_kernel<bf16>, grid, dim3(128), sizeof(DecodeSmem<bf16>), st, a)
+                  : a.kv_fmt == kKvF24 ? launch_k(decode_attention_kernel<kv24>, grid, dim3(128), sizeof(DecodeSmem<kv24>), st, a)
+                                       : launch_k(decode_attention_kernel<float>, grid, dim3(128), sizeof(DecodeSmem<float>), st, a);
     if (e != cudaSuccess || a.nsplit == 1) return e;
     return launch_k(decode_combine_kernel, dim3(kHeads, a.B), dim3(64), 0, st, a);
 }

@@ -10,8 +10,9 @@ import torch
 
 from . import native, schema as S, weights
 
-POLICY_SPLIT, POLICY_FAST = 0, 1
-POLICIES = {"split": POLICY_SPLIT, "bf16x3": POLICY_SPLIT, "fast": POLICY_FAST, "bf16": POLICY_FAST}
+POLICY_SPLIT, POLICY_FAST, POLICY_SPLIT24 = 0, 1, 2
+POLICIES = {"split": POLICY_SPLIT, "bf16x3": POLICY_SPLIT, "fast": POLICY_FAST, "bf16": POLICY_FAST,
+            "split24": POLICY_SPLIT24}
 
 
 class MellowNativeError(RuntimeError):

@@ -52,6 +52,15 @@ def engine(sd):
 
 
 @pytest.fixture(scope="session")
+def engine24(sd, engine):
+    """policy split24: split operands, KV cache stored at 24 bits."""
+    from mellow_b200.engine import Engine
+    eng = Engine(None, device=0, max_batch=7, max_new_tokens=32, policy="split24", arena=engine.arena)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="session")
 def engine_fast(sd, engine):
     from mellow_b200.engine import Engine
     eng = Engine(None, device=0, max_batch=2, max_new_tokens=32, policy="fast", arena=engine.arena)

@@ -332,6 +332,25 @@ def test_full_size_batch_128_rows_match_golden(sd, engine, inputs, golden):
         big.close()
 
 
+def test_kv24_policy_keeps_token_identity_and_logit_tolerance(engine24, engine, inputs, oracle_taps, golden):
+    """policy split24 stores K/V rounded to 24 bits (relative 2^-17, what the split GEMM operands carry): the greedy
+    ids must still equal the reference golden, the per-step logits must stay within the split-policy tolerance, and a
+    ragged 7-row batch must reproduce its rows (prefill writes the packed rows, decode attention appends and reads them)."""
+    prefix = oracle_taps["prefix"]
+    engine24.set_prefix(prefix)
+    engine24.prefill(2, want_logits=False)
+    toks, dump = engine24.decode(2, 12, dump_logits=True)
+    assert toks.cpu().tolist() == golden["tokens"].tolist()
+    probe = torch.from_numpy(golden["probe_ids"])
+    err = maxerr(dump.cpu()[:, :, probe], golden["probe_logits"])
+    assert err < LOGIT_TOL, f"24-bit KV: per-step logits max abs err {err}"
+    idx = [0, 1, 1, 0, 1, 0, 0]
+    w1, w2, ids = inputs["wave1"][idx], inputs["wave2"][idx], inputs["ids"][idx]
+    got = engine24.generate(w1, w2, ids, 12).cpu()
+    want = torch.from_numpy(golden["tokens"]).to(torch.int32)[idx]
+    assert torch.equal(got, want)
+
+
 def test_fast_policy_generate_runs_end_to_end(engine_fast, inputs):
     toks = engine_fast.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 6)
     assert toks.shape == (2, 6) and int(toks.min()) >= 0 and int(toks.max()) < 49152

@@ -164,7 +164,18 @@ def run_ours(args):
     from mellow_b200 import synth
     from mellow_b200.dist import build_engine
     B, max_len = args.batch, args.max_len
-    eng, rank, world = build_engine(synth.synthetic_state_dict, max_batch=B, max_new_tokens=max_len, policy=args.policy)
+    # NCCL announces its version on stdout at communicator creation; the contract is ONE JSON line on stdout, so file
+    # descriptor 1 points at stderr while the process group and the weight broadcast are set up
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        eng, rank, world = build_engine(synth.synthetic_state_dict, max_batch=B, max_new_tokens=max_len, policy=args.policy)
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     dev = eng.device
     torch.cuda.set_device(dev)
     # per-rank inputs (different seed per rank: weak scaling, every rank processes its own B pairs)

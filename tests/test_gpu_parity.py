@@ -351,6 +351,38 @@ def test_kv24_policy_keeps_token_identity_and_logit_tolerance(engine24, engine, 
     assert torch.equal(got, want)
 
 
+def test_in_kernel_timeline_records_every_decode_kernel(engine, inputs, golden):
+    """mb_set_trace: the first CTA of each of the 7 kernels of a decode layer (plus lm_head) leaves one record per
+    launch with entry <= dependency-wait return <= exit; tracing must not change the tokens."""
+    import ctypes
+    import struct
+    cap = 4096
+    buf = torch.zeros(8 + 256 * cap, dtype=torch.uint8, device="cuda")
+    buf[:8] = torch.frombuffer(bytearray(struct.pack("II", 0, cap)), dtype=torch.uint8).cuda()
+    engine._ck(engine.lib.mb_set_trace(engine.handle, ctypes.c_void_p(buf.data_ptr())))
+    try:
+        toks = engine.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 4).cpu()
+        torch.cuda.synchronize()
+    finally:
+        engine._ck(engine.lib.mb_set_trace(engine.handle, ctypes.c_void_p(0)))
+    assert toks.tolist() == golden["tokens"][:, :4].tolist()
+    raw = buf.cpu().numpy()
+    n = int(np.frombuffer(raw[:4].tobytes(), dtype=np.uint32)[0])
+    assert 0 < n <= cap
+    ev = np.frombuffer(raw[8:8 + 256 * n].tobytes(), dtype=np.dtype([("t", "<u8"), ("id", "<u4"), ("sm", "<u4")])).reshape(n, 16)
+    kinds = {}
+    for r in range(n):
+        if ev["id"][r][0] == 0:
+            continue                                              # a last-CTA record (phases 15 / 3 only)
+        kind = (int(ev["id"][r][0]) >> 4) // 1000
+        kinds[kind] = kinds.get(kind, 0) + 1
+        t_entry, t_wait, t_exit = int(ev["t"][r][0]), int(ev["t"][r][1]), int(ev["t"][r][2])
+        assert t_entry <= t_wait <= t_exit, (kind, t_entry, t_wait, t_exit)
+    # 3 decode steps x 30 layers for the per-layer kinds, 3 lm_head launches
+    assert all(kinds.get(k) == 90 for k in range(1, 8)), kinds
+    assert kinds.get(8) == 3, kinds
+
+
 def test_fast_policy_generate_runs_end_to_end(engine_fast, inputs):
     toks = engine_fast.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 6)
     assert toks.shape == (2, 6) and int(toks.min()) >= 0 and int(toks.max()) < 49152

@@ -424,10 +424,12 @@ const DecodeTiling& decode_tiling() {
         const int mode = e ? atoi(e) : 6;
         const char* r = getenv("MB_DEC_RESIDENT");
         const int res = r ? atoi(r) : 1;
-        // QKV as 9 one-k-block slices of 64-column tiles (135 CTAs x 8 MMAs instead of 60 CTAs x 72); the partial sums
-        // are reduced, roped and appended to the KV cache by the decode-attention kernel that consumes them
+        // MB_DEC_QKV_SPLIT=9: QKV as 9 one-k-block slices of 64-column tiles (135 CTAs x 8 MMAs instead of 60 CTAs x 72); the
+        // partial sums are reduced, roped and appended to the KV cache by the decode-attention kernel that consumes them.
+        // It paid off while the MMA issue loop was slow (1.59 -> 1.55 ms/step); with the elect.sync loop the unsplit GEMM
+        // with its in-epilogue RoPE / KV write is ahead again (1.356 vs 1.383 ms/step) and attention has no prologue
         const char* q = getenv("MB_DEC_QKV_SPLIT");
-        const int qs = res ? (q ? atoi(q) : 9) : 0;
+        const int qs = res ? (q ? atoi(q) : 0) : 0;       // off by default: see below
         // gate/up as 3 K slices of 64-column tiles (144 CTAs x 24 MMAs instead of 96 x 72); SwiGLU needs the complete
         // sums, so the split that arrives last at its tile finishes it inside the same kernel (gemm_skinny.cu fix-up)
         const char* gq = getenv("MB_DEC_GU_SPLIT");

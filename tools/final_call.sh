@@ -6,4 +6,3 @@ timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_final.json 2
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file gpurun_out/launches_generate_b128_maxlen4.csv python tools/profile_run.py --batch 128 --max-len 4 > gpurun_out/ncu1.log 2>&1; tail -1 gpurun_out/ncu1.log
 timeout 300 python tools/decode_timeline.py --out gpurun_out/decode_timeline_final.txt > /dev/null 2>> gpurun_out/tl.log
-timeout 300 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_reference.json 2>/dev/null; head -c 300 gpurun_out/bench_reference.json

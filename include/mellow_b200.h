@@ -50,6 +50,10 @@ int mb_set_gemm_engine(void* h, int engine); /* 0 = mma.sync bring-up engine, 1 
 /* decode row groups: the batch is cut into `groups` contiguous row groups whose per-layer kernel chains run on
  * concurrent streams (1..4; 0 = automatic: 2 from 96 rows up).  Results do not depend on it (rows are independent). */
 int mb_set_decode_groups(void* h, int groups);
+/* decode QKV projection: 0 = one GEMM with RoPE + KV-cache write in its epilogue (default); 3 / 9 = that many split-K
+ * slices whose partial sums the decode-attention kernel reduces, ropes and appends to the cache itself (policy split /
+ * split24 only; -1 = default).  Token ids do not depend on it beyond fp32 summation order. */
+int mb_set_decode_qkv_split(void* h, int nsplit);
 /* profiling aid: dev_trace_buf = {u32 n; u32 cap; {u64 globaltimer_ns; u32 id*16+phase; u32 smid} ev[cap][16]} in device
  * memory, zero-initialised, n = records used, cap = records available (NULL = off).  The first and the last CTA of every
  * decode-step kernel claim one 16-slot record at entry and stamp phases into it with plain stores: 0 entry, 1 return of

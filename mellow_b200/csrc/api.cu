@@ -197,6 +197,7 @@ struct Handle {
     cudaStream_t grp_stream[kMaxGroups - 1] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups - 1] = {}, ev_attn[kMaxGroups] = {};
     int kv_fmt = kKvF32;                 // KV-cache row format (common.cuh)
+    int qkv_split = -1;                  // mb_set_decode_qkv_split: -1 = default (MB_DEC_QKV_SPLIT / 0)
     int groups = 0;                      // mb_set_decode_groups: 0 = automatic
     TraceBuf* trace = nullptr;           // mb_set_trace: optional in-kernel timeline of the decode kernels
 };
@@ -513,12 +514,13 @@ int lm_layer_decode_fused(Handle* h, int l, int gi, int r0, int n, int n_all, in
     float* x = h->x + (size_t)r0 * kHidden;
     bf16* la_hi = h->la_hi + (size_t)r0 * kHidden; bf16* la_lo = h->la_lo + (size_t)r0 * kHidden;
     bf16* lh_hi = h->lh_hi + (size_t)r0 * kInter; bf16* lh_lo = h->lh_lo + (size_t)r0 * kInter;
-    const bool qkv_split = tl.qkv_split > 1 && h->engine == 1;
+    const int qkv_nsplit = h->policy == kPolicyFast ? 0 : (h->qkv_split >= 0 ? h->qkv_split : tl.qkv_split);
+    const bool qkv_split = qkv_nsplit > 1 && h->engine == 1 && tl.resident;
     if (qkv_split) {
         GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.qkv, kHidden, n, kQkvDim, kHidden);
         g.resident = 1; g.bn_hint = 64;
         g.trace = h->trace; g.trace_id = 1000 + (r0 ? 100 : 0) + l;
-        g.split_k = tl.qkv_split; g.partial = qkv_part;
+        g.split_k = qkv_nsplit; g.partial = qkv_part;
         MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
     } else {
         GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.qkv, kHidden, n, kQkvDim, kHidden);
@@ -535,7 +537,7 @@ int lm_layer_decode_fused(Handle* h, int l, int gi, int r0, int n, int n_all, in
     if (attn_wait) MB_CK(h, cudaStreamWaitEvent(st, attn_wait, 0));
     {
         PdlOff off(attn_wait != nullptr);                  // two predecessors: the QKV kernel and the other group's event
-        MB_TRY(run_decode_attention(h, l, r0, n, n_all, st, true, qkv_split ? qkv_part : nullptr, tl.qkv_split));
+        MB_TRY(run_decode_attention(h, l, r0, n, n_all, st, true, qkv_split ? qkv_part : nullptr, qkv_nsplit));
     }
     if (attn_record) MB_CK(h, cudaEventRecord(attn_record, st));
     {
@@ -1043,6 +1045,13 @@ int mb_set_decode_groups(void* hv, int groups) {
     Handle* h = reinterpret_cast<Handle*>(hv);
     if (groups < 0 || groups > kMaxGroups) return fail(h, "decode row groups must be 0 (automatic) .. 4");
     h->groups = groups;
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    return 0;
+}
+int mb_set_decode_qkv_split(void* hv, int nsplit) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    if (nsplit != -1 && nsplit != 0 && nsplit != 3 && nsplit != 9) return fail(h, "decode QKV split must be -1 (default), 0, 3 or 9");
+    h->qkv_split = nsplit;
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
     return 0;
 }

@@ -87,6 +87,10 @@ class Engine:
         """Row groups of the decode step (0 = automatic); a scheduling choice only, token ids do not depend on it."""
         self._ck(self.lib.mb_set_decode_groups(self.handle, int(groups)))
 
+    def set_decode_qkv_split(self, nsplit):
+        """0: QKV GEMM with RoPE / KV write in its epilogue (default); 3 or 9: split-K slices finished inside decode attention."""
+        self._ck(self.lib.mb_set_decode_qkv_split(self.handle, int(nsplit)))
+
     def workspace_bytes(self):
         return self.lib.mb_workspace_bytes(self.handle)
 

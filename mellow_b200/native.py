@@ -93,6 +93,7 @@ SYMBOLS = [
     ("mb_workspace_bytes", _ll, [_vp]),
     ("mb_set_gemm_engine", _i, [_vp, _i]),
     ("mb_set_decode_groups", _i, [_vp, _i]),
+    ("mb_set_decode_qkv_split", _i, [_vp, _i]),
     ("mb_set_trace", _i, [_vp, _vp]),
     ("mb_kernel_launches", _ll, [_vp]),
     ("mb_frontend", _i, [_vp, _vp, _i, _vp, _vp, _vp]),

@@ -351,6 +351,30 @@ def test_kv24_policy_keeps_token_identity_and_logit_tolerance(engine24, engine, 
     assert torch.equal(got, want)
 
 
+@pytest.mark.parametrize("which", ["engine", "engine24"])
+def test_fused_qkv_decode_attention_variant(which, request, inputs, oracle_taps, golden):
+    """mb_set_decode_qkv_split(9 / 3): the QKV projection leaves split-K partial sums and the decode-attention kernel
+    reduces them, applies RoPE, appends the new K/V row to the cache (fp32 and 24-bit rows) and uses it from shared
+    memory.  Golden ids and logits must hold, for key splits (B=2, 7 splits per row) and for a ragged 7-row batch."""
+    eng = request.getfixturevalue(which)
+    prefix = oracle_taps["prefix"]
+    try:
+        for nsplit in (9, 3):
+            eng.set_decode_qkv_split(nsplit)
+            eng.set_prefix(prefix)
+            eng.prefill(2, want_logits=False)
+            toks, dump = eng.decode(2, 12, dump_logits=True)
+            assert toks.cpu().tolist() == golden["tokens"].tolist(), f"nsplit={nsplit}"
+            probe = torch.from_numpy(golden["probe_ids"])
+            assert maxerr(dump.cpu()[:, :, probe], golden["probe_logits"]) < LOGIT_TOL
+            if eng.max_batch >= 3:
+                idx = [0, 1, 1][: eng.max_batch] if eng.max_batch < 7 else [0, 1, 1, 0, 1, 0, 0]
+                got = eng.generate(inputs["wave1"][idx], inputs["wave2"][idx], inputs["ids"][idx], 12).cpu()
+                assert torch.equal(got, torch.from_numpy(golden["tokens"]).to(torch.int32)[idx])
+    finally:
+        eng.set_decode_qkv_split(-1)
+
+
 def test_in_kernel_timeline_records_every_decode_kernel(engine, inputs, golden):
     """mb_set_trace: the first CTA of each of the 7 kernels of a decode layer (plus lm_head) leaves one record per
     launch with entry <= dependency-wait return <= exit; tracing must not change the tokens."""

@@ -3,13 +3,20 @@
 //
 //   * WEIGHT-RESIDENT: the CTA's whole weight slice (BN rows x its K range, <= KBMAX k-blocks) has its own shared
 //     memory region and is requested in full BEFORE griddepcontrol.wait.  The kernel is resident several microseconds
-//     before its predecessor finishes (PDL), so the HBM latency of every weight byte is hidden; the ring version only
-//     prefetched as many k-blocks as it had stages and paid one exposed HBM round trip per ring revolution after the wait
-//     (measured with the in-kernel timeline, tools/decode_timeline.py: 2.5-3.3 us of a 3.4-8.2 us kernel body).
+//     before its predecessor finishes (PDL), so no weight byte is waited for after the dependency resolves (the ring
+//     version could only prefetch as many k-blocks as it had stages).
 //   * the 128-row activation tile streams through a ring of its own (as deep as the remaining shared memory allows),
-//     requested right after the wait: these are L2 hits (the predecessor just wrote them).
-//   * one elected thread issues the MMAs k-block by k-block as the activation stages land; eight epilogue warps drain
-//     the TMEM accumulator (one row per thread) into the fused epilogue or the split-K partial buffer.
+//     requested right after the wait: these are L2 hits (the predecessor just wrote them); the first stage lands
+//     ~0.7 us after the wait, and the re-read of the tile by every N tile (tiles_n x 128 x K x 4 B) is what bounds the
+//     k-loop once the issue loop is out of the way.
+//   * one elect.sync-elected thread issues the MMAs from a fully unrolled loop; eight epilogue warps drain the TMEM
+//     accumulator (one row per thread) into the fused epilogue or the split-K partial buffer.
+//   What the in-kernel timeline (tools/decode_timeline.py) showed on the way here: the ring kernel spent 0.8 us per
+//   k-block whatever the tile width, stage count, accumulator layout or commit count; an EMPTY k-block iteration of the
+//   single issuing thread already cost 0.3 us because every uniform-datapath operand was wrapped in an
+//   ELECT / R2UR.BROADCAST loop (`lane == 0` does not tell the compiler that one thread is active) and descriptors
+//   were rebuilt in 64-bit arithmetic.  Bodies went 8.2 / 3.4 / 8.8 / 5.6 us -> 4.1 / 2.8 / 5.2 / 3.7 us
+//   (QKV / o_proj / gate-up / down at B = 128).
 //
 // Warp roles (320 threads): warps 0..7 = epilogue, warp 8 = TMA producer, warp 9 = TMEM allocator + MMA issuer.  The two
 // single-thread roles sit in the HIGHEST-numbered warps of their schedulers (warp id % 4) and the epilogue warps sleep

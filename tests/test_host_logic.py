@@ -164,3 +164,41 @@ def test_plan_fit_draws_like_the_reference():
     rng = random.Random(7)
     want = random.Random(7).randrange(323585 - 320000)
     assert plan_fit(323585, 320000, rng) == want                          # long clip: one randrange draw
+
+
+def test_local_hf_tokenizer_plumbing(tmp_path):
+    """with a local tokenizer directory (tokenizer= / $MELLOW_TOKENIZER) the wrapper uses a real
+    Hugging Face fast tokenizer the way the reference does (wrapper.py:84-85,186-190,254): pad token '!', right padding /
+    truncation to 129 ids, no BOS / EOS added, stop id = first id of '<|endoftext|>', text cut at the stop token.  The
+    SmolLM2 files are not available offline, so a small byte-level BPE tokenizer with the same special token is built."""
+    tokenizers = pytest.importorskip("tokenizers")
+    from tokenizers import Tokenizer, models, pre_tokenizers, decoders, trainers
+    from mellow_b200.tokenizer import load_tokenizer, tokenize_prompts
+    tk = Tokenizer(models.BPE())
+    tk.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    tk.decoder = decoders.ByteLevel()
+    trainer = trainers.BpeTrainer(vocab_size=400, special_tokens=["<|endoftext|>"],
+                                  initial_alphabet=pre_tokenizers.ByteLevel.alphabet())
+    tk.train_from_iterator(["what is the difference between the two audios?", "describe the audio in detail!",
+                            "is there a dog barking? yes! no!"] * 4, trainer)
+    tk.save(str(tmp_path / "tokenizer.json"))
+    (tmp_path / "tokenizer_config.json").write_text(
+        '{"tokenizer_class": "PreTrainedTokenizerFast", "eos_token": "<|endoftext|>", "bos_token": "<|endoftext|>", '
+        '"unk_token": "<|endoftext|>", "model_max_length": 8192}')
+    tok = load_tokenizer("HuggingFaceTB/SmolLM2-135M", local=str(tmp_path))
+    assert not getattr(tok, "is_stand_in", False)
+    assert tok.pad_token == "!" and tok.pad_token_id == tok.encode("!")[0]
+    stop_id = tok.encode("<|endoftext|>")[0]
+    assert stop_id == 0                                                # first special token, like SmolLM2
+    prompts = ["what is the difference between the two audios?", "yes! " * 200]
+    ids = tokenize_prompts(tok, prompts, 129)
+    assert ids.shape == (2, 129) and ids.dtype == torch.int64
+    n0 = len(tok.encode(prompts[0]))
+    assert ids[0, :n0].tolist() == tok.encode(prompts[0])              # no BOS / EOS added
+    assert ids[0, n0:].eq(tok.pad_token_id).all()                      # right padding with '!'
+    assert ids[1].tolist() == tok.encode(prompts[1])[:129]             # truncation
+    # detokenisation rule of wrapper.py:251-254
+    row = tok.encode("a dog barking") + [stop_id] + tok.encode("garbage after the stop token")
+    assert tok.decode(row).split("<|endoftext|>")[0] == "a dog barking"
+    with pytest.raises(Exception):
+        load_tokenizer("HuggingFaceTB/SmolLM2-135M", local=str(tmp_path / "missing"))

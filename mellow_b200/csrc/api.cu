@@ -246,6 +246,8 @@ GemmArgs gemm_base(const Handle* h, const bf16* a_hi, const bf16* a_lo, int lda,
     g.W_hi = wgt.hi; g.W_lo = lo_of(h, wgt.lo); g.ldw = ldw;
     g.M = M; g.N = N; g.K = K;
     g.passes = h->policy == kPolicySplit ? 3 : 1;
+    static const int epi_sleep = getenv("MB_EPI_SLEEP") ? atoi(getenv("MB_EPI_SLEEP")) : 128;
+    g.epi_sleep = epi_sleep;
     return g;
 }
 

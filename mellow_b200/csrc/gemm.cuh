@@ -18,6 +18,7 @@ struct GemmArgs {
     unsigned* fix_counter;                            // weight-resident kernel, split_k > 1: per-N-tile arrival counters (zero between
                                                       // launches).  The split that arrives last sums the partials in z order and runs
                                                       // the fused epilogue itself, so no consumer-side reduction is needed.
+    int epi_sleep;                                    // weight-resident kernel: ns the epilogue warps sleep between polls of the accumulator barrier
     int resident;                                     // decode chain: use the weight-resident kernel (gemm_skinny.cu) when the shape fits
     int bn_hint;                                      // decode-sized split-K GEMMs: N-tile width 48 / 64 (0 = default rule)
     int compact;                                      // decode-sized GEMMs: use the two-CTAs-per-SM variants (gemm_umma.cu)

@@ -179,7 +179,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             float rc[8], rs[8];
             if (EPI == EPI_QKV_ROPE && nsplit == 1 && m < g.M)       // RoPE factors of the first unit, fetched while the MMAs run
                 qkv_rope_load(g, m, n0 + half * 16, rc, rs);
-            mbar_wait_sleep(tfull, 0);
+            mbar_wait_sleep(tfull, 0, (unsigned)g.epi_sleep);
             if (threadIdx.x == 0) trace_put(g.trace, trec, g.trace_id, 7);              // accumulator complete
             tc_fence_after();
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16);

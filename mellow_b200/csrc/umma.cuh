@@ -74,7 +74,7 @@ __device__ __forceinline__ void umma_bf16_c(uint32_t tmem_d, uint64_t adesc, uin
 // Wait used by warps that have nothing to do until the barrier flips (the epilogue warps waiting for the accumulator):
 // a polling loop without back-off keeps those warps eligible every cycle and they win the issue slots of the warp
 // scheduler they share with the TMA-producer / MMA-issuer warps, slowing the critical single-thread loops several-fold.
-__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns = 128) {
     const uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     const long long t0 = clock64();
@@ -82,7 +82,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) 
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) break;
-        __nanosleep(128);
+        if (ns) __nanosleep(ns);
         if (clock64() - t0 > 4000000000LL) __trap();
     }
 }

@@ -407,6 +407,24 @@ def test_in_kernel_timeline_records_every_decode_kernel(engine, inputs, golden):
     assert kinds.get(8) == 4, kinds
 
 
+@pytest.mark.parametrize("batch", [32, 64])
+def test_baseline_config_batches_32_and_64_rows_match_golden(batch, engine, inputs, golden):
+    """BASELINE.json configs[1] (batch 32) and the per-GPU slices of configs[3] / [4] (64 rows): copies of the two golden
+    pairs must reproduce their golden ids at these sizes too -- decode attention splits the keys 4 / 2 ways there and
+    merges the partial softmax states in decode_combine_kernel, unlike the unsplit batch-128 path."""
+    from mellow_b200.engine import Engine
+    eng = Engine(None, device=0, max_batch=batch, max_new_tokens=16, policy="split", arena=engine.arena)
+    try:
+        rep = batch // 2
+        toks = eng.generate(inputs["wave1"].repeat(rep, 1), inputs["wave2"].repeat(rep, 1), inputs["ids"].repeat(rep, 1), 12).cpu()
+        want = torch.from_numpy(golden["tokens"]).to(torch.int32)
+        assert toks.shape == (batch, 12)
+        assert torch.equal(toks[0::2], want[0:1].expand(rep, -1))
+        assert torch.equal(toks[1::2], want[1:2].expand(rep, -1))
+    finally:
+        eng.close()
+
+
 def test_fast_policy_generate_runs_end_to_end(engine_fast, inputs):
     toks = engine_fast.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 6)
     assert toks.shape == (2, 6) and int(toks.min()) >= 0 and int(toks.max()) < 49152

@@ -271,10 +271,20 @@ def _rot_half(x):
     return torch.cat([-x[..., HEAD_DIM // 2:], x[..., :HEAD_DIM // 2]], dim=-1)
 
 
-def llama_hidden(sd, x, taps=None):
+def round_to_24_bits(t):
+    """What mellow_b200's policy split24 stores in its KV cache: fp32 rounded (nearest-even) to sign + 8 exponent + 15
+    mantissa bits.  Test infrastructure for the tolerance claim of that policy; the reference keeps fp32."""
+    u = t.contiguous().view(torch.int32).to(torch.int64) & 0xFFFFFFFF
+    r = (u + 0x7F + ((u >> 8) & 1)) & 0xFFFFFF00
+    r = torch.where(r >= 2 ** 31, r - 2 ** 32, r).to(torch.int32)
+    return r.view(torch.float32).view_as(t)
+
+
+def llama_hidden(sd, x, taps=None, kv_round=None):
     """LlamaModel.forward with inputs_embeds, no cache, no attention mask => pure causal mask over all
     positions, pads attended (reference wrapper.py:217; transformers modeling_llama.py:375-425).
-    x (B,S,576) -> final-normed hidden (B,S,576)."""
+    x (B,S,576) -> final-normed hidden (B,S,576).  kv_round (optional, not in the reference): applied to the roped keys
+    and to the values, i.e. to what a KV cache would hold."""
     b, s, _ = x.shape
     cos, sin = rope_tables(s)
     causal = torch.full((s, s), float("-inf")).triu(1)
@@ -286,6 +296,8 @@ def llama_hidden(sd, x, taps=None):
         v = F.linear(h, sd[p + "self_attn.v_proj.weight"]).view(b, s, N_KV, HEAD_DIM).transpose(1, 2)
         q = q * cos + _rot_half(q) * sin                                               # :166-167
         k = k * cos + _rot_half(k) * sin
+        if kv_round is not None:
+            k, v = kv_round(k), kv_round(v)
         k = k.repeat_interleave(N_HEADS // N_KV, dim=1)                                # repeat_kv :187-196
         v = v.repeat_interleave(N_HEADS // N_KV, dim=1)
         att = (q @ k.transpose(-2, -1)) * (HEAD_DIM ** -0.5) + causal

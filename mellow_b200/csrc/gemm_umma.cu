@@ -148,7 +148,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 for (; kb < t.KB; ++kb, ++it) {
                     const int s = it % C::STAGES;
                     const uint32_t ph = (it / C::STAGES) & 1;
-                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_wait_fast(&empty[s], ph ^ 1);
                     unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
                     mbar_expect_tx(&full[s], C::STAGE_BYTES);
                     tma_load_2d(st + C::A_TILE, &tm_b_hi, &full[s], (t.kb_begin + kb) * BK, t.n0);
@@ -178,19 +178,21 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 for (int kb = 0; kb < t.KB; ++kb, ++it) {
                     const int s = it % C::STAGES;
                     const uint32_t ph = (it / C::STAGES) & 1;
-                    mbar_wait(&full[s], ph);
+                    mbar_wait_fast(&full[s], ph);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(smem + (size_t)s * C::STAGE_BYTES);
-                    const uint32_t b_hi = a_hi + C::A_TILE;
-                    const uint32_t a_lo = b_hi + C::B_BYTES;
-                    const uint32_t b_lo = a_lo + C::A_TILE;
+                    // descriptor low words (16-byte units); a k-step advances them by 2 (umma.cuh)
+                    const uint32_t a_hi = umma_desc_lo(smem_u32(smem + (size_t)s * C::STAGE_BYTES));
+                    const uint32_t b_hi = a_hi + (C::A_TILE >> 4);
+                    const uint32_t a_lo = b_hi + (C::B_BYTES >> 4);
+                    const uint32_t b_lo = a_lo + (C::A_TILE >> 4);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        const uint32_t off = k * 32;                 // 16 bf16 = 32 B along the swizzled row
-                        umma_bf16(tacc, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | k) != 0);
+                        const uint64_t dah = umma_desc_join(a_hi + 2 * k), dbh = umma_desc_join(b_hi + 2 * k);
+                        if (k == 0 && kb == 0) umma_bf16_c<false>(tacc, dah, dbh, idesc);
+                        else umma_bf16_c<true>(tacc, dah, dbh, idesc);
                         if (SPLIT) {
-                            umma_bf16(tacc, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1);
-                            umma_bf16(tacc, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+                            umma_bf16_c<true>(tacc, dah, umma_desc_join(b_lo + 2 * k), idesc);
+                            umma_bf16_c<true>(tacc, umma_desc_join(a_lo + 2 * k), dbh, idesc);
                         }
                     }
                     if (CL > 1) umma_commit_mc(&empty[s], cmask);    // every producer of the cluster writes into this stage

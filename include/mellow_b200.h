@@ -46,14 +46,18 @@ const char* mb_last_error(void* h); /* h may be NULL for mb_create failures */
 /* binds a packed device arena of mb_weights_size() bytes (caller keeps it alive; it is what gets NCCL-broadcast) */
 int mb_bind_weights(void* h, const void* dev_arena, long long nbytes);
 long long mb_workspace_bytes(void* h);
-int mb_set_gemm_engine(void* h, int engine); /* 0 = mma.sync bring-up engine, 1 = tcgen05 engine where a tile fits */
-/* decode row groups: the batch is cut into `groups` contiguous row groups whose per-layer kernel chains run on
- * concurrent streams (1..4; 0 = automatic: 2 from 96 rows up).  Results do not depend on it (rows are independent). */
-int mb_set_decode_groups(void* h, int groups);
-/* decode QKV projection: 0 = one GEMM with RoPE + KV-cache write in its epilogue (default); 3 / 9 = that many split-K
- * slices whose partial sums the decode-attention kernel reduces, ropes and appends to the cache itself (policy split /
- * split24 only; -1 = default).  Token ids do not depend on it beyond fp32 summation order. */
-int mb_set_decode_qkv_split(void* h, int nsplit);
+/* handle-scoped options (defaults in parentheses; none changes a result beyond fp32 summation order except
+ * skip_finished, see mb_decode):
+ *   "graph"          (1) replay the decode step as one CUDA graph; 0 = individual launches
+ *   "decode_unfused" (0) 1 = use the generic per-layer decode path (the one batches > 128 rows take) for every batch
+ *   "skip_finished"  (1) rows that emitted eos_id stop streaming their KV cache (their later tokens are not meaningful);
+ *                        0 = every row keeps decoding until all rows have stopped, like the reference loop
+ *   "kv_prefetch"    (-1) keys per (row, kv head) stream decode attention prefetches into L2 while it waits for its
+ *                        predecessor: -1 = the whole immutable history, 0 = off
+ *   "wide_tiles"     (-1) decode split-K GEMM tiling: 1 = 32-column tiles x 3 / 8 K slices, 0 = 16-column tiles x 3 / 4,
+ *                        -1 = by policy (wide except MB_POLICY_FAST)
+ *   "gemm_engine"    (1) 0 = mma.sync cross-check engine (lab builds only, MB_BUILD_LAB=1) */
+int mb_set_option(void* h, const char* name, int value);
 /* profiling aid: dev_trace_buf = {u32 n; u32 cap; {u64 globaltimer_ns; u32 id*16+phase; u32 smid} ev[cap][16]} in device
  * memory, zero-initialised, n = records used, cap = records available (NULL = off).  The first and the last CTA of every
  * decode-step kernel claim one 16-slot record at entry and stamp phases into it with plain stores: 0 entry, 1 return of
@@ -85,9 +89,15 @@ int mb_prefix(void* h, const int* input_ids, int B, float* prefix_out, void* str
 int mb_set_prefix(void* h, const float* prefix, int B, void* stream);
 /* LM prefill over the 389-token prefix, fills the KV cache; logits_out [B,49152] f32 of the last position (may be NULL) */
 int mb_prefill(void* h, int B, float* logits_out, void* stream);
+/* The reference's inner seams used by _generate_batch (wrapper.py:217-218, 237):
+ * mb_lm_forward_last = model.caption_decoder.lm(inputs_embeds=embeds).logits[:, -1]: one cache-less causal forward over
+ * embeds [B,S,576] f32 (1 <= S <= 389 + max_new_tokens, B*S <= max_batch*389) -> logits_out [B,49152] f32; it
+ * overwrites the prefix / KV state of the handle.  mb_embed_tokens = lm.model.embed_tokens: ids [n] i32 -> out [n,576]. */
+int mb_lm_forward_last(void* h, const float* embeds, int B, int S, float* logits_out, void* stream);
+int mb_embed_tokens(void* h, const int* ids, int n, float* out, void* stream);
 /* decode loop.  tokens_out [B,max_len] i32 (row stride max_len); *steps_out_host = number of valid columns (the
  * reference breaks once every row has emitted eos_id).  Each row is valid up to and including its first eos_id: the
- * reference discards what follows (wrapper.py:254), and finished rows stop streaming their KV cache here.  logits_dump [max_len][B][49152] f32 (NULL = off);
+ * reference discards what follows (wrapper.py:254), and finished rows stop streaming their KV cache here (option "skip_finished").  logits_dump [max_len][B][49152] f32 (NULL = off);
  * forced_tokens [B,max_len] i32 (NULL = off): teacher forcing, tokens_out still records the model's own argmax. */
 int mb_decode(void* h, int B, int max_len, float temperature, float top_p, int eos_id, int* tokens_out,
               int* steps_out_host, float* logits_dump, const int* forced_tokens, void* stream);

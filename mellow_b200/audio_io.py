@@ -11,12 +11,14 @@ import numpy as np
 import torch
 
 
-def read_wav(path):
-    """-> (channels, samples) float32 in [-1, 1], sample_rate."""
+def read_wav(path, info_only=False):
+    """-> (channels, samples) float32 in [-1, 1], sample_rate; info_only: -> (channels, samples per channel, rate)."""
     from scipy.io import wavfile
-    sr, data = wavfile.read(path)
+    sr, data = wavfile.read(path, mmap=info_only)
     if data.ndim == 1:
         data = data[:, None]
+    if info_only:
+        return data.shape[1], data.shape[0], int(sr)
     if data.dtype == np.int16:
         x = data.astype(np.float32) / 32768.0
     elif data.dtype == np.int32:
@@ -26,6 +28,30 @@ def read_wav(path):
     else:
         x = data.astype(np.float32)
     return torch.from_numpy(np.ascontiguousarray(x.T)), int(sr)
+
+
+def read_audio(path, info_only=False):
+    """What the reference gets from ``torchaudio.load`` (wrapper.py:144): (channels, samples) float32, sample rate.
+    PCM / float RIFF files are decoded here; anything else (flac, mp3, ogg, compressed wav) goes to ``soundfile`` or
+    ``torchaudio.load`` when this installation has a working decoder, and raises otherwise."""
+    try:
+        return read_wav(path, info_only)
+    except Exception as wav_exc:
+        audio = None
+        try:
+            import soundfile
+            data, sr = soundfile.read(path, dtype="float32", always_2d=True)
+            audio = torch.from_numpy(np.ascontiguousarray(data.T))
+        except Exception:
+            try:
+                import torchaudio
+                audio, sr = torchaudio.load(path)
+            except Exception as exc:
+                raise RuntimeError(f"cannot decode {path}: not a PCM/float WAV ({wav_exc}) and neither soundfile nor "
+                                   f"torchaudio.load can read it here ({type(exc).__name__}: {exc})") from exc
+        if info_only:
+            return audio.shape[0], audio.shape[1], int(sr)
+        return audio.to(torch.float32), int(sr)
 
 
 def sinc_resample_kernel(orig_freq, new_freq, lowpass_filter_width=6, rolloff=0.99):
@@ -53,8 +79,13 @@ def sinc_resample_kernel(orig_freq, new_freq, lowpass_filter_width=6, rolloff=0.
 
 
 def resampled_length(n_in, orig, new):
-    """torchaudio: ceil(new * length / orig), evaluated in floating point like `_apply_sinc_resample_kernel`."""
-    return int(math.ceil(new * n_in / orig))
+    """Output length of torchaudio's resampler: ``torch.ceil(torch.as_tensor(new * length / orig))`` with orig / new
+    reduced by their gcd (``_apply_sinc_resample_kernel``).  The float64 quotient is rounded to float32 by
+    ``as_tensor`` BEFORE the ceil, which differs from ``math.ceil`` for ~1 % of the lengths (44.1 kHz -> 32 kHz,
+    n = 300044: 217719 here and in torchaudio, 217720 in exact arithmetic)."""
+    g = math.gcd(int(orig), int(new))
+    orig, new = int(orig) // g, int(new) // g
+    return int(math.ceil(float(np.float32(new * int(n_in) / orig))))
 
 
 def plan_fit(total, target, rng=random):
@@ -67,7 +98,7 @@ def plan_fit(total, target, rng=random):
 
 def load_audio_into_tensor(path, audio_duration, sample_rate_target, resample=True, rng=random):
     """Restates reference wrapper.py:141-168 (same branch conditions and the same ``random.randrange`` draw)."""
-    audio, sr = read_wav(path)
+    audio, sr = read_audio(path)
     if resample and sample_rate_target != sr:
         import torchaudio.transforms as T
         audio = T.Resample(sr, sample_rate_target)(audio)

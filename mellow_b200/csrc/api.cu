@@ -6,32 +6,50 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/mellow_b200.h"
 #include "gemm.cuh"
 #include "kernels.cuh"
 
 namespace mb {
 
-namespace { thread_local int g_pdl_off = 0; }
-bool pdl_enabled() {
-    static const bool on = getenv("MB_NO_PDL") == nullptr;
-    return on && g_pdl_off == 0;
+// Environment switches, read ONCE (first use).  They exist for A/B measurements and the sanitizer runs; none of them
+// changes a result beyond fp32 summation order.
+//   MB_NO_PDL=1        launch without programmatic dependent launch
+//   MB_NO_GRAPH=1      replay the decode step as individual launches instead of one CUDA graph
+//   MB_DECODE_UNFUSED=1 use the generic per-layer path (the one batches > 128 rows take) for every batch size
+//   MB_EPI_SLEEP=<ns>  back-off of the epilogue warps that wait for the accumulator (decode GEMMs)
+//   MB_KV_PREFETCH=<keys> decode: keys per (row, kv head) stream the attention kernel prefetches into L2 (0 = off)
+struct Tunables {
+    bool pdl, graph, decode_unfused;
+    int epi_sleep, kv_prefetch;
+};
+const Tunables& tunables() {
+    static const Tunables t = [] {
+        Tunables v;
+        v.pdl = getenv("MB_NO_PDL") == nullptr;
+        v.graph = getenv("MB_NO_GRAPH") == nullptr;
+        v.decode_unfused = getenv("MB_DECODE_UNFUSED") != nullptr;
+        v.epi_sleep = getenv("MB_EPI_SLEEP") ? atoi(getenv("MB_EPI_SLEEP")) : 128;
+        v.kv_prefetch = getenv("MB_KV_PREFETCH") ? atoi(getenv("MB_KV_PREFETCH")) : -1;
+        return v;
+    }();
+    return t;
 }
-// Scope in which kernels are launched with a full (non-programmatic) dependency: the first kernel after a stream
-// fork / join of the row-group decode step, whose predecessors are event edges rather than one kernel.
-struct PdlOff {
-    bool on;
-    explicit PdlOff(bool enable = true) : on(enable) { if (on) ++g_pdl_off; }
-    ~PdlOff() { if (on) --g_pdl_off; }
+bool pdl_enabled() { return tunables().pdl; }
+
+// NVTX range per stage of the path (visible in nsys / ncu --nvtx; a no-op without an attached tool)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
 };
 
 cudaError_t launch_gemm_umma(const GemmArgs& g, int epi, cudaStream_t st, bool* handled);   // gemm_umma.cu
 
 namespace {
 
-constexpr int kMaxSplitK = 12;
-constexpr int kMaxGroups = 4;
-constexpr int kGuSplitMax = 3;
+constexpr int kMaxSplitK = 8;
 constexpr int kDepths[4] = {2, 2, 6, 2};
 constexpr int kHeadsPerStage[4] = {4, 8, 16, 32};
 inline int stage_dim(int i) { return kEmbed << i; }
@@ -177,12 +195,9 @@ struct Handle {
     bf16 *la_hi = nullptr, *la_lo = nullptr, *lh_hi = nullptr, *lh_lo = nullptr;
     void *kcache = nullptr, *vcache = nullptr;
     size_t kv_layer_elems = 0;
-    float *part_acc = nullptr, *part_ml = nullptr, *gemm_partial = nullptr, *cand_val = nullptr, *qkv_part = nullptr, *gu_part = nullptr;
-    float* rope_cur = nullptr;           // cos | sin row of the position the current decode step writes (step_advance_kernel)
-    unsigned* fix_counter = nullptr;     // split-K fix-up tickets of the gate/up tiles (self-resetting)
+    float *part_acc = nullptr, *part_ml = nullptr, *gemm_partial = nullptr, *cand_val = nullptr;
     int* cand_idx = nullptr;
     bool logits_fused = false;           // the last lm_head wrote argmax candidates instead of logits
-    unsigned* chain_bar = nullptr;       // [kLayers][8] grid-barrier counters of the fused decode chain
     int *d_tokens = nullptr, *d_done = nullptr, *d_step = nullptr, *d_stop = nullptr, *d_ids = nullptr;
     float *wave_stage = nullptr;
     int prefix_B = 0;
@@ -193,14 +208,16 @@ struct Handle {
     float g_temp = 0.f;
     cudaStream_t g_stream = nullptr;
     cudaStream_t own_stream = nullptr;   // used when the caller passes NULL (the legacy stream cannot be graph-captured)
-    // row-group decode: groups 1.. run on their own streams, forked from / joined to the caller's stream by events
-    cudaStream_t grp_stream[kMaxGroups - 1] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[kMaxGroups - 1] = {}, ev_attn[kMaxGroups] = {};
     int kv_fmt = kKvF32;                 // KV-cache row format (common.cuh)
-    int qkv_split = -1;                  // mb_set_decode_qkv_split: -1 = default (MB_DEC_QKV_SPLIT / 0)
-    int groups = 0;                      // mb_set_decode_groups: 0 = automatic
+    // mb_set_option (defaults from the environment switches above)
+    bool use_graph = true, decode_unfused = false, skip_finished = true;
+    int kv_prefetch = -1;                // keys per stream prefetched into L2 by decode attention (-1 = automatic)
+    int wide_tiles = -1;                 // decode split-K tiling: -1 = by policy, 0 = 16-column tiles, 1 = 32-column tiles
     TraceBuf* trace = nullptr;           // mb_set_trace: optional in-kernel timeline of the decode kernels
 };
+inline void drop_graph(Handle* h) {
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+}
 
 inline cudaStream_t pick_stream(Handle* h, void* stream) { return stream ? (cudaStream_t)stream : h->own_stream; }
 
@@ -246,8 +263,7 @@ GemmArgs gemm_base(const Handle* h, const bf16* a_hi, const bf16* a_lo, int lda,
     g.W_hi = wgt.hi; g.W_lo = lo_of(h, wgt.lo); g.ldw = ldw;
     g.M = M; g.N = N; g.K = K;
     g.passes = h->policy == kPolicySplit ? 3 : 1;
-    static const int epi_sleep = getenv("MB_EPI_SLEEP") ? atoi(getenv("MB_EPI_SLEEP")) : 128;
-    g.epi_sleep = epi_sleep;
+    g.epi_sleep = tunables().epi_sleep;
     return g;
 }
 
@@ -264,10 +280,14 @@ int run_gemm(Handle* h, const GemmArgs& g, int epi, cudaStream_t st) {
         MB_CK(h, launch_gemm_umma(g, epi, st, &handled));
         if (handled) { h->launches++; return 0; }
     }
+#ifdef MB_LAB
     if (epi == EPI_ARGMAX) return fail(h, "argmax epilogue needs the tcgen05 engine");
     MB_CK(h, launch_gemm_mma(g, epi, st));
     h->launches++;
     return 0;
+#else
+    return fail(h, "GEMM shape not supported by the tcgen05 engine (K >= 64, K % 8 == 0, 16-byte aligned planes)");
+#endif
 }
 
 int run_norm(Handle* h, int kind, const float* x, const float* w, const float* b, int rows, int C, bf16* hi, bf16* lo,
@@ -293,11 +313,7 @@ int swin_block(Handle* h, float* x, int n_clips, int stage, int b, cudaStream_t 
         g.bias = k.qkv_b; g.out_f32 = h->qkv; g.ldo = 3 * C;
         MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
     }
-    static const bool fp32_win = getenv("MB_ATTN_FP32") != nullptr;            // CUDA-core fp32 kernel, kept for A/B checks
-    if (fp32_win)
-        MB_CK(h, launch_window_attention(h->qkv, k.relbias, h->a_hi, lo_of(h, h->a_lo), n_clips, R, C, nH, shift, st));
-    else
-        MB_CK(h, launch_window_attention_mma(h->qkv, k.relbias, h->a_hi, lo_of(h, h->a_lo), n_clips, R, C, nH, shift, st));
+    MB_CK(h, launch_window_attention_mma(h->qkv, k.relbias, h->a_hi, lo_of(h, h->a_lo), n_clips, R, C, nH, shift, st));
     h->launches++;
     {
         GemmArgs g = gemm_base(h, h->a_hi, h->a_lo, C, k.proj, C, M, C, C);
@@ -320,6 +336,7 @@ int swin_block(Handle* h, float* x, int n_clips, int stage, int b, cudaStream_t 
 
 // bn [n,1001,64] -> rows33 (or a tap).  Returns the buffer holding the residual stream in *x_final.
 int encoder_body(Handle* h, int n_clips, int stop_stage, float* tap_out, float* rows_out, cudaStream_t st) {
+    NvtxRange r_("mellow.encoder");
     PatchW pw{h->w.pe_w, h->w.pe_b, h->w.pe_ln_w, h->w.pe_ln_b};
     MB_CK(h, launch_patch_embed(h->bn, n_clips, pw, h->xa, st));
     h->launches++;
@@ -395,6 +412,7 @@ int encoder_body(Handle* h, int n_clips, int stop_stage, float* tap_out, float* 
 }
 
 int frontend(Handle* h, const float* wave, int n_clips, float* logmel_out, float* bn_out, cudaStream_t st) {
+    NvtxRange r_("mellow.frontend");
     FrontendW fw{h->w.window, h->w.twiddle, h->w.melW, h->w.mel_lo, h->w.mel_hi, h->w.bn_scale, h->w.bn_shift};
     MB_CK(h, launch_logmel(wave, n_clips, fw, logmel_out, bn_out, st));
     h->launches++;
@@ -417,229 +435,78 @@ inline int decode_nsplit(const Handle* h, int B) {
     return ns < 1 ? 1 : (ns > kMaxAttnSplit ? kMaxAttnSplit : ns);
 }
 
-// Tiling of the split-K decode GEMMs (gemm_umma.cu launch_epi): N-tile width x K split.  The default follows the
-// measured rule "a decode GEMM costs what its CTAs' tcgen05.mma COUNT costs": wide tiles, 1-2 k-blocks per CTA.
-// MB_DEC_TILING=0 restores the 16-column tiles with split 3 / 4.
-struct DecodeTiling { int o_bn, o_split, down_bn, down_split, resident, qkv_split, gu_split; };
-const DecodeTiling& decode_tiling() {
-    static const DecodeTiling t = [] {
-        const char* e = getenv("MB_DEC_TILING");
-        const int mode = e ? atoi(e) : 6;
-        const char* r = getenv("MB_DEC_RESIDENT");
-        const int res = r ? atoi(r) : 1;
-        // MB_DEC_QKV_SPLIT=9: QKV as 9 one-k-block slices of 64-column tiles (135 CTAs x 8 MMAs instead of 60 CTAs x 72); the
-        // partial sums are reduced, roped and appended to the KV cache by the decode-attention kernel that consumes them.
-        // It paid off while the MMA issue loop was slow (1.59 -> 1.55 ms/step); with the elect.sync loop the unsplit GEMM
-        // with its in-epilogue RoPE / KV write is ahead again (1.356 vs 1.383 ms/step) and attention has no prologue
-        const char* q = getenv("MB_DEC_QKV_SPLIT");
-        const int qs = res ? (q ? atoi(q) : 0) : 0;       // off by default: see below
-        // gate/up as 3 K slices of 64-column tiles (144 CTAs x 24 MMAs instead of 96 x 72); SwiGLU needs the complete
-        // sums, so the split that arrives last at its tile finishes it inside the same kernel (gemm_skinny.cu fix-up)
-        const char* gq = getenv("MB_DEC_GU_SPLIT");
-        const int gs = res ? (gq ? atoi(gq) : 0) : 0;   // measured slower (fence + ticket + re-read cost more than the MMAs saved): off
-        if (mode == 1) return DecodeTiling{48, 9, 48, 12, res, qs, gs};
-        if (mode == 2) return DecodeTiling{64, 9, 64, 12, res, qs, gs};
-        if (mode == 3) return DecodeTiling{48, 9, 48, 6, res, qs, gs};
-        if (mode == 4) return DecodeTiling{48, 3, 48, 6, res, qs, gs};
-        if (mode == 5) return DecodeTiling{0, 3, 32, 8, res, qs, gs};
-        if (mode == 6) return DecodeTiling{32, 3, 32, 8, res, qs, gs};
-        if (mode == 7) return DecodeTiling{0, 3, 48, 12, res, qs, gs};
-        if (mode == 8) return DecodeTiling{32, 3, 0, 4, res, qs, gs};
-        if (mode == 0) return DecodeTiling{0, 3, 0, 4, res, qs, gs};
-        return DecodeTiling{32, 3, 32, 8, res, qs, gs};
-    }();
-    return t;
+// Tiling of the split-K decode GEMMs (weight-resident kernel, gemm_skinny.cu): N-tile width x K split.  Rule measured
+// in round 1: a decode GEMM costs what its CTAs' tcgen05.mma COUNT costs, so o_proj / down run as 3 / 8 K slices of
+// 32-column tiles (54 / 144 CTAs x 24 MMAs) whose partial sums add_rmsnorm_row_kernel reduces in a fixed order.
+// Policy fast keeps 16-column tiles with 3 / 4 slices (open issue with its 32-column variant).
+struct DecodeTiling { int o_bn, o_split, down_bn, down_split; };
+inline DecodeTiling decode_tiling(const Handle* h) {
+    const bool wide = h->wide_tiles >= 0 ? h->wide_tiles != 0 : h->policy != kPolicyFast;
+    return wide ? DecodeTiling{32, 3, 32, 8} : DecodeTiling{16, 3, 16, 4};
 }
 
-// Row groups of the decode step (see decode_step).  MB_DECODE_GROUPS / MB_DECODE_COMPACT override the defaults for
-// A/B measurements.
-int decode_groups(const Handle* h, int B) {
-    static const int forced = getenv("MB_DECODE_GROUPS") ? atoi(getenv("MB_DECODE_GROUPS")) : 0;
-    int G = h->groups > 0 ? h->groups : (forced > 0 ? forced : 1);
-    if (G > kMaxGroups) G = kMaxGroups;
-    if (G > B) G = B;
-    if (h->engine != 1) G = 1;
-    return G < 1 ? 1 : G;
-}
-int decode_stagger(int G) {
-    static const int forced = getenv("MB_DECODE_STAGGER") ? atoi(getenv("MB_DECODE_STAGGER")) : -1;
-    return G > 1 ? (forced >= 0 ? forced : 0) : 0;
-}
-int decode_compact(int G) {
-    static const int forced = getenv("MB_DECODE_COMPACT") ? atoi(getenv("MB_DECODE_COMPACT")) : -1;
-    return forced >= 0 ? forced : 1;
-}
-
-// Rows [r0, r0+n) of the batch; n_all = rows of the whole step (all row groups), which sets the key split.
-int run_decode_attention(Handle* h, int l, int r0, int n, int n_all, cudaStream_t st, bool skip_done = true,
-                         const float* qkv_part = nullptr, int qkv_nsplit = 0) {
+int run_decode_attention(Handle* h, int l, int B, cudaStream_t st, bool skip_done = true) {
     DecodeAttnArgs a;
-    a.qkv_part = qkv_part; a.qkv_nsplit = qkv_nsplit; a.rope_cur = h->rope_cur;
-    const size_t kv_off = (size_t)r0 * kKvHeads * h->t_max * kv_row_bytes(h->kv_fmt);
-    a.q = h->q + (size_t)r0 * kHidden;
-    a.kc = reinterpret_cast<char*>(kv_layer(h, h->kcache, l)) + kv_off;
-    a.vc = reinterpret_cast<char*>(kv_layer(h, h->vcache, l)) + kv_off;
-    a.kv_fmt = h->kv_fmt; a.B = n; a.t_max = h->t_max;
-    a.nsplit = decode_nsplit(h, n_all);
+    a.q = h->q;
+    a.kc = kv_layer(h, h->kcache, l);
+    a.vc = kv_layer(h, h->vcache, l);
+    a.kv_fmt = h->kv_fmt; a.B = B; a.t_max = h->t_max;
+    a.nsplit = decode_nsplit(h, B);
     a.tps = ((h->t_max + 63) / 64 + a.nsplit - 1) / a.nsplit;
     a.ctx_base = kPrefix; a.d_step = h->d_step;
-    a.done = skip_done ? h->d_done + r0 : nullptr;
-    a.part_acc = h->part_acc + (size_t)r0 * kHeads * a.nsplit * kHeadDim;
-    a.part_ml = h->part_ml + (size_t)r0 * kHeads * a.nsplit * 2;
-    a.out_hi = h->la_hi + (size_t)r0 * kHidden; a.out_lo = lo_of(h, h->la_lo + (size_t)r0 * kHidden);
-    a.trace = h->trace; a.trace_id = 2000 + (r0 ? 100 : 0) + l;
+    a.done = (skip_done && h->skip_finished) ? h->d_done : nullptr;
+    a.part_acc = h->part_acc; a.part_ml = h->part_ml;
+    a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
+    a.pf_keys = h->kv_prefetch;
+    a.trace = h->trace; a.trace_id = 2000 + l;
     MB_CK(h, launch_decode_attention(a, st));
     h->launches += a.nsplit == 1 ? 1 : 2;
     return 0;
 }
-int run_decode_attention(Handle* h, int l, int B, cudaStream_t st, bool skip_done = true) {
-    return run_decode_attention(h, l, 0, B, B, st, skip_done);
-}
 
-// Decode layer for one row group [r0, r0+n), n <= 128 rows (one M tile).  The residual stream update and the next
-// RMSNorm are fused into add_rmsnorm_kernel, which also reduces the split-K partial sums of o_proj / down_proj in a
-// fixed order.  On entry la_hi/la_lo hold RMSNorm(x) with this layer's input_layernorm; on exit they hold RMSNorm(x)
-// with `next_norm` (the next layer's input_layernorm, or the final model norm).  Every row is independent of every
-// other row, so the values are identical however the batch is cut into groups.
-int lm_layer_decode_fused(Handle* h, int l, int gi, int r0, int n, int n_all, int compact,
-                          const float* next_norm, cudaStream_t st, cudaEvent_t attn_wait = nullptr,
-                          cudaEvent_t attn_record = nullptr) {
-    float* partial = h->gemm_partial + (size_t)gi * kMaxSplitK * 128 * kHidden;           // split-K partials of this row group
-    float* qkv_part = h->qkv_part + (size_t)gi * kQkvSplitMax * 128 * kQkvDim;
+// Decode layer over n <= 128 rows (one M tile).  The residual stream update and the next RMSNorm are fused into
+// add_rmsnorm_row_kernel, which also reduces the split-K partial sums of o_proj / down_proj in a fixed order.  On entry
+// la_hi/la_lo hold RMSNorm(x) with this layer's input_layernorm; on exit they hold RMSNorm(x) with `next_norm` (the
+// next layer's input_layernorm, or the final model norm).
+int lm_layer_decode_fused(Handle* h, int l, int n, const float* next_norm, cudaStream_t st) {
     const LmLayerW& k = h->w.layer[l];
-    // Policy fast keeps the 16-column tiles and the in-GEMM QKV epilogue: with the 32-column split-K tiles its first
-    // decode on a fresh handle produced non-finite logits on 3 of ~12 boxes (B=2; never with policy split, never
-    // under compute-sanitizer memcheck / initcheck / racecheck) -- unexplained, see DESIGN.md section 10.
-    static const DecodeTiling conservative{0, 3, 0, 4, decode_tiling().resident, 0, 0};
-    const DecodeTiling& tl = h->policy == kPolicyFast ? conservative : decode_tiling();
-    const size_t kv_off = (size_t)r0 * kKvHeads * h->t_max * kv_row_bytes(h->kv_fmt);
-    float* x = h->x + (size_t)r0 * kHidden;
-    bf16* la_hi = h->la_hi + (size_t)r0 * kHidden; bf16* la_lo = h->la_lo + (size_t)r0 * kHidden;
-    bf16* lh_hi = h->lh_hi + (size_t)r0 * kInter; bf16* lh_lo = h->lh_lo + (size_t)r0 * kInter;
-    const int qkv_nsplit = h->policy == kPolicyFast ? 0 : (h->qkv_split >= 0 ? h->qkv_split : tl.qkv_split);
-    const bool qkv_split = qkv_nsplit > 1 && h->engine == 1 && tl.resident;
-    if (qkv_split) {
-        GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.qkv, kHidden, n, kQkvDim, kHidden);
-        g.resident = 1; g.bn_hint = 64;
-        g.trace = h->trace; g.trace_id = 1000 + (r0 ? 100 : 0) + l;
-        g.split_k = qkv_nsplit; g.partial = qkv_part;
-        MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
-    } else {
-        GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.qkv, kHidden, n, kQkvDim, kHidden);
-        g.compact = compact; g.resident = tl.resident;
-        g.trace = h->trace; g.trace_id = 1000 + (r0 ? 100 : 0) + l;
-        g.q_out = h->q + (size_t)r0 * kHidden;
-        g.k_cache = reinterpret_cast<char*>(kv_layer(h, h->kcache, l)) + kv_off;
-        g.v_cache = reinterpret_cast<char*>(kv_layer(h, h->vcache, l)) + kv_off;
+    const DecodeTiling tl = decode_tiling(h);
+    {
+        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.qkv, kHidden, n, kQkvDim, kHidden);
+        g.resident = 1;
+        g.trace = h->trace; g.trace_id = 1000 + l;
+        g.q_out = h->q;
+        g.k_cache = kv_layer(h, h->kcache, l); g.v_cache = kv_layer(h, h->vcache, l);
         g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
         g.rows_per_seq = 1; g.pos_base = kPrefix - 1; g.d_pos = h->d_step;
         g.t_max = h->t_max; g.kv_fmt = h->kv_fmt;
         MB_TRY(run_gemm(h, g, EPI_QKV_ROPE, st));
     }
-    if (attn_wait) MB_CK(h, cudaStreamWaitEvent(st, attn_wait, 0));
+    MB_TRY(run_decode_attention(h, l, n, st));
     {
-        PdlOff off(attn_wait != nullptr);                  // two predecessors: the QKV kernel and the other group's event
-        MB_TRY(run_decode_attention(h, l, r0, n, n_all, st, true, qkv_split ? qkv_part : nullptr, qkv_nsplit));
-    }
-    if (attn_record) MB_CK(h, cudaEventRecord(attn_record, st));
-    {
-        GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.o, kHidden, n, kHidden, kHidden);
-        g.compact = compact; g.resident = tl.resident;
-        g.trace = h->trace; g.trace_id = 3000 + (r0 ? 100 : 0) + l;
-        g.split_k = tl.o_split; g.bn_hint = tl.o_bn; g.partial = partial;
+        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.o, kHidden, n, kHidden, kHidden);
+        g.resident = 1;
+        g.trace = h->trace; g.trace_id = 3000 + l;
+        g.split_k = tl.o_split; g.bn_hint = tl.o_bn; g.partial = h->gemm_partial;
         MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
     }
-    MB_CK(h, launch_add_rmsnorm(x, partial, tl.o_split, n, k.ln2, la_hi, lo_of(h, la_lo), st, h->trace, 4000 + (r0 ? 100 : 0) + l));
+    MB_CK(h, launch_add_rmsnorm(h->x, h->gemm_partial, tl.o_split, n, k.ln2, h->la_hi, lo_of(h, h->la_lo), st, h->trace, 4000 + l));
     h->launches++;
     {
-        GemmArgs g = gemm_base(h, la_hi, la_lo, kHidden, k.gu, kHidden, n, 2 * kInter, kHidden);
-        g.compact = compact; g.resident = tl.resident;
-        g.trace = h->trace; g.trace_id = 5000 + (r0 ? 100 : 0) + l;
-        if (tl.gu_split > 1 && h->engine == 1) {
-            g.split_k = tl.gu_split; g.bn_hint = 64;
-            g.partial = h->gu_part + (size_t)gi * kGuSplitMax * 128 * 2 * kInter;
-            g.fix_counter = h->fix_counter + (size_t)gi * 64;
-        }
-        g.out_hi = lh_hi; g.out_lo = lo_of(h, lh_lo); g.ldp = kInter;
+        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.gu, kHidden, n, 2 * kInter, kHidden);
+        g.resident = 1;
+        g.trace = h->trace; g.trace_id = 5000 + l;
+        g.out_hi = h->lh_hi; g.out_lo = lo_of(h, h->lh_lo); g.ldp = kInter;
         MB_TRY(run_gemm(h, g, EPI_SWIGLU, st));
     }
     {
-        GemmArgs g = gemm_base(h, lh_hi, lh_lo, kInter, k.down, kInter, n, kHidden, kInter);
-        g.compact = compact; g.resident = tl.resident;
-        g.trace = h->trace; g.trace_id = 6000 + (r0 ? 100 : 0) + l;
-        g.split_k = tl.down_split; g.bn_hint = tl.down_bn; g.partial = partial;
+        GemmArgs g = gemm_base(h, h->lh_hi, h->lh_lo, kInter, k.down, kInter, n, kHidden, kInter);
+        g.resident = 1;
+        g.trace = h->trace; g.trace_id = 6000 + l;
+        g.split_k = tl.down_split; g.bn_hint = tl.down_bn; g.partial = h->gemm_partial;
         MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
     }
-    MB_CK(h, launch_add_rmsnorm(x, partial, tl.down_split, n, next_norm, la_hi, lo_of(h, la_lo), st, h->trace, 7000 + (r0 ? 100 : 0) + l));
-    h->launches++;
-    return 0;
-}
-
-// Fused chain after the attention of layer l (decode_chain.cu): o_proj, +norm, gate/up, down, +norm, next layer's QKV.
-int lm_layer_decode_chain(Handle* h, int l, int B, cudaStream_t st) {
-    const LmLayerW& k = h->w.layer[l];
-    const bool last = l + 1 == kLayers;
-    ChainMaps maps;
-    ChainArgs ca;
-    memset(&ca, 0, sizeof(ca));
-    ca.split = h->policy == kPolicySplit;
-    ca.bar = h->chain_bar + (size_t)l * 8;
-    auto mk = [&](int idx, const bf16* hi, const bf16* lo, int rows, int K, int ld, int box) -> int {
-        MB_CK(h, build_chain_map(&maps.m[idx], hi, rows, K, ld, box));
-        if (ca.split) MB_CK(h, build_chain_map(&maps.m[idx + 1], lo, rows, K, ld, box));
-        else maps.m[idx + 1] = maps.m[idx];
-        return 0;
-    };
-    MB_TRY(mk(0, h->la_hi, h->la_lo, B, kHidden, kHidden, 128));
-    MB_TRY(mk(2, h->lh_hi, h->lh_lo, B, kInter, kInter, 128));
-    MB_TRY(mk(4, k.o.hi, k.o.lo, kHidden, kHidden, kHidden, 16));
-    MB_TRY(mk(6, k.gu.hi, k.gu.lo, 2 * kInter, kHidden, kHidden, 32));
-    MB_TRY(mk(8, k.down.hi, k.down.lo, kHidden, kInter, kInter, 16));
-    if (!last) MB_TRY(mk(10, h->w.layer[l + 1].qkv.hi, h->w.layer[l + 1].qkv.lo, kQkvDim, kHidden, kHidden, 16));
-    else { maps.m[10] = maps.m[0]; maps.m[11] = maps.m[0]; }
-    int n = 0;
-    {   // o_proj, split-K 3 -> partial
-        ChainOp& op = ca.op[n++];
-        op.kind = CH_GEMM; op.map_a = 0; op.map_b = 4; op.bn = 16; op.epi = EPI_GENERIC;
-        op.g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.o, kHidden, B, kHidden, kHidden);
-        op.g.split_k = 3; op.g.partial = h->gemm_partial;
-    }
-    {   // x += partials; planes = RMSNorm(x) * post_attention_layernorm
-        ChainOp& op = ca.op[n++];
-        op.kind = CH_ADDNORM; op.g.M = B; op.x = h->x; op.partial = h->gemm_partial; op.n_partial = 3; op.w = k.ln2;
-        op.hi = h->la_hi; op.lo = lo_of(h, h->la_lo);
-    }
-    {   // gate/up + SwiGLU -> hidden planes
-        ChainOp& op = ca.op[n++];
-        op.kind = CH_GEMM; op.map_a = 0; op.map_b = 6; op.bn = 32; op.epi = EPI_SWIGLU;
-        op.g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.gu, kHidden, B, 2 * kInter, kHidden);
-        op.g.out_hi = h->lh_hi; op.g.out_lo = lo_of(h, h->lh_lo); op.g.ldp = kInter;
-    }
-    {   // down, split-K 4 -> partial
-        ChainOp& op = ca.op[n++];
-        op.kind = CH_GEMM; op.map_a = 2; op.map_b = 8; op.bn = 16; op.epi = EPI_GENERIC;
-        op.g = gemm_base(h, h->lh_hi, h->lh_lo, kInter, k.down, kInter, B, kHidden, kInter);
-        op.g.split_k = 4; op.g.partial = h->gemm_partial;
-    }
-    {   // x += partials; planes = RMSNorm(x) * (next input_layernorm | final norm)
-        ChainOp& op = ca.op[n++];
-        op.kind = CH_ADDNORM; op.g.M = B; op.x = h->x; op.partial = h->gemm_partial; op.n_partial = 4;
-        op.w = last ? h->w.lm_norm : h->w.layer[l + 1].ln1;
-        op.hi = h->la_hi; op.lo = lo_of(h, h->la_lo);
-    }
-    if (!last) {   // next layer's QKV + RoPE + KV-cache write
-        ChainOp& op = ca.op[n++];
-        op.kind = CH_GEMM; op.map_a = 0; op.map_b = 10; op.bn = 16; op.epi = EPI_QKV_ROPE;
-        GemmArgs& g = op.g;
-        g = gemm_base(h, h->la_hi, h->la_lo, kHidden, h->w.layer[l + 1].qkv, kHidden, B, kQkvDim, kHidden);
-        g.q_out = h->q;
-        g.k_cache = kv_layer(h, h->kcache, l + 1); g.v_cache = kv_layer(h, h->vcache, l + 1);
-        g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
-        g.rows_per_seq = 1; g.pos_base = kPrefix - 1; g.d_pos = h->d_step;
-        g.t_max = h->t_max; g.kv_fmt = h->kv_fmt;
-    }
-    ca.n_ops = n;
-    MB_CK(h, launch_decode_chain(maps, ca, st));
+    MB_CK(h, launch_add_rmsnorm(h->x, h->gemm_partial, tl.down_split, n, next_norm, h->la_hi, lo_of(h, h->la_lo), st, h->trace, 7000 + l));
     h->launches++;
     return 0;
 }
@@ -663,15 +530,8 @@ int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_
     if (decode) {
         MB_TRY(run_decode_attention(h, l, B, st));
     } else {
-        static const bool fp32_attn = getenv("MB_ATTN_FP32") != nullptr;      // CUDA-core fp32 kernel, kept for A/B checks
-        if (fp32_attn)
-            MB_CK(h, launch_prefill_attention(h->q, kv_layer(h, h->kcache, l), kv_layer(h, h->vcache, l),
-                                              h->kv_fmt, B, rows_per_seq, h->t_max, h->la_hi,
-                                              lo_of(h, h->la_lo), st));
-        else
-            MB_CK(h, launch_prefill_attention_mma(h->q, kv_layer(h, h->kcache, l), kv_layer(h, h->vcache, l),
-                                                  h->kv_fmt, B, rows_per_seq, h->t_max, h->la_hi,
-                                                  lo_of(h, h->la_lo), st));
+        MB_CK(h, launch_prefill_attention_mma(h->q, kv_layer(h, h->kcache, l), kv_layer(h, h->vcache, l), h->kv_fmt, B,
+                                              rows_per_seq, h->t_max, h->la_hi, lo_of(h, h->la_lo), st));
         h->launches++;
     }
     {
@@ -716,74 +576,16 @@ int lm_head(Handle* h, int B, int row_stride, int row_off, bool fused, cudaStrea
 }
 
 int decode_step(Handle* h, int B, bool fused, cudaStream_t st) {
-    if (B <= 128 && h->engine == 1 && getenv("MB_DECODE_UNFUSED") == nullptr && getenv("MB_CHAIN") != nullptr) {
-        // Experimental (MB_CHAIN=1): 2 kernels per layer, decode attention + one persistent chain kernel whose phases
-        // are separated by software grid barriers.  Parity-green, but measured 10 % slower than the PDL-linked
-        // per-phase kernels below (1.94 vs 1.76 ms/step at B=128): a grid barrier plus the TMA round trip after it
-        // costs as much as a programmatic kernel boundary.  Kept as the starting point of a deeper fusion.
-        MB_CK(h, cudaMemsetAsync(h->chain_bar, 0, sizeof(unsigned) * kLayers * 8, st));
+    if (B <= 128 && h->engine == 1 && !h->decode_unfused) {
+        // 7 PDL-linked kernels per layer: QKV (+RoPE + KV write), attention, o_proj (split-K), add + RMSNorm, gate/up
+        // (+SwiGLU), down (split-K), add + RMSNorm; then lm_head with the per-16-column argmax.
         MB_CK(h, launch_add_rmsnorm(h->x, nullptr, 0, B, h->w.layer[0].ln1, h->la_hi, lo_of(h, h->la_lo), st));
         h->launches++;
-        {
-            const LmLayerW& k0 = h->w.layer[0];
-            GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k0.qkv, kHidden, B, kQkvDim, kHidden);
-            g.q_out = h->q;
-            g.k_cache = kv_layer(h, h->kcache, 0); g.v_cache = kv_layer(h, h->vcache, 0);
-            g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
-            g.rows_per_seq = 1; g.pos_base = kPrefix - 1; g.d_pos = h->d_step;
-            g.t_max = h->t_max; g.kv_fmt = h->kv_fmt;
-            MB_TRY(run_gemm(h, g, EPI_QKV_ROPE, st));
-        }
-        for (int l = 0; l < kLayers; ++l) {
-            MB_TRY(run_decode_attention(h, l, B, st));
-            MB_TRY(lm_layer_decode_chain(h, l, B, st));
-        }
+        for (int l = 0; l < kLayers; ++l)
+            MB_TRY(lm_layer_decode_fused(h, l, B, l + 1 < kLayers ? h->w.layer[l + 1].ln1 : h->w.lm_norm, st));
         return lm_head_gemm(h, B, fused, st);
     }
-    if (B <= 128 && getenv("MB_DECODE_UNFUSED") == nullptr) {
-        // Row groups: the batch is cut into G contiguous row groups whose per-layer kernel chains (7 PDL-linked
-        // kernels per layer) run on G streams.  Each chain is latency-bound (a dependent kernel every ~6 us) except
-        // its HBM-bound attention kernel, so while one group streams its K/V the other groups' GEMM / norm phases
-        // run; the compact GEMM variants keep two CTAs per SM so that the chains do not queue behind each other's
-        // shared memory.  Rows never interact, so the result does not depend on G.  lm_head runs once over all rows
-        // after the join (its 113 MB weight stream is the cost, not the rows).
-        const int G = decode_groups(h, B);
-        const int compact = decode_compact(G);
-        // Chains that start together stay in lock-step (all groups stream K/V at the same time, then all wait on
-        // their GEMM phases), which gains nothing.  stagger 1: group g starts when group g-1 has finished its first
-        // attention, half a layer period later.  stagger 2: the attention kernels of a layer are chained through
-        // events (g waits for g-1, group 0 of the next layer for the last group), so exactly one group streams K/V at
-        // any time while the others are in their GEMM / norm phases.
-        const int stagger = decode_stagger(G);
-        if (G > 1) MB_CK(h, cudaEventRecord(h->ev_fork, st));
-        for (int gi = 1; gi < G; ++gi) MB_CK(h, cudaStreamWaitEvent(h->grp_stream[gi - 1], h->ev_fork, 0));
-        for (int l = 0; l < kLayers; ++l) {
-            for (int gi = 0; gi < G; ++gi) {
-                const int r0 = (int)(((long long)B * gi) / G), n = (int)(((long long)B * (gi + 1)) / G) - r0;
-                cudaStream_t sg = gi == 0 ? st : h->grp_stream[gi - 1];
-                if (l == 0) {
-                    if (stagger == 1 && gi > 0) MB_CK(h, cudaStreamWaitEvent(sg, h->ev_attn[gi - 1], 0));
-                    PdlOff off(gi > 0);                     // a forked chain starts behind event edges, not a kernel
-                    MB_CK(h, launch_add_rmsnorm(h->x + (size_t)r0 * kHidden, nullptr, 0, n, h->w.layer[0].ln1,
-                                                h->la_hi + (size_t)r0 * kHidden, lo_of(h, h->la_lo + (size_t)r0 * kHidden), sg));
-                    h->launches++;
-                }
-                cudaEvent_t wait_ev = nullptr, rec_ev = nullptr;
-                if (stagger == 2) {
-                    wait_ev = gi > 0 ? h->ev_attn[gi - 1] : (l > 0 ? h->ev_attn[G - 1] : nullptr);
-                    rec_ev = h->ev_attn[gi];
-                } else if (stagger == 1 && l == 0 && gi + 1 < G) {
-                    rec_ev = h->ev_attn[gi];
-                }
-                MB_TRY(lm_layer_decode_fused(h, l, gi, r0, n, B, compact,
-                                             l + 1 < kLayers ? h->w.layer[l + 1].ln1 : h->w.lm_norm, sg, wait_ev, rec_ev));
-            }
-        }
-        for (int gi = 1; gi < G; ++gi) MB_CK(h, cudaEventRecord(h->ev_join[gi - 1], h->grp_stream[gi - 1]));
-        for (int gi = 1; gi < G; ++gi) MB_CK(h, cudaStreamWaitEvent(st, h->ev_join[gi - 1], 0));
-        PdlOff off(G > 1);                                  // after the join lm_head has G predecessors
-        return lm_head_gemm(h, B, fused, st);
-    }
+    // generic path (batches above one 128-row tile): the prefill kernels with one row per sequence
     for (int l = 0; l < kLayers; ++l) MB_TRY(lm_layer(h, l, B, 1, true, st));
     return lm_head(h, B, 1, 0, fused, st);
 }
@@ -797,7 +599,7 @@ int sample_and_advance(Handle* h, int B, int max_len, float temperature, float t
     a.temperature = temperature; a.top_p = top_p; a.d_step = h->d_step; a.tokens_out = h->d_tokens;
     a.forced = forced; a.x_next = h->x; a.done = h->d_done; a.logits_dump = logits_dump;
     MB_CK(h, launch_sample(a, st));
-    MB_CK(h, launch_step_advance(h->d_step, h->d_done, B, h->d_stop, h->w.rope_cos, h->w.rope_sin, kPrefix - 1, h->rope_cur, st));
+    MB_CK(h, launch_step_advance(h->d_step, h->d_done, B, h->d_stop, st));
     h->launches += 2;
     return 0;
 }
@@ -809,6 +611,7 @@ int check_ready(Handle* h, int B) {
 }
 
 int do_prefill(Handle* h, int B, float* logits_out, cudaStream_t st) {
+    NvtxRange r_("mellow.lm_prefill");
     for (int l = 0; l < kLayers; ++l) MB_TRY(lm_layer(h, l, B, kPrefix, false, st));
     MB_TRY(lm_head(h, B, kPrefix, kPrefix - 1, /*fused=*/false, st));   // step-0 logits stay available to mb_prefill callers
     if (logits_out)
@@ -818,6 +621,7 @@ int do_prefill(Handle* h, int B, float* logits_out, cudaStream_t st) {
 
 int do_decode(Handle* h, int B, int max_len, float temperature, float top_p, int eos_id, int* tokens_out,
               int tokens_on_host, int* steps_out_host, float* logits_dump, const int* forced, cudaStream_t st) {
+    NvtxRange r_("mellow.decode");
     if (max_len < 1 || max_len > h->max_new) return fail(h, "max_len out of range for this handle");
     MB_CK(h, cudaMemsetAsync(h->d_step, 0, sizeof(int), st));
     MB_CK(h, cudaMemsetAsync(h->d_done, 0, sizeof(int) * B, st));
@@ -825,13 +629,13 @@ int do_decode(Handle* h, int B, int max_len, float temperature, float top_p, int
     MB_CK(h, cudaMemsetAsync(h->d_tokens, 0, sizeof(int) * (size_t)B * max_len, st));
     // step 0: logits come from the prefill
     MB_TRY(sample_and_advance(h, B, max_len, temperature, top_p, eos_id, logits_dump, forced, st));
-    const bool use_graph = !logits_dump && !forced && getenv("MB_NO_GRAPH") == nullptr;
+    const bool use_graph = !logits_dump && !forced && h->use_graph;
     int stop = -1;
     if (use_graph && max_len > 1) {
         const bool hit = h->graph && h->g_B == B && h->g_max_len == max_len && h->g_eos == eos_id &&
                          h->g_temp == temperature && h->g_stream == st;
         if (!hit) {
-            if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+            drop_graph(h);
             cudaGraph_t graph = nullptr;
             const long long before = h->launches;
             MB_CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -875,9 +679,12 @@ int do_generate(Handle* h, const float* w1, const float* w2, const int* ids, int
     MB_TRY(frontend(h, w1, B, nullptr, h->bn, st));
     MB_TRY(frontend(h, w2, B, nullptr, h->bn + (size_t)B * kFrames * kMels, st));
     MB_TRY(encoder_body(h, 2 * B, -1, nullptr, nullptr, st));
-    MB_CK(h, launch_prefix(h->rows33, ids, h->w.embed, B, h->x, st));
-    h->launches++;
-    h->prefix_B = B;
+    {
+        NvtxRange r_("mellow.prefix");
+        MB_CK(h, launch_prefix(h->rows33, ids, h->w.embed, B, h->x, st));
+        h->launches++;
+        h->prefix_B = B;
+    }
     MB_TRY(do_prefill(h, B, nullptr, st));
     return do_decode(h, B, max_len, temperature, top_p, eos_id, tokens_out, tokens_on_host, steps_out_host, nullptr,
                      nullptr, st);
@@ -905,13 +712,6 @@ void mb_destroy(void* hv) {
     cudaSetDevice(h->device);
     if (h->graph) cudaGraphExecDestroy(h->graph);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
-    for (int i = 0; i < kMaxGroups - 1; ++i) {
-        if (h->grp_stream[i]) cudaStreamDestroy(h->grp_stream[i]);
-        if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
-    }
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-    for (int i = 0; i < kMaxGroups; ++i)
-        if (h->ev_attn[i]) cudaEventDestroy(h->ev_attn[i]);
     for (void* p : h->allocs) cudaFree(p);
     delete h;
 }
@@ -963,19 +763,7 @@ static int create_body(Handle* h) {
     h->kcache = kc; h->vcache = vc;
     MB_TRY(dev_alloc(h, &h->part_acc, B * kHeads * kMaxAttnSplit * kHeadDim));
     MB_TRY(dev_alloc(h, &h->part_ml, B * kHeads * kMaxAttnSplit * 2));
-    MB_TRY(dev_alloc(h, &h->gemm_partial, (size_t)kMaxGroups * kMaxSplitK * 128 * kHidden));
-    MB_TRY(dev_alloc(h, &h->qkv_part, (size_t)kMaxGroups * kQkvSplitMax * 128 * kQkvDim));
-    MB_TRY(dev_alloc(h, &h->rope_cur, 64));
-    MB_TRY(dev_alloc(h, &h->gu_part, (size_t)kMaxGroups * kGuSplitMax * 128 * 2 * kInter));
-    MB_TRY(dev_alloc(h, &h->fix_counter, (size_t)kMaxGroups * 64));
-    MB_CK(h, cudaMemset(h->fix_counter, 0, sizeof(unsigned) * kMaxGroups * 64));
-    for (int i = 0; i < kMaxGroups - 1; ++i) {
-        MB_CK(h, cudaStreamCreateWithFlags(&h->grp_stream[i], cudaStreamNonBlocking));
-        MB_CK(h, cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming));
-    }
-    MB_CK(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    for (int i = 0; i < kMaxGroups; ++i) MB_CK(h, cudaEventCreateWithFlags(&h->ev_attn[i], cudaEventDisableTiming));
-    MB_TRY(dev_alloc(h, &h->chain_bar, (size_t)kLayers * 8));
+    MB_TRY(dev_alloc(h, &h->gemm_partial, (size_t)kMaxSplitK * 128 * kHidden));
     MB_TRY(dev_alloc(h, &h->d_tokens, B * h->max_new));
     MB_TRY(dev_alloc(h, &h->d_done, B));
     MB_TRY(dev_alloc(h, &h->d_step, 4));
@@ -1009,13 +797,10 @@ void* mb_create(int device, int max_batch, int max_new_tokens, int policy) {
     cudaSetDevice(device);
     Handle* h = new Handle();
     h->device = device; h->max_batch = max_batch; h->max_new = max_new_tokens;
-    {
-        // kPolicySplit24 = kPolicySplit with the KV cache stored at 24 bits (MB_KV24=1 turns it on for kPolicySplit too)
-        const char* e = getenv("MB_KV24");
-        const bool kv24 = policy == kPolicySplit24 || (e && atoi(e) != 0);
-        h->policy = policy == kPolicySplit24 ? kPolicySplit : policy;
-        h->kv_fmt = policy == kPolicyFast ? kKvBf16 : (kv24 ? kKvF24 : kKvF32);
-    }
+    // kPolicySplit24 = kPolicySplit with the KV cache stored at 24 bits
+    h->policy = policy == kPolicySplit24 ? kPolicySplit : policy;
+    h->kv_fmt = policy == kPolicyFast ? kKvBf16 : (policy == kPolicySplit24 ? kKvF24 : kKvF32);
+    h->use_graph = tunables().graph; h->decode_unfused = tunables().decode_unfused; h->kv_prefetch = tunables().kv_prefetch;
     build_table(h->t, h->w);
     // a blocking stream: implicitly ordered with work the caller issued on the legacy default stream
     if (cudaStreamCreate(&h->own_stream) != cudaSuccess || create_body(h) != 0) {
@@ -1032,35 +817,34 @@ int mb_bind_weights(void* hv, const void* dev_arena, long long nbytes) {
     if (((uintptr_t)dev_arena & 255) != 0) return fail(h, "weight arena must be 256-byte aligned");
     for (auto& e : h->t.entries) *e.slot = reinterpret_cast<const char*>(dev_arena) + e.offset;
     h->bound = true;
+    drop_graph(h);                                        // a captured decode step holds weight pointers / tensor maps by value
     return 0;
 }
 
 long long mb_workspace_bytes(void* hv) { return (long long)reinterpret_cast<Handle*>(hv)->ws_bytes; }
-int mb_set_gemm_engine(void* hv, int engine) {
+int mb_set_option(void* hv, const char* name, int value) {
     Handle* h = reinterpret_cast<Handle*>(hv);
-    if (engine != 0 && engine != 1) return fail(h, "unknown GEMM engine");
-    h->engine = engine;
-    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
-    return 0;
-}
-int mb_set_decode_groups(void* hv, int groups) {
-    Handle* h = reinterpret_cast<Handle*>(hv);
-    if (groups < 0 || groups > kMaxGroups) return fail(h, "decode row groups must be 0 (automatic) .. 4");
-    h->groups = groups;
-    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
-    return 0;
-}
-int mb_set_decode_qkv_split(void* hv, int nsplit) {
-    Handle* h = reinterpret_cast<Handle*>(hv);
-    if (nsplit != -1 && nsplit != 0 && nsplit != 3 && nsplit != 9) return fail(h, "decode QKV split must be -1 (default), 0, 3 or 9");
-    h->qkv_split = nsplit;
-    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    const std::string n = name ? name : "";
+    if (n == "graph") h->use_graph = value != 0;
+    else if (n == "decode_unfused") h->decode_unfused = value != 0;
+    else if (n == "skip_finished") h->skip_finished = value != 0;
+    else if (n == "kv_prefetch") h->kv_prefetch = value;
+    else if (n == "wide_tiles") h->wide_tiles = value;
+    else if (n == "gemm_engine") {
+#ifdef MB_LAB
+        if (value != 0 && value != 1) return fail(h, "unknown GEMM engine");
+        h->engine = value;
+#else
+        if (value != 1) return fail(h, "the mma.sync cross-check engine is only in lab builds (MB_BUILD_LAB=1)");
+#endif
+    } else return fail(h, "mb_set_option: unknown option");
+    drop_graph(h);
     return 0;
 }
 int mb_set_trace(void* hv, void* dev_trace_buf) {
     Handle* h = reinterpret_cast<Handle*>(hv);
     h->trace = reinterpret_cast<TraceBuf*>(dev_trace_buf);
-    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    drop_graph(h);
     return 0;
 }
 long long mb_kernel_launches(void* hv) { return reinterpret_cast<Handle*>(hv)->launches; }
@@ -1146,6 +930,36 @@ int mb_prefill(void* hv, int B, float* logits_out, void* stream) {
     if (h->prefix_B != B) return fail(h, "mb_prefill: no prefix of this batch size (call mb_prefix / mb_set_prefix)");
     cudaSetDevice(h->device);
     return do_prefill(h, B, logits_out, pick_stream(h, stream));
+}
+
+// The reference's inner seam `model.caption_decoder.lm(inputs_embeds=x).logits[:, -1]` (wrapper.py:217-218): one
+// cache-less causal forward over S positions, last-position logits.  Uses the prefill kernels with rows_per_seq = S.
+int mb_lm_forward_last(void* hv, const float* embeds, int B, int S, float* logits_out, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    MB_TRY(check_ready(h, B));
+    if (S < 1 || S > h->t_max || (long long)B * S > (long long)h->max_batch * kPrefix)
+        return fail(h, "mb_lm_forward_last: need 1 <= S <= 389 + max_new_tokens and B*S <= max_batch*389");
+    cudaSetDevice(h->device);
+    cudaStream_t st = pick_stream(h, stream);
+    NvtxRange r_("mellow.lm_forward_last");
+    MB_CK(h, cudaMemcpyAsync(h->x, embeds, (size_t)B * S * kHidden * 4, cudaMemcpyDeviceToDevice, st));
+    h->prefix_B = 0;                                       // the prefix / KV state of a previous mb_prefix is overwritten
+    for (int l = 0; l < kLayers; ++l) MB_TRY(lm_layer(h, l, B, S, false, st));
+    MB_TRY(lm_head(h, B, S, S - 1, /*fused=*/false, st));
+    if (logits_out)
+        MB_CK(h, cudaMemcpyAsync(logits_out, h->logits, (size_t)B * kVocab * 4, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
+// `lm.model.embed_tokens(ids)` (wrapper.py:237): ids [n] i32 -> out [n,576] f32
+int mb_embed_tokens(void* hv, const int* ids, int n, float* out, void* stream) {
+    Handle* h = reinterpret_cast<Handle*>(hv);
+    if (!h->bound) return fail(h, "weights not bound");
+    if (n < 1) return fail(h, "mb_embed_tokens: n < 1");
+    cudaSetDevice(h->device);
+    MB_CK(h, launch_embed_rows(ids, n, h->w.embed, out, pick_stream(h, stream)));
+    h->launches++;
+    return 0;
 }
 
 int mb_decode(void* hv, int B, int max_len, float temperature, float top_p, int eos_id, int* tokens_out,

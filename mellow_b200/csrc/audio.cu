@@ -62,11 +62,12 @@ cudaError_t launch_resample(const float* x, long long n_in, int orig, int nw, co
                             float* y, long long n_out, cudaStream_t st) {
     const size_t smem = ((size_t)klen * (PH + 1) + (size_t)(FR - 1) * orig + klen) * sizeof(float);
     if (smem > 200 * 1024) return cudaErrorInvalidValue;
-    static size_t configured = 0;
-    if (smem > configured) {
+    static size_t configured[kMaxDevices] = {};
+    const int dev = current_device();
+    if (smem > configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        configured = smem;
+        configured[dev] = smem;
     }
     const long long frames = (n_out + nw - 1) / nw;
     dim3 grid((unsigned)((frames + FR - 1) / FR), (unsigned)((nw + PH - 1) / PH));

@@ -39,7 +39,7 @@ constexpr int kKvHeads = 3;
 constexpr int kHeadDim = 64;
 constexpr int kQkvDim = 960;        // 576 q + 192 k + 192 v
 constexpr int kInter = 1536;
-constexpr int kMaxPos = 1024;       // rope table rows (389 + max_new <= 1024)
+constexpr int kMaxPos = 8192;       // rope table rows = SmolLM2 max_position_embeddings (389 + max_new <= 8192)
 
 // Precision policy (mb_create): how the tensor-core GEMM operands are represented.
 //   kPolicySplit: every fp32 operand x is carried as two bf16 planes hi=bf16(x), lo=bf16(x-hi) and each GEMM
@@ -161,6 +161,19 @@ __device__ __forceinline__ uint32_t f24_bits(float x) {
     return (u + 0x7Fu + ((u >> 8) & 1u)) & 0xFFFFFF00u;
 }
 __device__ __forceinline__ float f24_round(float x) { return __uint_as_float(f24_bits(x)); }
+// Unpack: `hw` holds the upper halves of two consecutive values (even in the low 16 bits), `lw` their mantissa bytes at
+// byte 2*sel (even) and 2*sel+1 (odd).  One PRMT per value; the lowest byte of the result repeats the mantissa byte
+// instead of being zero, i.e. the value is exact to 2^-25 relative (256x below the 24-bit rounding).
+__device__ __forceinline__ float f24_unpack_even(uint32_t hw, uint32_t lw, int sel) {
+    return __uint_as_float(__byte_perm(hw, lw, sel ? 0x1066u : 0x1044u));
+}
+__device__ __forceinline__ float f24_unpack_odd(uint32_t hw, uint32_t lw, int sel) {
+    return __uint_as_float(__byte_perm(hw, lw, sel ? 0x3277u : 0x3255u));
+}
+// asks the L2 to fetch [p, p + bytes) (p 16-byte aligned, bytes a multiple of 16); no destination, no completion
+__device__ __forceinline__ void l2_prefetch(const void* p, int bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 
 // KV-cache element types
 __device__ __forceinline__ float kv_load(const float* p) { return *p; }
@@ -173,6 +186,30 @@ __device__ __forceinline__ void kv_store2(bf16* p, float a, float b) {
     v.x = __float2bfloat16_rn(a);
     v.y = __float2bfloat16_rn(b);
     *reinterpret_cast<__nv_bfloat162*>(p) = v;
+}
+
+// Host: per-device caches of one-time launch setup (cudaFuncSetAttribute is per device; a process may drive several
+// GPUs, one handle each).
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+}
+inline int sm_count() {
+    static int n[kMaxDevices] = {};
+    const int dev = current_device();
+    if (n[dev] == 0) cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    return n[dev];
+}
+// once per (kernel, device): opt in to more than 48 KB of dynamic shared memory
+template <typename K>
+inline cudaError_t ensure_smem(K kern, size_t bytes, bool* configured) {
+    const int dev = current_device();
+    if (configured[dev]) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) configured[dev] = true;
+    return e;
 }
 
 // Host: launch with the programmatic-stream-serialization attribute (disabled by MB_NO_PDL=1).

@@ -1,5 +1,5 @@
-// HTSAT (Swin) encoder glue kernels: row normalisation feeding the GEMM operand planes, shifted-window attention,
-// and the TSCAM tail gathers.  Reference: mellow/model/htsat.py:414-455 (block), :301-332 (window attention),
+// HTSAT (Swin) encoder glue kernels: row normalisation feeding the GEMM operand planes and the TSCAM tail gathers
+// (the shifted-window attention lives in attn_mma.cu).  Reference: mellow/model/htsat.py:414-455 (block), :301-332 (window attention),
 // :478-499 (patch merging), :742-796 (tail), mellow/model/mellow.py:48-52 (projection).
 #include "kernels.cuh"
 
@@ -78,83 +78,6 @@ cudaError_t launch_norm_kind(const NormArgs& a, cudaStream_t st) {
         case 1536: return launch_k(norm_kernel<1536, KIND>, dim3(grid), dim3(256), 0, st, a);
         default: return cudaErrorInvalidValue;
     }
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// (Shifted-)window attention, one CTA per (clip, window, head), one thread per query token.  The cyclic shift and
-// the window partition / reverse of the reference (htsat.py:428-449) are pure index arithmetic here: local token
-// (iy,ix) of window (wy,wx) lives at source token ((wy*8+iy+shift)%R, (wx*8+ix+shift)%R), which is also where its
-// output row goes.  The q rows of the qkv weight are pre-scaled by head_dim^-0.5 at pack time (htsat.py:311).
-constexpr int kHd = 24;
-
-__device__ __forceinline__ int shift_band(int v, int R) { return v < R - kWin ? 0 : (v < R - kWin / 2 ? 1 : 2); }
-
-__global__ void __launch_bounds__(64) window_attention_kernel(const float* __restrict__ qkv,
-                                                              const float* __restrict__ relbias,
-                                                              bf16* __restrict__ out_hi, bf16* __restrict__ out_lo,
-                                                              int R, int C, int n_heads, int shift) {
-    __shared__ __align__(16) float sk[kWinTok][kHd];
-    __shared__ __align__(16) float sv[kWinTok][kHd];
-    __shared__ float sbias[kWinTok][kWinTok + 1];
-    __shared__ int slab[kWinTok];
-    const int i = threadIdx.x;
-    const int head = blockIdx.x, win = blockIdx.y, clip = blockIdx.z;
-    const int nwx = R / kWin;
-    const int wy = win / nwx, wx = win - wy * nwx;
-    const int y = wy * kWin + (i >> 3), x = wx * kWin + (i & 7);          // coordinates in the shifted frame
-    const int sy = (y + shift) % R, sx = (x + shift) % R;
-    const size_t tok = (size_t)clip * R * R + (size_t)sy * R + sx;
-    const float* row = qkv + tok * 3 * C + head * kHd;
-    pdl_trigger();
-    pdl_wait();
-    float q[kHd];
-#pragma unroll
-    for (int d = 0; d < kHd; d += 4) {
-        const float4 a = *reinterpret_cast<const float4*>(row + d);
-        q[d] = a.x; q[d + 1] = a.y; q[d + 2] = a.z; q[d + 3] = a.w;
-        *reinterpret_cast<float4*>(&sk[i][d]) = *reinterpret_cast<const float4*>(row + C + d);
-        *reinterpret_cast<float4*>(&sv[i][d]) = *reinterpret_cast<const float4*>(row + 2 * C + d);
-    }
-    slab[i] = shift > 0 ? shift_band(y, R) * 3 + shift_band(x, R) : 0;
-    const float* bsrc = relbias + (size_t)head * kWinTok * kWinTok;
-    for (int e = i; e < kWinTok * kWinTok; e += 64) sbias[e >> 6][e & 63] = bsrc[e];
-    __syncthreads();
-
-    float s[kWinTok];
-    const int mylab = slab[i];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < kWinTok; ++j) {
-        float acc = 0.f;
-#pragma unroll
-        for (int d = 0; d < kHd; d += 4) {
-            const float4 k4 = *reinterpret_cast<const float4*>(&sk[j][d]);
-            acc += q[d] * k4.x; acc += q[d + 1] * k4.y; acc += q[d + 2] * k4.z; acc += q[d + 3] * k4.w;
-        }
-        acc += sbias[i][j];
-        if (slab[j] != mylab) acc += -100.0f;                              // attn_mask, htsat.py:408
-        s[j] = acc;
-        mx = fmaxf(mx, acc);
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int j = 0; j < kWinTok; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
-    const float inv = 1.0f / sum;
-    float o[kHd];
-#pragma unroll
-    for (int d = 0; d < kHd; ++d) o[d] = 0.f;
-#pragma unroll
-    for (int j = 0; j < kWinTok; ++j) {
-        const float p = s[j] * inv;
-#pragma unroll
-        for (int d = 0; d < kHd; d += 4) {
-            const float4 v4 = *reinterpret_cast<const float4*>(&sv[j][d]);
-            o[d] += p * v4.x; o[d + 1] += p * v4.y; o[d + 2] += p * v4.z; o[d + 3] += p * v4.w;
-        }
-    }
-    const size_t ob = tok * C + head * kHd;
-#pragma unroll
-    for (int d = 0; d < kHd; d += 2) store_planes2(out_hi, out_lo, ob + d, o[d], o[d + 1]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -244,13 +167,6 @@ cudaError_t launch_norm(const NormArgs& a, int kind, cudaStream_t st) {
         case NORM_LN_MERGE: return launch_norm_kind<NORM_LN_MERGE>(a, st);
     }
     return cudaErrorInvalidValue;
-}
-
-cudaError_t launch_window_attention(const float* qkv, const float* relbias, bf16* out_hi, bf16* out_lo, int n_clips,
-                                    int res, int C, int n_heads, int shift, cudaStream_t st) {
-    if (C != n_heads * kHd || res % kWin != 0) return cudaErrorInvalidValue;
-    dim3 grid(n_heads, (res / kWin) * (res / kWin), n_clips);
-    return launch_k(window_attention_kernel, grid, dim3(64), 0, st, qkv, relbias, out_hi, out_lo, res, C, n_heads, shift);
 }
 
 cudaError_t launch_tail_gather(const float* y, int n_clips, float* latent, bf16* col_hi, bf16* col_lo,

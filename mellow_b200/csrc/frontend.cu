@@ -175,13 +175,8 @@ __global__ void __launch_bounds__(256) patch_embed_kernel(const float* __restric
 
 cudaError_t launch_logmel(const float* wave, int n_clips, const FrontendW& w, float* logmel_out, float* bn_out,
                           cudaStream_t st) {
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(logmel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(LogmelSmem));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static bool configured[kMaxDevices] = {};
+    if (cudaError_t e = ensure_smem(logmel_kernel, sizeof(LogmelSmem), configured); e != cudaSuccess) return e;
     dim3 grid((kFrames + kFramesPerCta - 1) / kFramesPerCta, n_clips);
     return launch_k(logmel_kernel, grid, dim3(kFramesPerCta * 32), sizeof(LogmelSmem), st, wave, w, logmel_out, bn_out);
 }

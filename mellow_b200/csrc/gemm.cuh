@@ -15,13 +15,9 @@ struct GemmArgs {
     int passes;                                       // 3: hi*hi + hi*lo + lo*hi ; 1: hi*hi
     int split_k; float* partial;                      // split_k > 1: raw fp32 partial sums [split_k][M][N], no epilogue
     TraceBuf* trace; unsigned trace_id;               // optional timeline stamps (common.cuh)
-    unsigned* fix_counter;                            // weight-resident kernel, split_k > 1: per-N-tile arrival counters (zero between
-                                                      // launches).  The split that arrives last sums the partials in z order and runs
-                                                      // the fused epilogue itself, so no consumer-side reduction is needed.
     int epi_sleep;                                    // weight-resident kernel: ns the epilogue warps sleep between polls of the accumulator barrier
     int resident;                                     // decode chain: use the weight-resident kernel (gemm_skinny.cu) when the shape fits
-    int bn_hint;                                      // decode-sized split-K GEMMs: N-tile width 48 / 64 (0 = default rule)
-    int compact;                                      // decode-sized GEMMs: use the two-CTAs-per-SM variants (gemm_umma.cu)
+    int bn_hint;                                      // decode-sized GEMMs: N-tile width 16 / 32 (0 = default rule)
     // EPI_GENERIC: v = act(acc + bias) + residual -> out_f32 and/or bf16 planes
     const float* bias;
     const float* residual; int ldr;
@@ -281,7 +277,7 @@ __device__ __forceinline__ void epilogue_row16(const GemmArgs& g, int m, int n, 
     }
 }
 
-// Engine entry points (gemm_mma.cu, gemm_umma.cu)
+// Engine entry points (gemm_umma.cu, gemm_skinny.cu; gemm_mma.cu = mma.sync cross-check engine of lab builds)
 cudaError_t launch_gemm_mma(const GemmArgs& g, int epi, cudaStream_t st);
 cudaError_t launch_gemm_skinny(const GemmArgs& g, int epi, int bn, cudaStream_t st);   // gemm_skinny.cu
 

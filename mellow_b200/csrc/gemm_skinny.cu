@@ -67,7 +67,6 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     uint64_t* tfull = aempty + C::STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
     uint32_t* trace_slot = tmem_slot + 1;
-    uint32_t* last_slot = trace_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsplit = g.split_k > 1 ? g.split_k : 1;
@@ -212,53 +211,6 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
     }
     if (threadIdx.x == 0) trace_put(g.trace, trec, g.trace_id, 8);                      // this warp's epilogue stores issued
-    if (nsplit > 1 && g.fix_counter != nullptr) {
-        // In-kernel split-K fix-up: every split has written its partial tile; the one whose ticket shows that all the
-        // others arrived before it re-reads the nsplit partials from L2, adds them in z order (deterministic whoever
-        // is last) and runs the fused epilogue.  The counter returns to zero for the next launch.
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == kProducerWarp * 32) {
-            const unsigned ticket = atomicAdd(g.fix_counter + (blockIdx.x - z * tiles_n), 1u);
-            const bool last = ticket == (unsigned)(nsplit - 1);
-            if (last) g.fix_counter[blockIdx.x - z * tiles_n] = 0u;
-            *last_slot = last ? 1u : 0u;
-        }
-        __syncthreads();
-        if (*last_slot != 0u && warp < kEpiWarps) {
-            __threadfence();
-            const int q = warp & 3, half = warp >> 2;
-            const int m = q * 32 + lane;
-            constexpr int kUnits = BN / 16;
-            if (m < g.M) {
-#pragma unroll 1
-                for (int u = half; u < kUnits; u += 2) {
-                    const int n = n0 + u * 16;
-                    if (n >= g.N) break;
-                    float v[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
-                    const float* p0 = g.partial + (size_t)m * g.N + n;
-                    for (int zz = 0; zz < nsplit; zz += 3) {         // three splits' loads in flight at a time
-                        float4 t[3][4];
-#pragma unroll
-                        for (int k = 0; k < 3; ++k)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                t[k][j] = zz + k < nsplit ? __ldcg(reinterpret_cast<const float4*>(p0 + (size_t)(zz + k) * g.M * g.N) + j)
-                                                          : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k)
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                v[4 * j] += t[k][j].x; v[4 * j + 1] += t[k][j].y; v[4 * j + 2] += t[k][j].z; v[4 * j + 3] += t[k][j].w;
-                            }
-                    }
-                    epilogue_row16<EPI>(g, m, n, v);
-                }
-            }
-        }
-    }
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == kProducerWarp * 32) trace_close(g.trace, *trace_slot, g.trace_id);
@@ -272,12 +224,8 @@ template <int BN, int EPI, bool SPLIT, int KBMAX>
 cudaError_t launch_skinny(const GemmArgs& g, cudaStream_t st) {
     using C = SkinnyCfg<BN, SPLIT, KBMAX>;
     auto kern = gemm_skinny_kernel<BN, EPI, SPLIT, KBMAX>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static bool configured[kMaxDevices] = {};
+    if (cudaError_t e = ensure_smem(kern, C::SMEM, configured); e != cudaSuccess) return e;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
     if (!make_map(&ta_hi, g.A_hi, g.M, g.K, g.lda, BM) || !make_map(&tb_hi, g.W_hi, g.N, g.K, g.ldw, BN))
         return cudaErrorInvalidValue;
@@ -309,12 +257,6 @@ cudaError_t launch_skinny_epi(const GemmArgs& g, int bn, cudaStream_t st) {
     }
     if (bn == 16 && kb_max <= 9) return launch_skinny_p<16, EPI, 9>(g, st);
     if (bn == 32 && kb_max <= 9) return launch_skinny_p<32, EPI, 9>(g, st);
-    if constexpr (EPI == EPI_GENERIC) {
-        if (bn == 48 && kb_max <= 3) return launch_skinny_p<48, EPI, 3>(g, st);
-    }
-    if constexpr (EPI == EPI_GENERIC || EPI == EPI_SWIGLU) {
-        if (bn == 64 && kb_max <= 3) return launch_skinny_p<64, EPI, 3>(g, st);
-    }
     return cudaErrorNotSupported;
 }
 
@@ -324,12 +266,7 @@ cudaError_t launch_skinny_epi(const GemmArgs& g, int bn, cudaStream_t st) {
 // fit this kernel (more than one M tile, more tiles than SMs, K slice longer than the weight region); the caller then
 // uses the persistent ring kernel of gemm_umma.cu.
 cudaError_t launch_gemm_skinny(const GemmArgs& g, int epi, int bn, cudaStream_t st) {
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int num_sms = sm_count();
     const int total = ((g.N + bn - 1) / bn) * (g.split_k > 1 ? g.split_k : 1);
     if (g.M > BM || total > num_sms) return cudaErrorNotSupported;
     switch (epi) {

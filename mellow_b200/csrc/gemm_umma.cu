@@ -18,31 +18,18 @@ namespace {
 
 using namespace umma;
 
-// AM: rows of the activation tile that TMA actually fetches (128, or 64 for row groups of <= 64 decode rows).  The UMMA
-//     always runs M=128: with AM=64 the descriptor's rows 64..127 alias whatever follows in shared memory (the W tile,
-//     the next stage, the tail pad).  Accumulator row r depends on A row r only, so those rows hold garbage that the
-//     epilogue never reads (m < M guard); TAIL_PAD keeps the aliased reads inside the allocation.
-// ST: ring depth; 0 = as deep as 227 KB allows (one CTA per SM).  ST > 0 selects the "compact" decode variants whose
-//     footprint (< 113 KB) lets two CTAs share an SM, so the CTAs of the next kernel of a PDL chain -- or of another
-//     row group's chain -- are resident (barriers initialised, TMEM allocated, weight tiles in flight) while the
-//     current kernel still runs.
-template <int BN, bool SPLIT, int AM = BM, int ST = 0>
+template <int BN, bool SPLIT>
 struct Cfg {
-    static constexpr uint32_t A_TILE = AM * BK * 2;
+    static constexpr uint32_t A_TILE = BM * BK * 2;
     static constexpr uint32_t B_BYTES = BN * BK * 2;
     static constexpr uint32_t STAGE_BYTES = (SPLIT ? 2 : 1) * (A_TILE + B_BYTES);
-    static constexpr uint32_t STAGING_BYTES = 0;
-    static constexpr uint32_t TAIL_PAD = AM < BM ? A_BYTES - A_TILE : 0;
-    static constexpr uint32_t BUDGET = 227u * 1024u - 1024u - 256u - STAGING_BYTES - TAIL_PAD;
+    static constexpr uint32_t BUDGET = 227u * 1024u - 1024u - 256u;
     static constexpr int STAGES_FIT = (int)(BUDGET / STAGE_BYTES);
-    static constexpr int STAGES = ST > 0 ? ST : (STAGES_FIT > 8 ? 8 : STAGES_FIT);
-    static constexpr int MIN_CTAS = ST > 0 ? 2 : 1;
+    static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
     static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                             // two accumulators: MMA of tile i+1
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 256 + TAIL_PAD;   // overlaps epilogue of tile i
-    static_assert(STAGES >= 2 && STAGES <= STAGES_FIT, "tile does not fit");
-    static_assert(ST == 0 || SMEM <= 113u * 1024u, "compact variant must leave room for a second CTA on the SM");
-    static_assert(AM == BM || AM == 64, "activation tile is 128 or 64 rows");
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;       // overlaps epilogue of tile i
+    static_assert(STAGES >= 2, "tile does not fit");
 };
 
 struct TileCoord { int m0, n0, z, kb_begin, KB; };
@@ -64,20 +51,15 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile, int
 // Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence (n fastest, so the CTAs that run
 // concurrently share A rows and the whole W in L2).  The smem ring runs continuously across tiles; the accumulator
 // is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-// CL > 1 (decode-sized GEMMs): CL CTAs of a thread-block cluster own CL consecutive N tiles of the same 128-row
-// activation tile.  Each CTA loads 1/CL of every A k-block and TMA-multicasts it to all of them, so the activation
-// bytes pulled from L2 drop CL-fold; a stage is recycled only after all CL consumers released it (multicast commit).
-template <int BN, int EPI, bool SPLIT, int CL, int AM, int ST>
-__global__ void __launch_bounds__(kThreads, (Cfg<BN, SPLIT, AM, ST>::MIN_CTAS))
+template <int BN, int EPI, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                  const GemmArgs g) {
-    using C = Cfg<BN, SPLIT, AM, ST>;
-    static_assert(CL == 1 || AM == BM, "multicast clusters split the full 128-row tile");
+    using C = Cfg<BN, SPLIT>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* staging = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + C::STAGING_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
     uint64_t* empty = full + C::STAGES;
     uint64_t* tfull = empty + C::STAGES;       // [2] accumulator ready
     uint64_t* tempty = tfull + 2;              // [2] accumulator drained by the 4 epilogue warps
@@ -89,14 +71,11 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int per_split = tiles_n * ((g.M + BM - 1) / BM);
     const int total = per_split * nsplit;
 
-    const uint32_t crank = CL > 1 ? cluster_rank() : 0u;
-    constexpr uint16_t cmask = (uint16_t)((1u << CL) - 1u);
-    constexpr uint32_t A_PART = C::A_TILE / CL;                       // bytes of the A tile this CTA fetches per plane
     pdl_trigger();
     unsigned trec = kTraceNone;                                      // thread 0 only
     if (threadIdx.x == 0) {
         trec = trace_open(g.trace, g.trace_id);
-        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
+        for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
         mbar_init(&tempty[0], kEpiWarps); mbar_init(&tempty[1], kEpiWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -107,7 +86,6 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (CL > 1) cluster_sync_all();                                  // peers' barriers are initialised before any remote arrive
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -133,14 +111,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     if (first_cta()) trace_put(g.trace, trec, g.trace_id, TR_WAITED);
                     for (int i = 0; i < npre; ++i) {
                         unsigned char* st = smem + (size_t)i * C::STAGE_BYTES;
-                        if (CL > 1) {
-                            const int mr = t.m0 + (int)crank * (BM / CL);
-                            tma_load_2d_mc(st + crank * A_PART, &tm_a_hi, &full[i], (t.kb_begin + i) * BK, mr, cmask);
-                            if (SPLIT) tma_load_2d_mc(st + C::A_TILE + C::B_BYTES + crank * A_PART, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, mr, cmask);
-                        } else {
-                            tma_load_2d(st, &tm_a_hi, &full[i], (t.kb_begin + i) * BK, t.m0);
-                            if (SPLIT) tma_load_2d(st + C::A_TILE + C::B_BYTES, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, t.m0);
-                        }
+                        tma_load_2d(st, &tm_a_hi, &full[i], (t.kb_begin + i) * BK, t.m0);
+                        if (SPLIT) tma_load_2d(st + C::A_TILE + C::B_BYTES, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, t.m0);
                     }
                     kb = npre;
                     it = npre;
@@ -153,14 +125,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     mbar_expect_tx(&full[s], C::STAGE_BYTES);
                     tma_load_2d(st + C::A_TILE, &tm_b_hi, &full[s], (t.kb_begin + kb) * BK, t.n0);
                     if (SPLIT) tma_load_2d(st + 2 * C::A_TILE + C::B_BYTES, &tm_b_lo, &full[s], (t.kb_begin + kb) * BK, t.n0);
-                    if (CL > 1) {
-                        const int mr = t.m0 + (int)crank * (BM / CL);
-                        tma_load_2d_mc(st + crank * A_PART, &tm_a_hi, &full[s], (t.kb_begin + kb) * BK, mr, cmask);
-                        if (SPLIT) tma_load_2d_mc(st + C::A_TILE + C::B_BYTES + crank * A_PART, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, mr, cmask);
-                    } else {
-                        tma_load_2d(st, &tm_a_hi, &full[s], (t.kb_begin + kb) * BK, t.m0);
-                        if (SPLIT) tma_load_2d(st + C::A_TILE + C::B_BYTES, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, t.m0);
-                    }
+                    tma_load_2d(st, &tm_a_hi, &full[s], (t.kb_begin + kb) * BK, t.m0);
+                    if (SPLIT) tma_load_2d(st + C::A_TILE + C::B_BYTES, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, t.m0);
                 }
             }
         }
@@ -195,8 +161,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                             umma_bf16_c<true>(tacc, umma_desc_join(a_lo + 2 * k), dbh, idesc);
                         }
                     }
-                    if (CL > 1) umma_commit_mc(&empty[s], cmask);    // every producer of the cluster writes into this stage
-                    else umma_commit(&empty[s]);                     // frees the smem stage once these MMAs retire
+                    umma_commit(&empty[s]);                          // frees the smem stage once these MMAs retire
                 }
                 umma_commit(&tfull[buf]);                            // accumulator complete
             }
@@ -255,7 +220,6 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == 0) trace_close(g.trace, trec, g.trace_id);
-    if (CL > 1) cluster_sync_all();                                  // no CTA leaves while peers may still signal it
     if (warp == 1) {
         __syncwarp();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
@@ -263,86 +227,48 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN, int EPI, bool SPLIT, int CL = 1, int AM = BM, int ST = 0>
+template <int BN, int EPI, bool SPLIT>
 cudaError_t launch_one(const GemmArgs& g, cudaStream_t st) {
-    using C = Cfg<BN, SPLIT, AM, ST>;
-    auto kern = gemm_umma_kernel<BN, EPI, SPLIT, CL, AM, ST>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    using C = Cfg<BN, SPLIT>;
+    auto kern = gemm_umma_kernel<BN, EPI, SPLIT>;
+    static bool configured[kMaxDevices] = {};
+    if (cudaError_t e = ensure_smem(kern, C::SMEM, configured); e != cudaSuccess) return e;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    if (!make_map(&ta_hi, g.A_hi, g.M, g.K, g.lda, AM / CL) || !make_map(&tb_hi, g.W_hi, g.N, g.K, g.ldw, BN))
+    if (!make_map(&ta_hi, g.A_hi, g.M, g.K, g.lda, BM) || !make_map(&tb_hi, g.W_hi, g.N, g.K, g.ldw, BN))
         return cudaErrorInvalidValue;
     if (SPLIT) {
-        if (!make_map(&ta_lo, g.A_lo, g.M, g.K, g.lda, AM / CL) || !make_map(&tb_lo, g.W_lo, g.N, g.K, g.ldw, BN))
+        if (!make_map(&ta_lo, g.A_lo, g.M, g.K, g.lda, BM) || !make_map(&tb_lo, g.W_lo, g.N, g.K, g.ldw, BN))
             return cudaErrorInvalidValue;
     } else {
         ta_lo = ta_hi;
         tb_lo = tb_hi;
     }
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int num_sms = sm_count();
     const long long total = (long long)((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM) * (g.split_k > 1 ? g.split_k : 1);
     dim3 grid((unsigned)(total < num_sms ? total : num_sms));
-    if (CL == 1) return launch_k(kern, grid, dim3(kThreads), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
-    // cluster launch (caller guarantees: one tile per CTA, tiles_n % CL == 0)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = grid; cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 2 : 1;
-    return cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, g);
+    return launch_k(kern, grid, dim3(kThreads), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
 }
 
+template <int BN, int EPI>
+cudaError_t launch_p(const GemmArgs& g, cudaStream_t st) {
+    return g.passes == 3 ? launch_one<BN, EPI, true>(g, st) : launch_one<BN, EPI, false>(g, st);
+}
+
+// Tile width.  Every tcgen05.mma streams the 128-row A tile from shared memory (~65 cycles whatever N is), so narrow
+// tiles are A-read bound: N = 96 caps the tensor pipe near 74 %, N >= 192 is compute-paced.  N = 576 (o_proj, down,
+// projection) and N = 960 (QKV) therefore run as 3 / 5 tiles of 192 columns instead of 6 / 10 of 96.
 template <int EPI>
 cudaError_t launch_epi(const GemmArgs& g, cudaStream_t st) {
-    const bool split = g.passes == 3;
     if (g.M <= 128 && g.N <= 4096) {
-        // decode-sized (one 128-row UMMA tile): narrow N tiles (x split-K) so 60-144 SMs stream the weights; clusters
-        // of 4 CTAs multicast the shared activation tile when the tile count allows it
-        static const bool no_cluster = getenv("MB_CLUSTER4") == nullptr;   // measured: multicast clusters are ~10% slower here (latency-bound, not A-traffic-bound), off by default
-        const int bn = g.N >= 2048 ? 32 : 16;
-        if constexpr (EPI == EPI_GENERIC) {
-            // wide-tile split-K: every tcgen05.mma streams the 128-row activation tile from shared memory (~65 cycles
-            // whatever N is), so the decode GEMMs are paced by the NUMBER of MMAs a CTA issues.  A wide N tile with
-            // K cut into 1-2 k-blocks per CTA needs 12-24 MMAs instead of 36-108; the partial sums are reduced by the
-            // consumer kernel (add_rmsnorm / decode attention) in a fixed order.
-            if (g.bn_hint == 64 && g.split_k > 1) return split ? launch_one<64, EPI, true, 1, BM, 2>(g, st) : launch_one<64, EPI, false, 1, BM, 2>(g, st);
-            if (g.bn_hint == 48 && g.split_k > 1) return split ? launch_one<48, EPI, true, 1, BM, 2>(g, st) : launch_one<48, EPI, false, 1, BM, 2>(g, st);
-        }
-        if (g.compact) {
-            // co-resident variants (two CTAs per SM): row groups of <= 64 rows fetch a 64-row activation tile
-            if (g.M <= 64) {
-                if (bn == 32) return split ? launch_one<32, EPI, true, 1, 64, 4>(g, st) : launch_one<32, EPI, false, 1, 64, 4>(g, st);
-                return split ? launch_one<16, EPI, true, 1, 64, 5>(g, st) : launch_one<16, EPI, false, 1, 64, 5>(g, st);
-            }
-            if (bn == 16) return split ? launch_one<16, EPI, true, 1, BM, 3>(g, st) : launch_one<16, EPI, false, 1, BM, 6>(g, st);
-        }
-        const int tiles_n = (g.N + bn - 1) / bn;
-        const bool cl4 = !no_cluster && tiles_n % 4 == 0 && tiles_n * (g.split_k > 1 ? g.split_k : 1) <= 148;
-        if (bn == 32) {
-            if (cl4) return split ? launch_one<32, EPI, true, 4>(g, st) : launch_one<32, EPI, false, 4>(g, st);
-            return split ? launch_one<32, EPI, true>(g, st) : launch_one<32, EPI, false>(g, st);
-        }
-        if (cl4) return split ? launch_one<16, EPI, true, 4>(g, st) : launch_one<16, EPI, false, 4>(g, st);
-        return split ? launch_one<16, EPI, true>(g, st) : launch_one<16, EPI, false>(g, st);
+        // decode-sized (one 128-row UMMA tile) shapes the weight-resident kernel did not take: narrow N tiles
+        // (x split-K) so that many SMs stream the weights
+        if (g.N >= 2048) return launch_p<32, EPI>(g, st);
+        return launch_p<16, EPI>(g, st);
     }
-    if (g.N % 256 == 0 && g.M >= 1024 && getenv("MB_NO_BN256") == nullptr)       // widest tile: A tile re-used over 256 columns
-        return split ? launch_one<256, EPI, true>(g, st) : launch_one<256, EPI, false>(g, st);
-    const bool bn96 = (g.N % 128 != 0) && (g.N % 96 == 0);
-    if (bn96) return split ? launch_one<96, EPI, true>(g, st) : launch_one<96, EPI, false>(g, st);
-    return split ? launch_one<128, EPI, true>(g, st) : launch_one<128, EPI, false>(g, st);
+    if (g.N % 256 == 0 && g.M >= 1024) return launch_p<256, EPI>(g, st);   // widest tile: A tile re-used over 256 columns
+    if (g.N % 192 == 0 && g.M >= 1024) return launch_p<192, EPI>(g, st);
+    if ((g.N % 128 != 0) && (g.N % 96 == 0)) return launch_p<96, EPI>(g, st);
+    return launch_p<128, EPI>(g, st);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -352,7 +278,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 cudaError_t launch_gemm_umma(const GemmArgs& g, int epi, cudaStream_t st, bool* handled) {
     *handled = false;
     if (g.M < 1 || g.K < BK || (g.K % 8) != 0 || (g.lda % 8) != 0 || (g.ldw % 8) != 0) return cudaSuccess;
-    if (g.split_k > 1 && (epi != EPI_GENERIC || !g.partial || (g.N & 1) || g.fix_counter)) return cudaErrorInvalidValue;
+    if (g.split_k > 1 && (epi != EPI_GENERIC || !g.partial || (g.N & 1))) return cudaErrorInvalidValue;
     if (!aligned16(g.A_hi) || !aligned16(g.W_hi) || (g.passes == 3 && (!aligned16(g.A_lo) || !aligned16(g.W_lo)))) return cudaSuccess;
     if (!encode_fn()) return cudaSuccess;
     cudaError_t e;

@@ -37,8 +37,6 @@ struct NormArgs {
     int res;                                         // NORM_LN_MERGE: input grid side (tokens are res x res, C/4 wide)
 };
 cudaError_t launch_norm(const NormArgs& a, int kind, cudaStream_t st);
-cudaError_t launch_window_attention(const float* qkv, const float* relbias, bf16* out_hi, bf16* out_lo, int n_clips,
-                                    int res, int C, int n_heads, int shift, cudaStream_t st);
 cudaError_t launch_window_attention_mma(const float* qkv, const float* relbias, bf16* out_hi, bf16* out_lo, int n_clips,
                                         int res, int C, int n_heads, int shift, cudaStream_t st);   // attn_mma.cu
 cudaError_t launch_tail_gather(const float* y, int n_clips, float* latent, bf16* col_hi, bf16* col_lo, cudaStream_t st);
@@ -50,12 +48,9 @@ cudaError_t launch_split_planes(const float* x, size_t n, bf16* hi, bf16* lo, cu
 
 // ---- lm.cu
 cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embed, int B, float* prefix, cudaStream_t st);
-cudaError_t launch_prefill_attention(const float* q, const void* kc, const void* vc, int kv_fmt, int B, int S, int t_max,
-                                     bf16* out_hi, bf16* out_lo, cudaStream_t st);
-// tensor-core (mma.sync, split operands) version of the same attention (attn_mma.cu)
+// causal prefill attention on the tensor cores (attn_mma.cu)
 cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_fmt, int B, int S,
                                          int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st);
-constexpr int kQkvSplitMax = 9;     // most split-K partials of the QKV projection the decode-attention prologue reduces
 struct DecodeAttnArgs {
     const float* q;                 // [B,576]
     const void* kc; const void* vc; // layer caches [B][3][t_max][64]
@@ -65,11 +60,8 @@ struct DecodeAttnArgs {
     const int* done;                   // optional [B]: rows that already emitted the stop token skip their K/V stream
     float* part_acc; float* part_ml;   // [B][9][nsplit][64], [B][9][nsplit][2]
     bf16* out_hi; bf16* out_lo;        // [B,576]
-    // optional: the QKV projection arrives as split-K partial sums [qkv_nsplit][B][960] (columns q | k | v, q/k head dims
-    // pair-interleaved).  The kernel then reduces its own 320 columns, applies RoPE at position ctx-1, appends the new
-    // K/V row to the caches (kc / vc are written) and uses q / k / v from shared memory; `q` is not read.
-    const float* qkv_part; int qkv_nsplit;
-    const float* rope_cur;             // [64] cos | sin of position ctx-1, maintained by step_advance_kernel
+    int pf_keys;                       // L2 prefetch of the CTA's immutable K/V history before the dependency wait:
+                                       // 0 = off, -1 = all of it, n > 0 = keys below n only
     TraceBuf* trace; unsigned trace_id;
 };
 cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st);
@@ -89,31 +81,8 @@ struct SampleArgs {
 cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, int M, const float* w, bf16* hi, bf16* lo,
                                cudaStream_t st, TraceBuf* trace = nullptr, unsigned trace_id = 0);
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st);
-// rope_cur (optional, [64]): cos[32] | sin[32] of the position the NEXT decode step writes (pos_base + new step), copied
-// from the tables so that the decode-attention prologue reads them from a fixed address
-cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, const float* rope_cos,
-                                const float* rope_sin, int pos_base, float* rope_cur, cudaStream_t st);
-
-// ---- decode_chain.cu: one persistent kernel for the GEMM / norm phases between two decode-attention kernels
-enum { CH_GEMM = 0, CH_ADDNORM = 1 };
-constexpr int kChainMaxOps = 6;
-constexpr int kChainMaps = 12;
-struct ChainOp {
-    int kind;
-    int map_a, map_b;                  // index of the hi-plane tensor map in ChainMaps (lo plane = index + 1)
-    int bn;                            // weight-tile width of a GEMM phase: 16 or 32 columns
-    int epi;                           // EPI_* of a GEMM phase without split-K
-    GemmArgs g;                        // M, N, K, split_k, partial and the epilogue operands
-    float* x; const float* partial; int n_partial; const float* w; bf16* hi; bf16* lo;   // CH_ADDNORM
-};
-struct ChainArgs {
-    int n_ops;
-    int split;                         // operand policy: 1 = hi/lo planes and 3 MMA passes
-    unsigned* bar;                     // [kChainMaxOps] grid-barrier counters of this launch (zeroed once per decode step)
-    ChainOp op[kChainMaxOps];
-};
-struct ChainMaps { CUtensorMap m[kChainMaps]; };
-cudaError_t build_chain_map(CUtensorMap* map, const bf16* ptr, int rows, int K, int ld, int box_rows);
-cudaError_t launch_decode_chain(const ChainMaps& maps, const ChainArgs& args, cudaStream_t st);
+cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st);
+// out[i] = embed[ids[i]] (fp32 rows of 576): lm.model.embed_tokens of the reference (wrapper.py:237)
+cudaError_t launch_embed_rows(const int* ids, int n, const float* embed, float* out, cudaStream_t st);
 
 }  // namespace mb

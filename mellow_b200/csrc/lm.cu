@@ -45,86 +45,6 @@ __global__ void __launch_bounds__(144) prefix_kernel(const float* __restrict__ r
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Causal prefill attention, fp32 on CUDA cores: one CTA = 64 query rows of one (batch, head); one thread per query.
-// K/V tiles of 32 keys are staged in shared memory (converted to fp32) and read as warp-wide broadcasts.
-template <typename T>
-__global__ void __launch_bounds__(64) prefill_attention_kernel(const float* __restrict__ q, const T* __restrict__ kc,
-                                                               const T* __restrict__ vc, int S, int t_max,
-                                                               bf16* __restrict__ out_hi, bf16* __restrict__ out_lo) {
-    constexpr int TK = 32;
-    __shared__ __align__(16) float sk[TK][kHeadDim];
-    __shared__ __align__(16) float sv[TK][kHeadDim];
-    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int tid = threadIdx.x;
-    const int r = qt * 64 + tid;
-    const bool active = r < S;
-    const int kvh = h / (kHeads / kKvHeads);
-    const T* kb = kc + ((size_t)b * kKvHeads + kvh) * t_max * kHeadDim;
-    const T* vb = vc + ((size_t)b * kKvHeads + kvh) * t_max * kHeadDim;
-    float qr[kHeadDim], acc[kHeadDim];
-    const float* qp = q + ((size_t)b * S + (active ? r : 0)) * kHidden + h * kHeadDim;
-    pdl_trigger();
-    pdl_wait();
-#pragma unroll
-    for (int d = 0; d < kHeadDim; d += 4) {
-        const float4 a = *reinterpret_cast<const float4*>(qp + d);
-        qr[d] = a.x; qr[d + 1] = a.y; qr[d + 2] = a.z; qr[d + 3] = a.w;
-        acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
-    }
-    float m_run = -INFINITY, l_run = 0.f;
-    const int kend = min(S, qt * 64 + 64);
-    for (int k0 = 0; k0 < kend; k0 += TK) {
-        __syncthreads();
-        for (int e = tid; e < TK * kHeadDim; e += 64) {
-            const int j = e >> 6, d = e & 63;
-            const int key = k0 + j;
-            sk[j][d] = key < S ? kv_load(kb + (size_t)key * kHeadDim + d) : 0.f;
-            sv[j][d] = key < S ? kv_load(vb + (size_t)key * kHeadDim + d) : 0.f;
-        }
-        __syncthreads();
-        float s[TK];
-        float mt = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < TK; ++j) {
-            float a = 0.f;
-#pragma unroll
-            for (int d = 0; d < kHeadDim; d += 4) {
-                const float4 k4 = *reinterpret_cast<const float4*>(&sk[j][d]);
-                a += qr[d] * k4.x; a += qr[d + 1] * k4.y; a += qr[d + 2] * k4.z; a += qr[d + 3] * k4.w;
-            }
-            a *= 0.125f;                                            // head_dim^-0.5
-            if (k0 + j > r) a = -INFINITY;                          // causal mask
-            s[j] = a;
-            mt = fmaxf(mt, a);
-        }
-        if (mt == -INFINITY) continue;                              // whole tile is in this row's future (uniform bar count kept above)
-        const float m_new = fmaxf(m_run, mt);
-        const float alpha = expf(m_run - m_new);
-        float lsum = 0.f;
-#pragma unroll
-        for (int j = 0; j < TK; ++j) { s[j] = expf(s[j] - m_new); lsum += s[j]; }
-        l_run = l_run * alpha + lsum;
-        m_run = m_new;
-#pragma unroll
-        for (int d = 0; d < kHeadDim; ++d) acc[d] *= alpha;
-#pragma unroll
-        for (int j = 0; j < TK; ++j) {
-            const float p = s[j];
-#pragma unroll
-            for (int d = 0; d < kHeadDim; d += 4) {
-                const float4 v4 = *reinterpret_cast<const float4*>(&sv[j][d]);
-                acc[d] += p * v4.x; acc[d + 1] += p * v4.y; acc[d + 2] += p * v4.z; acc[d + 3] += p * v4.w;
-            }
-        }
-    }
-    if (!active) return;
-    const float inv = 1.0f / l_run;
-    const size_t ob = ((size_t)b * S + r) * kHidden + h * kHeadDim;
-#pragma unroll
-    for (int d = 0; d < kHeadDim; d += 2) store_planes2(out_hi, out_lo, ob + d, acc[d] * inv, acc[d + 1] * inv);
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // Decode attention: one new query per row, ctx keys.  CTA = (split, kv head, row): the 3 query heads that share the
 // kv head (GQA, modeling_llama.py:187-196) are processed together so K/V are read once.  128 threads, 64-key tiles,
 // cp.async double buffering; partial (m, l, acc) per split are merged by decode_combine_kernel.
@@ -137,13 +57,10 @@ struct DecodeSmem {
     __align__(16) float sc[3][64];
     float alpha[3], m[3], l[3];
     float red[4][3][kHeadDim];
-    __align__(16) float qs[3 * kHeadDim];       // fused-QKV mode: roped queries of the 3 heads, new key / value row
-    __align__(16) float knew[kHeadDim];
-    __align__(16) float vnew[kHeadDim];
 };
 
-// Three CTAs per SM (<= 170 registers): the fused-QKV prologue pushed the fp32 variant to 207 registers = two CTAs per SM
-// without the bound.  Four CTAs of the 24-bit variant (128 registers, unpadded rows) were measured slower: 23.4 vs 18.7 us.
+// Three CTAs per SM (<= 170 registers).  Four CTAs of the 24-bit variant (128 registers, unpadded rows) were measured
+// slower in round 1: 23.4 vs 18.7 us.
 template <typename T>
 __global__ void __launch_bounds__(128, 3) decode_attention_kernel(const DecodeAttnArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -181,30 +98,24 @@ __global__ void __launch_bounds__(128, 3) decode_attention_kernel(const DecodeAt
     const bool early1 = a.tps > 1 && (t_begin + 2) * 64 < a.ctx_base;
     if (early0) load_tile(0, t_begin, a.ctx_base);
     if (early1) load_tile(1, t_begin + 1, a.ctx_base);
-    pdl_wait();
-    if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, TR_WAITED);
-    // fused-QKV mode: this row's q | k | v columns (320 = 80 float4) arrive as split-K partial sums.  Their addresses, and
-    // that of the RoPE row of the new position (rope_cur), do not depend on the step counter, so all these loads are in
-    // flight together with the counter / stop-flag loads: one L2 round trip instead of three.
-    const bool fused = a.qkv_part != nullptr;
-    float4 pv[kQkvSplitMax];
-    float2 c2 = make_float2(1.f, 1.f), s2 = make_float2(0.f, 0.f);
-    int qcol = 0;
-    if (fused && tid < 80) {
-        qcol = tid < 48 ? kvh * 192 + tid * 4
-                        : (tid < 64 ? kHidden + kvh * kHeadDim + (tid - 48) * 4
-                                    : kHidden + kKvHeads * kHeadDim + kvh * kHeadDim + (tid - 64) * 4);
-        const float* pp = a.qkv_part + (size_t)b * kQkvDim + qcol;
-        const size_t zs = (size_t)a.B * kQkvDim;
-#pragma unroll
-        for (int z = 0; z < kQkvSplitMax; ++z)
-            pv[z] = z < a.qkv_nsplit ? *reinterpret_cast<const float4*>(pp + z * zs) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tid < 64) {                                             // RoPE angle index of this thread's two pairs
-            const int i = (qcol & (kHeadDim - 1)) >> 1;
-            c2 = *reinterpret_cast<const float2*>(a.rope_cur + i);
-            s2 = *reinterpret_cast<const float2*>(a.rope_cur + 32 + i);
+    if (a.pf_keys != 0 && warp == 1) {
+        // Everything this CTA will stream except the row the running QKV GEMM writes (key ctx-1) is immutable during
+        // this step (the step counter was advanced by the previous step's last kernel, a full dependency back), so
+        // while the CTA waits for its predecessor it asks the L2 to fetch its K/V history: the wait lasts 5-8 us
+        // (the QKV GEMM body), during which HBM is otherwise idle.
+        const int hist = a.ctx_base + (a.d_step ? *reinterpret_cast<const volatile int*>(a.d_step) : 0) - 1;
+        int k_lo = (t_begin + (early0 ? 1 : 0) + (early1 ? 1 : 0)) * 64;
+        int k_hi = min(hist, (t_begin + a.tps) * 64);
+        if (a.pf_keys > 0) k_hi = min(k_hi, a.pf_keys);
+        const int bytes = (k_hi - k_lo) * ROWB;
+        for (int off = lane * 4096; off < bytes; off += 32 * 4096) {
+            const int sz = min(4096, bytes - off);
+            l2_prefetch(kb + (size_t)k_lo * ROWB + off, sz);
+            l2_prefetch(vb + (size_t)k_lo * ROWB + off, sz);
         }
     }
+    pdl_wait();
+    if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, TR_WAITED);
     const int step_now = a.d_step ? *a.d_step : 0;
     // a row that has emitted the stop token is finished (the reference cuts its text there,
     // wrapper.py:254); its later tokens are never read, so its K/V stream -- the dominant decode traffic -- is skipped.
@@ -213,61 +124,17 @@ __global__ void __launch_bounds__(128, 3) decode_attention_kernel(const DecodeAt
     const int ctx = a.ctx_base + step_now;
     const int ntiles = (ctx + 63) >> 6;
     const int t_end = min(ntiles, t_begin + a.tps);
-    // fused-QKV mode: key ctx-1 is produced by this kernel, so the cache is only read up to ctx-2
-    const int ctx_ld = fused ? ctx - 1 : ctx;
+    const int ctx_ld = ctx;
     if (!early0 && t_begin < t_end) load_tile(0, t_begin, ctx_ld);
     cp_async_commit();
     if (!early1 && t_begin + 1 < t_end) load_tile(1, t_begin + 1, ctx_ld);
     cp_async_commit();
-    const int t_new = (ctx - 1) >> 6;                               // tile that holds the new key
-    if (fused) {
-        if (tid < 80) {
-            float4 acc4 = pv[0];                                    // fixed summation order z = 0..nsplit-1
-#pragma unroll
-            for (int z = 1; z < kQkvSplitMax; ++z)
-                if (z < a.qkv_nsplit) { acc4.x += pv[z].x; acc4.y += pv[z].y; acc4.z += pv[z].z; acc4.w += pv[z].w; }
-            if (tid < 64) {                                         // RoPE on q and k: pairs (2i, 2i+1) rotate by angle i
-                const float x0 = acc4.x * c2.x - acc4.y * s2.x, x1 = acc4.y * c2.x + acc4.x * s2.x;
-                const float x2 = acc4.z * c2.y - acc4.w * s2.y, x3 = acc4.w * c2.y + acc4.z * s2.y;
-                acc4 = make_float4(x0, x1, x2, x3);
-            }
-            if (tid < 48) {
-                *reinterpret_cast<float4*>(&sm.qs[tid * 4]) = acc4;
-            } else {
-                const int dd = (tid < 64 ? tid - 48 : tid - 64) * 4;
-                float* dst = tid < 64 ? &sm.knew[dd] : &sm.vnew[dd];
-                const bool owner = t_new >= t_begin && t_new < t_begin + a.tps;   // the split that owns the new key appends it to the cache
-                unsigned char* crow = const_cast<unsigned char*>(tid < 64 ? kb : vb) + (size_t)(ctx - 1) * ROWB;
-                // knew / vnew hold what later steps will read back from the cache (rounded to the cache format)
-                if constexpr (F24) {
-                    const uint32_t u0 = f24_bits(acc4.x), u1 = f24_bits(acc4.y), u2 = f24_bits(acc4.z), u3 = f24_bits(acc4.w);
-                    dst[0] = __uint_as_float(u0); dst[1] = __uint_as_float(u1); dst[2] = __uint_as_float(u2); dst[3] = __uint_as_float(u3);
-                    if (owner) {
-                        *reinterpret_cast<uint2*>(crow + dd * 2) = make_uint2((u0 >> 16) | (u1 & 0xFFFF0000u), (u2 >> 16) | (u3 & 0xFFFF0000u));
-                        *reinterpret_cast<uint32_t*>(crow + 128 + dd) =
-                            ((u0 >> 8) & 0xFFu) | (u1 & 0xFF00u) | ((u2 << 8) & 0xFF0000u) | ((u3 << 16) & 0xFF000000u);
-                    }
-                } else {
-                    T r0, r1, r2, r3;
-                    kv_cast(acc4.x, r0); kv_cast(acc4.y, r1); kv_cast(acc4.z, r2); kv_cast(acc4.w, r3);
-                    dst[0] = kv_load(&r0); dst[1] = kv_load(&r1); dst[2] = kv_load(&r2); dst[3] = kv_load(&r3);
-                    if (owner) {
-                        T* cb = reinterpret_cast<T*>(crow) + dd;
-                        cb[0] = r0; cb[1] = r1; cb[2] = r2; cb[3] = r3;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, 4);       // q / k / v of this step ready
-    }
-
     // score role: thread = (key j, half); each half owns every other 16 B chunk of the key row.  The matching
     // slices of the three query heads live in registers.
     const int sj = tid >> 1, shalf = tid & 1;
     float qreg[3][kHeadDim / 2];
     {
-        const float* qb = fused ? sm.qs : a.q + (size_t)b * kHidden + (kvh * 3) * kHeadDim;
+        const float* qb = a.q + (size_t)b * kHidden + (kvh * 3) * kHeadDim;
 #pragma unroll
         for (int h = 0; h < 3; ++h)
 #pragma unroll
@@ -288,35 +155,20 @@ __global__ void __launch_bounds__(128, 3) decode_attention_kernel(const DecodeAt
         const int buf = (t - t_begin) & 1;
         if (t + 1 < t_end) cp_async_wait<1>(); else cp_async_wait<0>();
         __syncthreads();
-        if (fused && t == t_new) {                                   // uniform: place the new key / value row into the tile
-            const int j = (ctx - 1) & 63;
-            const int d = tid & (kHeadDim - 1);
-            unsigned char* row = tid < kHeadDim ? sm.k[buf][j] : sm.v[buf][j];
-            const float val = tid < kHeadDim ? sm.knew[d] : sm.vnew[d];
-            if constexpr (F24) {
-                const uint32_t u = __float_as_uint(val);             // already rounded to 24 bits
-                reinterpret_cast<unsigned short*>(row)[d] = (unsigned short)(u >> 16);
-                row[128 + d] = (unsigned char)(u >> 8);
-            } else {
-                kv_cast(val, reinterpret_cast<T*>(row)[d]);
-            }
-            __syncthreads();
-        }
         {
             float p0 = 0.f, p1 = 0.f, p2 = 0.f;
 #pragma unroll
             for (int i = 0; i < NCH / 2; ++i) {
                 if constexpr (F24) {
-                    // 8 values: one 16 B read of upper halves, one 8 B read of mantissa bytes
+                    // 8 values: one 16 B read of upper halves, one 8 B read of mantissa bytes; one PRMT per value
                     const unsigned char* rowp = sm.k[buf][sj];
                     const uint4 hv = *reinterpret_cast<const uint4*>(rowp + (2 * i + shalf) * 16);
                     const uint2 lv = *reinterpret_cast<const uint2*>(rowp + 128 + (2 * i + shalf) * 8);
                     const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
                     for (int p = 0; p < 4; ++p) {
-                        const uint32_t lb = p < 2 ? lv.x >> (16 * p) : lv.y >> (16 * (p - 2));
-                        const float k0 = __uint_as_float((hw[p] << 16) | ((lb & 0xFFu) << 8));
-                        const float k1 = __uint_as_float((hw[p] & 0xFFFF0000u) | (lb & 0xFF00u));
+                        const float k0 = f24_unpack_even(hw[p], p < 2 ? lv.x : lv.y, p & 1);
+                        const float k1 = f24_unpack_odd(hw[p], p < 2 ? lv.x : lv.y, p & 1);
                         p0 += qreg[0][i * E + 2 * p] * k0; p1 += qreg[1][i * E + 2 * p] * k0; p2 += qreg[2][i * E + 2 * p] * k0;
                         p0 += qreg[0][i * E + 2 * p + 1] * k1; p1 += qreg[1][i * E + 2 * p + 1] * k1; p2 += qreg[2][i * E + 2 * p + 1] * k1;
                     }
@@ -372,8 +224,8 @@ __global__ void __launch_bounds__(128, 3) decode_attention_kernel(const DecodeAt
                         const unsigned char* rowp = sm.v[buf][j + u];
                         const uint32_t hw = *reinterpret_cast<const uint32_t*>(rowp + dp * 2);
                         const uint32_t lb = *reinterpret_cast<const unsigned short*>(rowp + 128 + dp);
-                        v0 = __uint_as_float((hw << 16) | ((lb & 0xFFu) << 8));
-                        v1 = __uint_as_float((hw & 0xFFFF0000u) | (lb & 0xFF00u));
+                        v0 = f24_unpack_even(hw, lb, 0);
+                        v1 = f24_unpack_odd(hw, lb, 0);
                     } else {
                         const T* vp = reinterpret_cast<const T*>(sm.v[buf][j + u]);
                         v0 = kv_load(vp + dp); v1 = kv_load(vp + dp + 1);
@@ -488,8 +340,9 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
         if (lane == 0) {
             if (bi < 0 || bi >= kVocab) bi = 0;                    // all-NaN row: never index the embedding table out of range
             a.tokens_out[(size_t)b * a.max_len + step] = bi;
-            if (bi == a.eos_id) a.done[b] = 1;
-            stoken = a.forced ? a.forced[(size_t)b * a.max_len + step] : bi;
+            const int fed = a.forced ? a.forced[(size_t)b * a.max_len + step] : bi;   // what the row continues with
+            if (fed == a.eos_id) a.done[b] = 1;
+            stoken = fed;
         }
     }
     __syncthreads();
@@ -501,51 +354,9 @@ __global__ void __launch_bounds__(1024) sample_kernel(const SampleArgs a) {
 
 // Decode-path fusion: x[row] += sum_s partial[s][row] (split-K partial sums of the preceding o_proj / down_proj GEMM,
 // fixed summation order => deterministic), then RMSNorm(x[row]) -> bf16 hi/lo planes for the next GEMM.
-// n_partial == 0 gives a plain RMSNorm.  One warp per row.
-template <int S>
-__global__ void __launch_bounds__(128) add_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ partial,
-                                                          int M, const float* __restrict__ w,
-                                                          bf16* __restrict__ hi, bf16* __restrict__ lo,
-                                                          TraceBuf* trace, unsigned trace_id) {
-    constexpr int PER = kHidden / 32;
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * 4 + (threadIdx.x >> 5);
-    unsigned trec = kTraceNone;
-    if (threadIdx.x == 0) trec = trace_open(trace, trace_id);
-    if (row >= M) return;
-    float v[PER], p[S > 0 ? S : 1][PER], wv[PER];
-    float* xr = x + (size_t)row * kHidden;
-    pdl_trigger();
-#pragma unroll
-    for (int j = 0; j < PER; ++j) wv[j] = w[lane + 32 * j];        // weights do not depend on the predecessor
-    pdl_wait();
-    if (threadIdx.x == 0 && first_cta()) trace_put(trace, trec, trace_id, TR_WAITED);
-#pragma unroll
-    for (int j = 0; j < PER; ++j) v[j] = xr[lane + 32 * j];
-#pragma unroll
-    for (int s = 0; s < S; ++s)                                    // all loads in flight before the first add
-#pragma unroll
-        for (int j = 0; j < PER; ++j) p[s][j] = partial[((size_t)s * M + row) * kHidden + lane + 32 * j];
-#pragma unroll
-    for (int s = 0; s < S; ++s)
-#pragma unroll
-        for (int j = 0; j < PER; ++j) v[j] += p[s][j];
-    float sq = 0.f;
-#pragma unroll
-    for (int j = 0; j < PER; ++j) sq += v[j] * v[j];
-    const float rstd = rsqrtf(warp_sum(sq) * (1.0f / kHidden) + 1e-5f);
-#pragma unroll
-    for (int j = 0; j < PER; ++j) {
-        const int i = lane + 32 * j;
-        if (S > 0) xr[i] = v[j];
-        store_planes1(hi, lo, (size_t)row * kHidden + i, wv[j] * (v[j] * rstd));
-    }
-    if (threadIdx.x == 0) trace_close(trace, trec, trace_id);
-}
-
-// Same operation with one CTA per row and 16-byte accesses (144 threads x float4 = 576 columns): up to 12 split-K
-// partials are all in flight before the first add, the sum order is fixed (s = 0..S-1), and the 128 rows of a decode
-// step spread over 128 SMs instead of 32.
+// n_partial == 0 gives a plain RMSNorm.
+// One CTA per row and 16-byte accesses (144 threads x float4 = 576 columns): up to 8 split-K partials are all in flight
+// before the first add, the sum order is fixed (s = 0..S-1), and the 128 rows of a decode step spread over 128 SMs.
 template <int S>
 __global__ void __launch_bounds__(160) add_rmsnorm_row_kernel(float* __restrict__ x, const float* __restrict__ partial,
                                                               int M, const float* __restrict__ w,
@@ -586,8 +397,7 @@ __global__ void __launch_bounds__(160) add_rmsnorm_row_kernel(float* __restrict_
 }
 
 // step += 1; records the first step count at which every row has emitted eos (wrapper.py:247-249)
-__global__ void step_advance_kernel(int* d_step, const int* done, int B, int* d_stop_step, const float* rope_cos,
-                                    const float* rope_sin, int pos_base, float* rope_cur) {
+__global__ void step_advance_kernel(int* d_step, const int* done, int B, int* d_stop_step) {
     __shared__ int all;
     pdl_trigger();
     pdl_wait();
@@ -596,18 +406,29 @@ __global__ void step_advance_kernel(int* d_step, const int* done, int B, int* d_
     for (int b = threadIdx.x; b < B; b += blockDim.x)
         if (!done[b]) all = 0;
     __syncthreads();
-    const int s = *d_step + 1;                                     // every thread reads the old value before thread 0 writes
-    if (rope_cur && threadIdx.x < 64 && pos_base + s < kMaxPos)
-        rope_cur[threadIdx.x] = threadIdx.x < 32 ? rope_cos[(pos_base + s) * 32 + threadIdx.x]
-                                                 : rope_sin[(pos_base + s) * 32 + threadIdx.x - 32];
-    __syncthreads();
     if (threadIdx.x == 0) {
+        const int s = *d_step + 1;
         *d_step = s;
         if (all && *d_stop_step < 0) *d_stop_step = s;
     }
 }
 
+// lm.model.embed_tokens (wrapper.py:237): one CTA per id, 144 x float4
+__global__ void __launch_bounds__(144) embed_rows_kernel(const int* __restrict__ ids, const float* __restrict__ embed,
+                                                         float* __restrict__ out) {
+    pdl_trigger();
+    pdl_wait();
+    int id = ids[blockIdx.x];
+    id = id < 0 ? 0 : (id >= kVocab ? kVocab - 1 : id);
+    reinterpret_cast<float4*>(out + (size_t)blockIdx.x * kHidden)[threadIdx.x] =
+        reinterpret_cast<const float4*>(embed + (size_t)id * kHidden)[threadIdx.x];
+}
+
 }  // namespace
+
+cudaError_t launch_embed_rows(const int* ids, int n, const float* embed, float* out, cudaStream_t st) {
+    return launch_k(embed_rows_kernel, dim3(n), dim3(144), 0, st, ids, embed, out);
+}
 
 cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embed, int B, float* prefix,
                           cudaStream_t st) {
@@ -615,30 +436,12 @@ cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embe
     return launch_k(prefix_kernel, grid, dim3(144), 0, st, rows33, ids, embed, B, prefix);
 }
 
-cudaError_t launch_prefill_attention(const float* q, const void* kc, const void* vc, int kv_fmt, int B, int S,
-                                     int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st) {
-    dim3 grid((S + 63) / 64, kHeads, B);
-    if (kv_fmt == kKvF24) return cudaErrorNotSupported;            // the CUDA-core A/B kernel reads element-wise formats only
-    if (kv_fmt)
-        return launch_k(prefill_attention_kernel<bf16>, grid, dim3(64), 0, st, q, (const bf16*)kc, (const bf16*)vc, S, t_max, out_hi, out_lo);
-    return launch_k(prefill_attention_kernel<float>, grid, dim3(64), 0, st, q, (const float*)kc, (const float*)vc, S, t_max, out_hi, out_lo);
-}
-
 cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
     dim3 grid(a.nsplit, kKvHeads, a.B);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(decode_attention_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)sizeof(DecodeSmem<float>));
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(decode_attention_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(DecodeSmem<bf16>));
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(decode_attention_kernel<kv24>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(DecodeSmem<kv24>));
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
+    static bool c0[kMaxDevices] = {}, c1[kMaxDevices] = {}, c2[kMaxDevices] = {};
+    if (cudaError_t e = ensure_smem(decode_attention_kernel<float>, sizeof(DecodeSmem<float>), c0); e != cudaSuccess) return e;
+    if (cudaError_t e = ensure_smem(decode_attention_kernel<bf16>, sizeof(DecodeSmem<bf16>), c1); e != cudaSuccess) return e;
+    if (cudaError_t e = ensure_smem(decode_attention_kernel<kv24>, sizeof(DecodeSmem<kv24>), c2); e != cudaSuccess) return e;
     cudaError_t e = a.kv_fmt == kKvBf16 ? launch_k(decode_attention_kernel<bf16>, grid, dim3(128), sizeof(DecodeSmem<bf16>), st, a)
                   : a.kv_fmt == kKvF24 ? launch_k(decode_attention_kernel<kv24>, grid, dim3(128), sizeof(DecodeSmem<kv24>), st, a)
                                        : launch_k(decode_attention_kernel<float>, grid, dim3(128), sizeof(DecodeSmem<float>), st, a);
@@ -648,38 +451,23 @@ cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
 
 cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, int M, const float* w, bf16* hi, bf16* lo,
                                cudaStream_t st, TraceBuf* trace, unsigned trace_id) {
-    static const bool v1 = getenv("MB_NORM_V1") != nullptr;       // warp-per-row version, kept for A/B measurements
-    if (!v1 || n_partial > 4) {
 #define MB_ROWNORM(S) launch_k(add_rmsnorm_row_kernel<S>, dim3(M), dim3(160), 0, st, x, partial, M, w, hi, lo, trace, trace_id)
-        switch (n_partial) {
-            case 0: return MB_ROWNORM(0);
-            case 3: return MB_ROWNORM(3);
-            case 4: return MB_ROWNORM(4);
-            case 6: return MB_ROWNORM(6);
-            case 8: return MB_ROWNORM(8);
-            case 9: return MB_ROWNORM(9);
-            case 12: return MB_ROWNORM(12);
-            default: return cudaErrorInvalidValue;
-        }
-#undef MB_ROWNORM
-    }
-    const int grid = (M + 3) / 4;
     switch (n_partial) {
-        case 0: return launch_k(add_rmsnorm_kernel<0>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo, trace, trace_id);
-        case 3: return launch_k(add_rmsnorm_kernel<3>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo, trace, trace_id);
-        case 4: return launch_k(add_rmsnorm_kernel<4>, dim3(grid), dim3(128), 0, st, x, partial, M, w, hi, lo, trace, trace_id);
+        case 0: return MB_ROWNORM(0);
+        case 3: return MB_ROWNORM(3);
+        case 4: return MB_ROWNORM(4);
+        case 8: return MB_ROWNORM(8);
         default: return cudaErrorInvalidValue;
     }
+#undef MB_ROWNORM
 }
 
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st) {
     return launch_k(sample_kernel, dim3(a.B), dim3(1024), 0, st, a);
 }
 
-cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, const float* rope_cos,
-                                const float* rope_sin, int pos_base, float* rope_cur, cudaStream_t st) {
-    return launch_k(step_advance_kernel, dim3(1), dim3(128), 0, st, d_step, done, B, d_stop_step, rope_cos, rope_sin,
-                    pos_base, rope_cur);
+cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st) {
+    return launch_k(step_advance_kernel, dim3(1), dim3(128), 0, st, d_step, done, B, d_stop_step);
 }
 
 }  // namespace mb

@@ -23,6 +23,29 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+class _LogitsOut:
+    """What ``lm(inputs_embeds=...)`` returns: ``.logits`` of shape (B, 1, V) -- the last position only."""
+    def __init__(self, logits):
+        self.logits = logits
+
+
+class _LmShim:
+    """Attribute-compatible stand-in for ``model.caption_decoder.lm`` (a transformers ``LlamaForCausalLM`` in the
+    reference): callable with ``inputs_embeds=`` and exposing ``.model.embed_tokens`` (wrapper.py:217,237)."""
+    def __init__(self, engine):
+        self._engine = engine
+        self.model = self
+        self.lm = self                                   # so that `engine.caption_decoder.lm` resolves to this object
+
+    def __call__(self, inputs_embeds=None, **unused):
+        if inputs_embeds is None:
+            raise ValueError("only lm(inputs_embeds=...) is supported, like the reference call at wrapper.py:217")
+        return _LogitsOut(self._engine.lm_forward_last(inputs_embeds)[:, None, :])
+
+    def embed_tokens(self, ids):
+        return self._engine.embed_tokens(ids)
+
+
 class Engine:
     def __init__(self, state_dict=None, device=0, max_batch=8, max_new_tokens=300, policy="split", arena=None,
                  verify=True):
@@ -36,6 +59,7 @@ class Engine:
         if not self.handle:
             raise MellowNativeError("mb_create failed: " + self.lib.mb_last_error(None).decode())
         self.arena = None
+        self.caption_decoder = _LmShim(self)             # reference seam: model.caption_decoder.lm(...)
         if arena is not None:
             self.bind_arena(arena)
         elif state_dict is not None:
@@ -65,6 +89,10 @@ class Engine:
     def _dev(self, t, dtype):
         return t.to(device=self.device, dtype=dtype).contiguous()
 
+    def eval(self):
+        """The reference calls ``model.eval()`` (wrapper.py:49,205); inference is the only mode here."""
+        return self
+
     def close(self):
         if getattr(self, "handle", None):
             self.lib.mb_destroy(self.handle)
@@ -80,16 +108,10 @@ class Engine:
     def kernel_launches(self):
         return self.lib.mb_kernel_launches(self.handle)
 
-    def set_gemm_engine(self, engine):
-        self._ck(self.lib.mb_set_gemm_engine(self.handle, int(engine)))
-
-    def set_decode_groups(self, groups):
-        """Row groups of the decode step (0 = automatic); a scheduling choice only, token ids do not depend on it."""
-        self._ck(self.lib.mb_set_decode_groups(self.handle, int(groups)))
-
-    def set_decode_qkv_split(self, nsplit):
-        """0: QKV GEMM with RoPE / KV write in its epilogue (default); 3 or 9: split-K slices finished inside decode attention."""
-        self._ck(self.lib.mb_set_decode_qkv_split(self.handle, int(nsplit)))
+    def set_option(self, name, value):
+        """Handle-scoped options of ``mb_set_option`` (include/mellow_b200.h): 'graph', 'decode_unfused',
+        'skip_finished', 'kv_prefetch', 'gemm_engine' (lab builds)."""
+        self._ck(self.lib.mb_set_option(self.handle, name.encode(), int(value)))
 
     def workspace_bytes(self):
         return self.lib.mb_workspace_bytes(self.handle)
@@ -172,6 +194,23 @@ class Engine:
         out = torch.empty(batch, S.VOCAB, device=self.device) if want_logits else None
         self._ck(self.lib.mb_prefill(self.handle, batch, _ptr(out), self._stream()))
         return out
+
+    def lm_forward_last(self, inputs_embeds):
+        """``model.caption_decoder.lm(inputs_embeds=x).logits[:, -1]`` of the reference (wrapper.py:217-218): one
+        cache-less causal forward over (B,S,576) embeddings -> last-position logits (B,49152)."""
+        x = self._dev(inputs_embeds, torch.float32)
+        b, s_len, hid = x.shape
+        assert hid == S.HIDDEN
+        out = torch.empty(b, S.VOCAB, device=self.device)
+        self._ck(self.lib.mb_lm_forward_last(self.handle, _ptr(x), b, s_len, _ptr(out), self._stream()))
+        return out
+
+    def embed_tokens(self, ids):
+        """``lm.model.embed_tokens(ids)`` (wrapper.py:237): integer ids of any shape -> (..., 576) float32."""
+        flat = self._dev(ids, torch.int32).reshape(-1)
+        out = torch.empty(flat.numel(), S.HIDDEN, device=self.device)
+        self._ck(self.lib.mb_embed_tokens(self.handle, _ptr(flat), flat.numel(), _ptr(out), self._stream()))
+        return out.view(*ids.shape, S.HIDDEN)
 
     def decode(self, batch, max_len, temperature=1.0, top_p=0.8, eos_id=0, dump_logits=False, forced_tokens=None):
         toks = torch.empty(batch, max_len, dtype=torch.int32, device=self.device)

@@ -16,7 +16,8 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libmellow_b200.so")
 HASH_PATH = os.path.join(CSRC, "libmellow_b200.srchash")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-SOURCES = ["api.cu", "frontend.cu", "encoder.cu", "lm.cu", "attn_mma.cu", "gemm_mma.cu", "gemm_umma.cu", "gemm_skinny.cu", "decode_chain.cu", "audio.cu"]
+SOURCES = ["api.cu", "frontend.cu", "encoder.cu", "lm.cu", "attn_mma.cu", "gemm_umma.cu", "gemm_skinny.cu", "audio.cu"]
+LAB_SOURCES = ["gemm_mma.cu"]          # mma.sync cross-check engine: only with MB_BUILD_LAB=1 (-DMB_LAB)
 HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", "umma.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -29,15 +30,28 @@ def _nvcc():
     raise RuntimeError("nvcc not found")
 
 
+def lab_build():
+    """MB_BUILD_LAB=1: also compile the mma.sync cross-check engine (``-DMB_LAB``); the product library ships without it."""
+    return bool(os.environ.get("MB_BUILD_LAB"))
+
+
+def _sources():
+    return SOURCES + (LAB_SOURCES if lab_build() else [])
+
+
+def _flags():
+    return NVCC_FLAGS + (["-DMB_LAB"] if lab_build() else [])
+
+
 def source_hash():
     h = hashlib.sha256()
-    for name in SOURCES + HEADERS:
+    for name in _sources() + HEADERS:
         with open(os.path.join(CSRC, name), "rb") as f:
             h.update(name.encode())
             h.update(f.read())
     with open(os.path.join(INCLUDE, "mellow_b200.h"), "rb") as f:
         h.update(f.read())
-    h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(" ".join(_flags()).encode())
     return h.hexdigest()
 
 
@@ -58,7 +72,7 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + _flags() + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
@@ -66,9 +80,9 @@ def build(force=False, verbose=False):
             sys.stderr.write(r.stdout + r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart"]
+    with ThreadPoolExecutor(max_workers=min(8, len(_sources()))) as ex:
+        objs = list(ex.map(compile_one, _sources()))
+    cmd = [nvcc, "-shared", "-o", LIB_PATH] + objs + ["-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
@@ -91,9 +105,7 @@ SYMBOLS = [
     ("mb_last_error", ctypes.c_char_p, [_vp]),
     ("mb_bind_weights", _i, [_vp, _vp, _ll]),
     ("mb_workspace_bytes", _ll, [_vp]),
-    ("mb_set_gemm_engine", _i, [_vp, _i]),
-    ("mb_set_decode_groups", _i, [_vp, _i]),
-    ("mb_set_decode_qkv_split", _i, [_vp, _i]),
+    ("mb_set_option", _i, [_vp, ctypes.c_char_p, _i]),
     ("mb_set_trace", _i, [_vp, _vp]),
     ("mb_kernel_launches", _ll, [_vp]),
     ("mb_frontend", _i, [_vp, _vp, _i, _vp, _vp, _vp]),
@@ -103,6 +115,8 @@ SYMBOLS = [
     ("mb_prefix", _i, [_vp, _vp, _i, _vp, _vp]),
     ("mb_set_prefix", _i, [_vp, _vp, _i, _vp]),
     ("mb_prefill", _i, [_vp, _i, _vp, _vp]),
+    ("mb_lm_forward_last", _i, [_vp, _vp, _i, _i, _vp, _vp]),
+    ("mb_embed_tokens", _i, [_vp, _vp, _i, _vp, _vp]),
     ("mb_decode", _i, [_vp, _i, _i, _f, _f, _i, _vp, ctypes.POINTER(_i), _vp, _vp, _vp]),
     ("mb_generate", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, ctypes.POINTER(_i), _vp]),
     ("mb_generate_host", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _f, _i, _vp, ctypes.POINTER(_i), _vp]),
@@ -123,9 +137,14 @@ def load(auto_build=True):
     if auto_build and is_stale():
         try:
             build()
-        except Exception as exc:                                  # stale-but-present library is still usable
+        except Exception as exc:
+            # A library whose recorded source hash differs from the sources next to it may have another ABI; loading
+            # it could corrupt memory silently.  Opt in explicitly (MB_ALLOW_STALE_LIB=1) to use it anyway.
             if not os.path.isfile(LIB_PATH):
                 raise RuntimeError("libmellow_b200.so is missing and could not be built; there is no fallback path") from exc
+            if not os.environ.get("MB_ALLOW_STALE_LIB"):
+                raise RuntimeError("libmellow_b200.so is stale (sources changed) and the rebuild failed; fix the build "
+                                   "or set MB_ALLOW_STALE_LIB=1 to load the old library") from exc
     if not os.path.isfile(LIB_PATH):
         raise RuntimeError(f"{LIB_PATH} is missing; run `python -c 'import __graft_entry__ as g; g.build()'`")
     lib = ctypes.CDLL(LIB_PATH)

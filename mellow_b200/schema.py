@@ -43,6 +43,7 @@ HEAD_DIM = 64
 INTER = 1536
 RMS_EPS = 1e-5
 ROPE_THETA = 100000.0
+MAX_POSITIONS = 8192         # max_position_embeddings; rope table rows of the library (csrc/common.cuh kMaxPos)
 LN_EPS = 1e-5
 BN_EPS = 1e-5
 

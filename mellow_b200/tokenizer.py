@@ -1,8 +1,9 @@
 """Tokenizer plumbing of the drop-in wrapper (reference mellow/wrapper.py:84-85,181-195,254).
 
 The reference uses the SmolLM2 BPE tokenizer from the Hugging Face hub.  With a local copy (directory given by
-``tokenizer=...`` or ``$MELLOW_TOKENIZER``) the same tokenizer is used.  Offline without one, ``ByteStandInTokenizer``
-keeps the pipeline runnable for synthetic-weight tests; it is NOT the SmolLM2 vocabulary and its text is meaningless.
+``tokenizer=...`` or ``$MELLOW_TOKENIZER``) the same tokenizer is used.  ``ByteStandInTokenizer`` keeps the pipeline
+runnable for synthetic-weight tests and is only used when asked for (``tokenizer='stand-in'``, the default of
+``checkpoint='synthetic'``); it is NOT the SmolLM2 vocabulary and its text is meaningless.
 """
 import os
 
@@ -45,17 +46,26 @@ class ByteStandInTokenizer:
         return ids + [17] * (length - len(ids))
 
 
+STAND_IN = "stand-in"
+
+
 def load_tokenizer(name_or_path, local=None):
+    """``local`` / ``$MELLOW_TOKENIZER``: a local SmolLM2 tokenizer directory, or the string ``'stand-in'`` to ask for
+    ``ByteStandInTokenizer`` explicitly (synthetic-weight runs).  Anything else goes to the hub like the reference
+    (wrapper.py:84) and a failure there RAISES: decoding a real checkpoint through the stand-in vocabulary would return
+    meaningless text without an error."""
     path = local or os.environ.get("MELLOW_TOKENIZER")
-    try:
-        from transformers import AutoTokenizer
-        tok = AutoTokenizer.from_pretrained(path or name_or_path)
-        tok.add_special_tokens({"pad_token": "!"})           # wrapper.py:85
-        return tok
-    except Exception:
-        if path:
-            raise
+    if path == STAND_IN:
         return ByteStandInTokenizer()
+    from transformers import AutoTokenizer
+    try:
+        tok = AutoTokenizer.from_pretrained(path or name_or_path)
+    except Exception as exc:
+        raise RuntimeError(
+            f"cannot load the tokenizer {path or name_or_path!r} ({type(exc).__name__}: {exc}); pass tokenizer=<local "
+            f"SmolLM2 tokenizer directory> (or $MELLOW_TOKENIZER), or tokenizer='{STAND_IN}' for synthetic-weight runs") from exc
+    tok.add_special_tokens({"pad_token": "!"})               # wrapper.py:85
+    return tok
 
 
 def tokenize_prompts(tokenizer, prompts, length):

@@ -7,7 +7,7 @@ module produces the bytes of every entry:
     SmolLM2 q|k|v stacked with the q/k head dims pair-interleaved (rotate-half partners adjacent), gate/up rows
     interleaved, the (2,3) TSCAM conv flattened to a [527, 4608] matrix, c2l K-padded 527 -> 544;
   * fp32 side tables: norm gains/biases, the BatchNorm folded to scale/shift, the 64x64 relative-position bias per
-    head (table gathered through the checkpoint's own index buffer), RoPE cos/sin for 1024 positions, FFT twiddles.
+    head (table gathered through the checkpoint's own index buffer), RoPE cos/sin for 8192 positions, FFT twiddles.
 It also verifies the assumptions the kernels bake in (``check_*``) and raises if a checkpoint violates them.
 """
 import math
@@ -20,7 +20,7 @@ from . import schema as S
 
 HT = "audio_encoder.base.htsat."
 LMK = "caption_decoder.lm."
-MAX_POS = 1024
+MAX_POS = 8192                     # rope table rows of the library (common.cuh kMaxPos)
 
 
 def strip_module_prefix(sd):

@@ -1,0 +1,173 @@
+"""GPU parity at the lengths BASELINE.json names (max_len = 300, ctx 389..688; configs[0] on the reference's own wavs),
+against fixtures produced by the UNMODIFIED reference classes under the reference's cache-less loop
+(tests/golden/make_golden_long.py).
+
+What "identical greedy ids" can mean over 300 steps: the reference's own decision margin (top-1 minus top-2 logit)
+drops to 2e-4 on some steps of these synthetic checkpoints, far below what fp32 re-association alone moves a logit
+(the KV-cached loop here vs the reference's cache-less loop; a different BLAS thread count on the CPU does the same).
+The gate is therefore stated against the tolerance: LOGIT_TOL = 1e-2 (the north-star "per-step logits within a stated
+tolerance"), and
+  * teacher-forced on the reference's ids, EVERY step's top-8 and probe logits are within LOGIT_TOL and the model's
+    own argmax equals the reference id wherever the reference margin is >= MARGIN_GATE = 2 * LOGIT_TOL;
+  * free-running, every row's ids are identical up to its first step whose reference margin is below MARGIN_GATE
+    (all 300 steps when there is none).
+"""
+import importlib.util
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+LOGIT_TOL = 1e-2
+MARGIN_GATE = 2 * LOGIT_TOL
+
+
+def _maker():
+    spec = importlib.util.spec_from_file_location("make_golden_long", os.path.join(GOLD, "make_golden_long.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)                     # imports oracle.reference_model lazily-safe: no reference access at import
+    return mod
+
+
+def _golden(name):
+    path = os.path.join(GOLD, f"ref_{name}.npz")
+    if not os.path.isfile(path):
+        pytest.skip(f"{path} not generated")
+    return dict(np.load(path))
+
+
+@pytest.fixture(scope="module")
+def arenas(engine):
+    """checkpoint seed -> device arena (seed 1234 is the session engine's)."""
+    from mellow_b200 import synth
+    cache = {1234: engine.arena}
+
+    def get(seed):
+        if seed not in cache:
+            cache[seed] = engine.pack_arena(synth.synthetic_state_dict(seed)).to(engine.device)
+        return cache[seed]
+    return get
+
+
+def _first_thin_step(margins_row):
+    thin = np.nonzero(margins_row < MARGIN_GATE)[0]
+    return int(thin[0]) if thin.size else margins_row.shape[0]
+
+
+@pytest.mark.parametrize("policy", ["split", "split24"])
+@pytest.mark.parametrize("name", ["long1234", "rows1234", "rows77"])
+def test_300_steps_against_the_reference_loop(name, policy, arenas):
+    from mellow_b200.engine import Engine
+    g = _golden(name)
+    seed, w1, w2, ids, steps = _maker().set_inputs(name)
+    assert np.array_equal(ids.numpy(), g["input_ids"])
+    ref = torch.from_numpy(g["tokens"]).to(torch.int32)                      # (B, 300)
+    B = ref.shape[0]
+    assert ref.shape[1] == steps == 300
+    margins = (g["top8_vals"][..., 0] - g["top8_vals"][..., 1]).T            # (B, steps)
+    eng = Engine(None, device=0, max_batch=B, max_new_tokens=steps, policy=policy, arena=arenas(seed))
+    try:
+        # free-running greedy loop (CUDA graph, KV cache) vs the reference's cache-less loop
+        free = eng.generate(w1, w2, ids, steps).cpu()
+        assert free.shape == (B, steps)
+        identical_rows = 0
+        for b in range(B):
+            upto = _first_thin_step(margins[b])
+            assert torch.equal(free[b, :upto], ref[b, :upto]), (
+                f"{name}/{policy} row {b}: ids differ at step {int((free[b, :upto] != ref[b, :upto]).nonzero()[0])} "
+                f"before the first thin-margin step {upto}")
+            identical_rows += int(torch.equal(free[b], ref[b]))
+        # teacher-forced on the reference ids: every step's logits, to ctx 688
+        eng.encode(w1, w2)
+        eng.prefix(ids)
+        eng.prefill(B, want_logits=False)
+        own, dump = eng.decode(B, steps, dump_logits=True, forced_tokens=ref)
+        own, dump = own.cpu(), dump.cpu()                                     # (B, steps), (steps, B, V)
+        assert torch.isfinite(dump).all()
+        top_ids = torch.from_numpy(g["top8_ids"])                             # (steps, B, 8)
+        got_top = torch.gather(dump, 2, top_ids)
+        err_top = (got_top - torch.from_numpy(g["top8_vals"])).abs().max().item()
+        got_probe = dump[:, :, torch.from_numpy(g["probe_ids"])]
+        err_probe = (got_probe - torch.from_numpy(g["probe_logits"])).abs().max().item()
+        assert err_top < LOGIT_TOL and err_probe < LOGIT_TOL, f"{name}/{policy}: top-8 {err_top:.2e}, probes {err_probe:.2e}"
+        decided = torch.from_numpy(margins >= MARGIN_GATE)
+        assert torch.equal(own[decided], ref[decided]), f"{name}/{policy}: argmax differs on a step with margin >= {MARGIN_GATE}"
+        agree = (own == ref).float().mean().item()
+        print(f"{name}/{policy}: teacher-forced max |dlogit| top-8 {err_top:.2e} probes {err_probe:.2e}; argmax agrees on "
+              f"{agree:.4f} of {B * steps} steps ({int((~decided).sum())} below the margin gate); free-running rows "
+              f"identical over all 300 steps: {identical_rows}/{B}")
+    finally:
+        eng.close()
+
+
+def test_batch_128_runs_300_steps_like_the_reference(engine):
+    """The bench configuration itself (B=128, max_len 300, default policy): 64 copies of the two long1234 rows."""
+    from mellow_b200.engine import Engine
+    g = _golden("long1234")
+    _, w1, w2, ids, steps = _maker().set_inputs("long1234")
+    ref = torch.from_numpy(g["tokens"]).to(torch.int32)
+    margins = (g["top8_vals"][..., 0] - g["top8_vals"][..., 1]).T
+    eng = Engine(None, device=0, max_batch=128, max_new_tokens=steps, policy="split24", arena=engine.arena)
+    try:
+        toks = eng.generate(w1.repeat(64, 1), w2.repeat(64, 1), ids.repeat(64, 1), steps).cpu()
+        assert toks.shape == (128, steps)
+        for b in range(2):
+            rows = toks[b::2]
+            assert (rows == rows[:1]).all(), "copies of one pair must decode identically whatever their row index"
+            upto = _first_thin_step(margins[b])
+            assert torch.equal(rows[0, :upto], ref[b, :upto])
+    finally:
+        eng.close()
+
+
+def test_config0_reference_wavs_through_the_wrapper():
+    """BASELINE.json configs[0]: resource/1.wav + 2.wav, random.seed(0), 30 greedy steps through MellowWrapper.generate()
+    (GPU resampler, tile / crop, stand-in tokenizer) against ids produced by the reference classes from audio prepared
+    exactly like wrapper.py:141-168."""
+    from mellow_b200 import MellowWrapper
+    from mellow_b200.tokenizer import ByteStandInTokenizer
+    g = _golden("config0")
+    res = os.path.join(GOLD, "resource")
+    prompt = _maker().CONFIG0_PROMPT
+    mw = MellowWrapper(config="v0", model="v0", device=0, use_cuda=True, checkpoint="synthetic")
+    random.seed(0)
+    out = mw.generate(examples=[[os.path.join(res, "1.wav"), os.path.join(res, "2.wav"), prompt]], max_len=30, top_p=0.8,
+                      temperature=1.0)
+    want = ByteStandInTokenizer().decode(g["tokens"][0].tolist()).split("<|endoftext|>")[0]
+    assert out == [want]
+    # the audio the GPU ingest produced is the reference's (tile for 1.wav, the seeded crop for 2.wav)
+    random.seed(0)
+    a1 = mw.preprocess_audio([os.path.join(res, "1.wav")], True)
+    a2 = mw.preprocess_audio([os.path.join(res, "2.wav")], True)
+    assert (a1[0, :4096].cpu() - torch.from_numpy(g["audio1_head"])).abs().max() < 5e-6
+    assert (a2[0, :4096].cpu() - torch.from_numpy(g["audio2_head"])).abs().max() < 5e-6
+    mw.model.close()
+
+
+def test_reference_inner_seams(engine, sd):
+    """wrapper.py:217,237 call `model.caption_decoder.lm(inputs_embeds=...)` and `lm.model.embed_tokens`; the cache-less
+    forward over prefix + t embeddings must give the reference's step-t logits (golden: t = 11) and the KV-cached loop."""
+    from oracle import restated as R
+    g = dict(np.load(os.path.join(GOLD, "ref_synth1234.npz")))
+    _, w1, w2, ids, _ = _maker().set_inputs("long1234")
+    prefix, od1, od2 = engine.generate_prefix_inference({"audio1": w1, "audio2": w2, "input": {"input_ids": ids}}, heads=False)
+    lm = engine.caption_decoder.lm
+    toks = torch.from_numpy(g["tokens"])                                      # (2, 12)
+    emb = lm.model.embed_tokens(toks[:, :11].cuda())
+    assert torch.equal(emb.cpu(), sd["caption_decoder.lm.model.embed_tokens.weight"][toks[:, :11]])
+    seq = torch.cat([prefix, emb], dim=1)                                     # (2, 400, 576)
+    logits = lm(inputs_embeds=seq).logits[:, -1, :].cpu()
+    top_ids = torch.from_numpy(g["top8_ids"][11])
+    err = (torch.gather(logits, 1, top_ids) - torch.from_numpy(g["top8_vals"][11])).abs().max().item()
+    assert err < LOGIT_TOL, err
+    assert logits.argmax(-1).tolist() == toks[:, 11].tolist()
+    with torch.no_grad():
+        want0 = R.last_logits(sd, R.llama_hidden(sd, prefix.cpu()))
+    got0 = lm(inputs_embeds=prefix).logits[:, -1, :].cpu()
+    assert (got0 - want0).abs().max() < LOGIT_TOL

@@ -85,8 +85,8 @@ def test_pack_roundtrip(sd, lib):
         assert lo[m] <= nz.min() and hi[m] > nz.max()
     # rope table equals the oracle's
     from oracle import restated as R
-    cos, sin = R.rope_tables(1024)
-    assert torch.equal(f32("lm.rope_cos").view(1024, 32), cos[:, :32]) and torch.equal(f32("lm.rope_sin").view(1024, 32), sin[:, :32])
+    cos, sin = R.rope_tables(S.MAX_POSITIONS)
+    assert torch.equal(f32("lm.rope_cos").view(-1, 32), cos[:, :32]) and torch.equal(f32("lm.rope_sin").view(-1, 32), sin[:, :32])
 
 
 def test_packer_rejects_bad_checkpoints(sd, lib):
@@ -134,6 +134,55 @@ def test_tokenizer_stand_in_and_wrapper_errors():
     if not torch.cuda.is_available():
         with pytest.raises(MellowNativeError):
             MellowWrapper(config="v0", model="v0", device="cpu", use_cuda=False, checkpoint="synthetic")
+
+
+def test_tokenizer_never_falls_back_silently(monkeypatch):
+    """ADVICE round 1: without a local tokenizer and without the hub, loading must RAISE (the reference raises too);
+    the stand-in is used only when asked for."""
+    from mellow_b200.tokenizer import ByteStandInTokenizer, load_tokenizer
+    monkeypatch.delenv("MELLOW_TOKENIZER", raising=False)
+    monkeypatch.setenv("HF_HUB_OFFLINE", "1")
+    with pytest.raises(RuntimeError, match="cannot load the tokenizer"):
+        load_tokenizer("HuggingFaceTB/SmolLM2-135M-not-cached-anywhere")
+    assert isinstance(load_tokenizer("HuggingFaceTB/SmolLM2-135M", local="stand-in"), ByteStandInTokenizer)
+    monkeypatch.setenv("MELLOW_TOKENIZER", "stand-in")
+    assert isinstance(load_tokenizer("HuggingFaceTB/SmolLM2-135M"), ByteStandInTokenizer)
+
+
+def test_resampled_length_rounds_like_torchaudio():
+    """torchaudio ceils the float32-rounded quotient; 1 % of the 44.1 kHz lengths differ from math.ceil."""
+    from mellow_b200.audio_io import resampled_length
+    assert resampled_length(300044, 44100, 32000) == 217719 == resampled_length(300044, 441, 320)
+    for n in list(range(300000, 300400)) + [403604, 445940, 1, 2, 441, 440999]:
+        want = int(torch.ceil(torch.as_tensor(320 * n / 441)).long())
+        assert resampled_length(n, 44100, 32000) == want, n
+    assert resampled_length(403604, 44100, 32000) == 292865 and resampled_length(445940, 44100, 32000) == 323585
+
+
+def test_global_stop_rule_of_split_runs():
+    """wrapper.py:247-249 evaluated after the fact (runs split into passes / ranks): columns up to and including the
+    first step at which every row has emitted the stop id."""
+    from mellow_b200.wrapper import MellowWrapper
+    t = torch.tensor([[5, 0, 7, 7, 7], [6, 6, 6, 0, 9], [0, 1, 2, 3, 4]])
+    assert MellowWrapper._global_stop(t, 0) == 4
+    assert MellowWrapper._global_stop(t, 8) == 5                      # never reached: max_len columns
+    assert MellowWrapper._global_stop(t[:1], 0) == 2
+
+
+def test_read_audio_info_and_errors(tmp_path):
+    import wave as wavmod
+    from mellow_b200.audio_io import read_audio
+    p = str(tmp_path / "s.wav")
+    with wavmod.open(p, "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(48000)
+        f.writeframes(np.arange(2 * 100, dtype="<i2").tobytes())
+    assert read_audio(p, info_only=True) == (2, 100, 48000)
+    x, sr = read_audio(p)
+    assert x.shape == (2, 100) and sr == 48000 and x[1, 0] == 1 / 32768.0
+    bad = tmp_path / "x.flac"
+    bad.write_bytes(b"fLaC" + bytes(64))
+    with pytest.raises(RuntimeError, match="cannot decode"):
+        read_audio(str(bad))
 
 
 def test_create_fails_loudly_without_gpu(lib):

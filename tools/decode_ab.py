@@ -1,7 +1,6 @@
-"""A/B timing of the decode loop under the library's environment switches (one process per configuration, because
-the switches are read once):
+"""A/B timing of the decode loop under the library's options (mb_set_option) / environment switches:
 
-    MB_DECODE_GROUPS=2 MB_DECODE_COMPACT=1 python tools/decode_ab.py --batch 128 --max-len 300 --tag g2
+    python tools/decode_ab.py --batch 128 --max-len 300 --policy split24 --opt kv_prefetch=0 --tag no_prefetch
 
 Prints one JSON line: decode ms per token step (CUDA events on the launch stream, 1 warm-up decode), prefill ms, and
 whether the greedy ids equal those of the first configuration run in this gpurun call (kept in gpurun_out/)."""
@@ -17,9 +16,13 @@ ap.add_argument("--max-len", type=int, default=300)
 ap.add_argument("--policy", default="split")
 ap.add_argument("--tag", default="")
 ap.add_argument("--iters", type=int, default=2)
+ap.add_argument("--opt", action="append", default=[], help="name=value for mb_set_option")
 args = ap.parse_args()
 B = args.batch
 eng = Engine(synth.synthetic_state_dict(), device=0, max_batch=B, max_new_tokens=args.max_len, policy=args.policy)
+for kv in args.opt:
+    k, v = kv.split("=")
+    eng.set_option(k, int(v))
 wave = synth.synthetic_waveforms(2 * B).cuda(); ids = synth.synthetic_prompt_ids(B).cuda()
 s = torch.cuda.Stream()
 with torch.cuda.stream(s):
@@ -47,7 +50,7 @@ if os.path.isfile(ref_path):
     first_diff = int(ne.any(dim=0).nonzero()[0]) if diff_rows else None
 else:
     torch.save(toks.cpu(), ref_path)
-print(json.dumps({"tag": args.tag, "env": {k: v for k, v in os.environ.items() if k.startswith("MB_")}, "batch": B,
+print(json.dumps({"tag": args.tag, "policy": args.policy, "opts": args.opt, "env": {k: v for k, v in os.environ.items() if k.startswith("MB_")}, "batch": B,
                   "steps": int(toks.shape[1]), "prefill_ms": e[0].elapsed_time(e[1]),
                   "decode_ms_per_step": e[1].elapsed_time(e[2]) / args.iters / toks.shape[1],
                   "tokens_equal_first_config": same, "rows_differing": diff_rows, "first_differing_step": first_diff}), flush=True)

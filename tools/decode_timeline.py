@@ -24,9 +24,14 @@ ap.add_argument("--steps", type=int, default=24)
 ap.add_argument("--show-step", type=int, default=12)
 ap.add_argument("--show-layer", type=int, default=15)
 ap.add_argument("--out", default="")
+ap.add_argument("--policy", default="split24")
+ap.add_argument("--opt", action="append", default=[], help="name=value for mb_set_option")
 args = ap.parse_args()
 B = args.batch
-eng = Engine(synth.synthetic_state_dict(), device=0, max_batch=B, max_new_tokens=max(args.steps, 8))
+eng = Engine(synth.synthetic_state_dict(), device=0, max_batch=B, max_new_tokens=max(args.steps, 8), policy=args.policy)
+for kv in args.opt:
+    k, v = kv.split("=")
+    eng.set_option(k, int(v))
 wave = synth.synthetic_waveforms(2 * B).cuda(); ids = synth.synthetic_prompt_ids(B).cuda()
 cap = args.steps * 230 * 2 * 2             # records of 16 events (first and last CTA of every launch)
 buf = torch.zeros(8 + 256 * cap, dtype=torch.uint8, device="cuda")

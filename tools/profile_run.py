@@ -10,12 +10,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--batch", type=int, default=128)
 ap.add_argument("--max-len", type=int, default=4)
 ap.add_argument("--policy", default="split")
-ap.add_argument("--engine", type=int, default=1)
 ap.add_argument("--phase", default="generate", choices=["generate", "decode", "prefill"])
 args = ap.parse_args()
 B = args.batch
 eng = Engine(synth.synthetic_state_dict(), device=0, max_batch=B, max_new_tokens=max(args.max_len, 8), policy=args.policy)
-eng.set_gemm_engine(args.engine)
+
 wave = synth.synthetic_waveforms(2 * B).cuda(); ids = synth.synthetic_prompt_ids(B).cuda()
 s = torch.cuda.Stream()
 with torch.cuda.stream(s):

@@ -46,6 +46,7 @@ struct NvtxRange {
 };
 
 cudaError_t launch_gemm_umma(const GemmArgs& g, int epi, cudaStream_t st, bool* handled);   // gemm_umma.cu
+int gemm_umma_ssq_parts(int M, int N);
 
 namespace {
 
@@ -192,7 +193,8 @@ struct Handle {
     bf16 *a33_hi = nullptr, *a33_lo = nullptr, *g33_hi = nullptr, *g33_lo = nullptr;
     // LM workspace (M = max_batch*389 rows)
     float *x = nullptr, *q = nullptr, *logits = nullptr;
-    bf16 *la_hi = nullptr, *la_lo = nullptr, *lh_hi = nullptr, *lh_lo = nullptr;
+    bf16 *la_hi = nullptr, *la_lo = nullptr, *lb_hi = nullptr, *lb_lo = nullptr, *lh_hi = nullptr, *lh_lo = nullptr;
+    float *ssq_a = nullptr, *ssq_b = nullptr;   // deferred-RMSNorm partial sums of squares [parts][rows] (o_proj -> gate/up, down -> QKV)
     void *kcache = nullptr, *vcache = nullptr;
     size_t kv_layer_elems = 0;
     float *part_acc = nullptr, *part_ml = nullptr, *gemm_partial = nullptr, *cand_val = nullptr;
@@ -511,13 +513,22 @@ int lm_layer_decode_fused(Handle* h, int l, int n, const float* next_norm, cudaS
     return 0;
 }
 
-// one transformer layer over M rows of h->x.  prefill: rows_per_seq = 389; decode: rows_per_seq = 1.
-int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_t st) {
+// one transformer layer over M rows of h->x.  prefill: rows_per_seq = S (389); decode: rows_per_seq = 1.
+// Prefill defers the RMSNorms (gemm.cuh, GemmArgs::norm_w): o_proj / down write the planes of x * gain of the NEXT norm
+// and per-row partial sums of squares, gate/up / QKV scale their accumulator rows by rstd.  `planes_ready`: the planes
+// already hold x * input_layernorm gain of this layer (written by the previous layer's down) and ssq_b its partials;
+// `next_gain`: the input_layernorm gain of the following layer (nullptr: the last layer, only x is needed).
+int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_t st, bool planes_ready = false,
+             const float* next_gain = nullptr) {
     const LmLayerW& k = h->w.layer[l];
     const int M = B * rows_per_seq;
-    MB_TRY(run_norm(h, NORM_RMS, h->x, k.ln1, nullptr, M, kHidden, h->la_hi, h->la_lo, nullptr, 1, 0, 0, st));
+    const bool defer = !decode && h->engine == 1 && M >= 1024;
+    const int parts = defer ? gemm_umma_ssq_parts(M, kHidden) : 0;
+    if (!(defer && planes_ready))
+        MB_TRY(run_norm(h, NORM_RMS, h->x, k.ln1, nullptr, M, kHidden, h->la_hi, h->la_lo, nullptr, 1, 0, 0, st));
     {
         GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.qkv, kHidden, M, kQkvDim, kHidden);
+        if (defer && planes_ready) { g.ssq_in = h->ssq_b; g.ssq_parts = parts; g.ssq_ld = M; }
         g.q_out = h->q;
         g.k_cache = kv_layer(h, h->kcache, l); g.v_cache = kv_layer(h, h->vcache, l);
         g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
@@ -537,19 +548,36 @@ int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_
     {
         GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.o, kHidden, M, kHidden, kHidden);
         g.residual = h->x; g.ldr = kHidden; g.out_f32 = h->x; g.ldo = kHidden;
+        if (defer) {                                     // planes of x * post_attention_layernorm gain for gate/up
+            g.out_hi = h->lb_hi; g.out_lo = lo_of(h, h->lb_lo); g.ldp = kHidden; g.norm_w = k.ln2;
+            g.ssq_out = h->ssq_a; g.ssq_ld = M;
+        }
         MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
     }
-    MB_TRY(run_norm(h, NORM_RMS, h->x, k.ln2, nullptr, M, kHidden, h->la_hi, h->la_lo, nullptr, 1, 0, 0, st));
+    if (!defer) MB_TRY(run_norm(h, NORM_RMS, h->x, k.ln2, nullptr, M, kHidden, h->la_hi, h->la_lo, nullptr, 1, 0, 0, st));
     {
-        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.gu, kHidden, M, 2 * kInter, kHidden);
+        GemmArgs g = defer ? gemm_base(h, h->lb_hi, h->lb_lo, kHidden, k.gu, kHidden, M, 2 * kInter, kHidden)
+                           : gemm_base(h, h->la_hi, h->la_lo, kHidden, k.gu, kHidden, M, 2 * kInter, kHidden);
+        if (defer) { g.ssq_in = h->ssq_a; g.ssq_parts = parts; g.ssq_ld = M; }
         g.out_hi = h->lh_hi; g.out_lo = lo_of(h, h->lh_lo); g.ldp = kInter;
         MB_TRY(run_gemm(h, g, EPI_SWIGLU, st));
     }
     {
         GemmArgs g = gemm_base(h, h->lh_hi, h->lh_lo, kInter, k.down, kInter, M, kHidden, kInter);
         g.residual = h->x; g.ldr = kHidden; g.out_f32 = h->x; g.ldo = kHidden;
+        if (defer && next_gain) {                        // planes of x * next input_layernorm gain for the next QKV
+            g.out_hi = h->la_hi; g.out_lo = lo_of(h, h->la_lo); g.ldp = kHidden; g.norm_w = next_gain;
+            g.ssq_out = h->ssq_b; g.ssq_ld = M;
+        }
         MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
     }
+    return 0;
+}
+
+// all 30 layers over B sequences of S rows held in h->x (prefill / the cache-less forward of mb_lm_forward_last)
+int lm_stack(Handle* h, int B, int S, cudaStream_t st) {
+    for (int l = 0; l < kLayers; ++l)
+        MB_TRY(lm_layer(h, l, B, S, false, st, /*planes_ready=*/l > 0, l + 1 < kLayers ? h->w.layer[l + 1].ln1 : nullptr));
     return 0;
 }
 
@@ -612,7 +640,7 @@ int check_ready(Handle* h, int B) {
 
 int do_prefill(Handle* h, int B, float* logits_out, cudaStream_t st) {
     NvtxRange r_("mellow.lm_prefill");
-    for (int l = 0; l < kLayers; ++l) MB_TRY(lm_layer(h, l, B, kPrefix, false, st));
+    MB_TRY(lm_stack(h, B, kPrefix, st));
     MB_TRY(lm_head(h, B, kPrefix, kPrefix - 1, /*fused=*/false, st));   // step-0 logits stay available to mb_prefill callers
     if (logits_out)
         MB_CK(h, cudaMemcpyAsync(logits_out, h->logits, (size_t)B * kVocab * 4, cudaMemcpyDeviceToDevice, st));
@@ -748,6 +776,10 @@ static int create_body(Handle* h) {
     MB_TRY(dev_alloc(h, &h->q, M * kHidden));
     MB_TRY(dev_alloc(h, &h->la_hi, M * kHidden));
     MB_TRY(dev_alloc(h, &h->la_lo, M * kHidden));
+    MB_TRY(dev_alloc(h, &h->lb_hi, M * kHidden));
+    MB_TRY(dev_alloc(h, &h->lb_lo, M * kHidden));
+    MB_TRY(dev_alloc(h, &h->ssq_a, M * 12));
+    MB_TRY(dev_alloc(h, &h->ssq_b, M * 12));
     MB_TRY(dev_alloc(h, &h->lh_hi, M * kInter));
     MB_TRY(dev_alloc(h, &h->lh_lo, M * kInter));
     MB_TRY(dev_alloc(h, &h->logits, B * kVocab));
@@ -944,7 +976,7 @@ int mb_lm_forward_last(void* hv, const float* embeds, int B, int S, float* logit
     NvtxRange r_("mellow.lm_forward_last");
     MB_CK(h, cudaMemcpyAsync(h->x, embeds, (size_t)B * S * kHidden * 4, cudaMemcpyDeviceToDevice, st));
     h->prefix_B = 0;                                       // the prefix / KV state of a previous mb_prefix is overwritten
-    for (int l = 0; l < kLayers; ++l) MB_TRY(lm_layer(h, l, B, S, false, st));
+    MB_TRY(lm_stack(h, B, S, st));
     MB_TRY(lm_head(h, B, S, S - 1, /*fused=*/false, st));
     if (logits_out)
         MB_CK(h, cudaMemcpyAsync(logits_out, h->logits, (size_t)B * kVocab * 4, cudaMemcpyDeviceToDevice, st));

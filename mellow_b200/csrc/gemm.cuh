@@ -18,6 +18,15 @@ struct GemmArgs {
     int epi_sleep;                                    // weight-resident kernel: ns the epilogue warps sleep between polls of the accumulator barrier
     int resident;                                     // decode chain: use the weight-resident kernel (gemm_skinny.cu) when the shape fits
     int bn_hint;                                      // decode-sized GEMMs: N-tile width 16 / 32 (0 = default rule)
+    // Deferred RMSNorm (LlamaRMSNorm, modeling_llama.py:62-67) across a producer / consumer pair of GEMMs.  RMSNorm(x) * W^T =
+    // rstd(x) * ((x * gain) * W^T), and rstd is one scalar per row, so the PRODUCER of x (o_proj / down_proj, EPI_GENERIC
+    // with a residual) writes the planes of x * gain (`norm_w`) plus per-row partial sums of x^2 (`ssq_out`, one per
+    // 32-column chunk group it owns), and the CONSUMER (gate/up, QKV) multiplies its accumulator rows by
+    // rstd = rsqrt(sum(partials) / K + eps) before its own epilogue.  This removes the stand-alone norm kernel and its pass
+    // over x; sums run in a fixed order (deterministic).
+    const float* norm_w;                              // producer: gain applied to the plane outputs (out_f32 keeps x itself)
+    float* ssq_out; int ssq_ld;                       // producer: partial row sums of squares [parts][ssq_ld]
+    const float* ssq_in; int ssq_parts;               // consumer: partials written by the producer (same ssq_ld), their count
     // EPI_GENERIC: v = act(acc + bias) + residual -> out_f32 and/or bf16 planes
     const float* bias;
     const float* residual; int ldr;
@@ -253,8 +262,18 @@ __device__ __forceinline__ void epilogue_row16(const GemmArgs& g, int m, int n, 
         }
         if (g.out_hi) {
             const size_t idx = (size_t)m * g.ldp + n;
-            store_planes8(g.out_hi, g.out_lo, idx, v);
-            store_planes8(g.out_hi, g.out_lo, idx + 8, v + 8);
+            if (g.norm_w) {                                            // planes of x * gain (deferred RMSNorm, see GemmArgs)
+                float y[16], gw[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) ldg4(g.norm_w + n + j, gw + j);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) y[j] = gw[j] * v[j];
+                store_planes8(g.out_hi, g.out_lo, idx, y);
+                store_planes8(g.out_hi, g.out_lo, idx + 8, y + 8);
+            } else {
+                store_planes8(g.out_hi, g.out_lo, idx, v);
+                store_planes8(g.out_hi, g.out_lo, idx + 8, v + 8);
+            }
         }
     } else if (EPI == EPI_SWIGLU) {
         float hv[8];
@@ -275,6 +294,13 @@ __device__ __forceinline__ void epilogue_row16(const GemmArgs& g, int m, int n, 
         qkv_rope_load(g, m, n, c, sn);
         epilogue_row16_qkv(g, m, n, v, c, sn);
     }
+}
+
+// consumer side of the deferred RMSNorm: rstd of row m from the producer's partial sums of squares (fixed order)
+__device__ __forceinline__ float deferred_rstd(const GemmArgs& g, int m) {
+    float t = 0.f;
+    for (int p = 0; p < g.ssq_parts; ++p) t += __ldcg(g.ssq_in + (size_t)p * g.ssq_ld + m);
+    return rsqrtf(t * (1.0f / (float)g.K) + 1e-5f);
 }
 
 // Engine entry points (gemm_umma.cu, gemm_skinny.cu; gemm_mma.cu = mma.sync cross-check engine of lab builds)

@@ -80,6 +80,13 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
     pdl_trigger();
     if (threadIdx.x == kProducerWarp * 32) {
+        // descriptor fetches are latency the dependency wait would otherwise expose (the A maps are first used after it)
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_hi) : "memory");
+        if (SPLIT) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a_lo) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_b_lo) : "memory");
+        }
         *trace_slot = trace_open(g.trace, g.trace_id);
         for (int i = 0; i < KBMAX; ++i) mbar_init(&bfull[i], 1);
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
@@ -174,6 +181,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         constexpr int kUnits = BN / 16;
         pdl_wait();                                                  // residual reads / output writes depend on the predecessor
         const int m = q * 32 + lane;
+        constexpr int kStgLd = BN + 4;                               // staging row stride (floats): 16-byte aligned, conflict-free
+        float* stg = reinterpret_cast<float*>(areg);                 // free once the accumulator is complete (all MMAs retired)
         if (half < kUnits) {
             float rc[8], rs[8];
             if (EPI == EPI_QKV_ROPE && nsplit == 1 && m < g.M)       // RoPE factors of the first unit, fetched while the MMAs run
@@ -194,19 +203,29 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                     for (int j = 0; j < 16; ++j) v[j] += w[j];
                 }
                 const int n = n0 + c0;
-                if (m < g.M && n < g.N) {
-                    if (nsplit > 1) {
-                        float* pz = g.partial + (size_t)z * g.M * g.N + (size_t)m * g.N + n;
+                if (nsplit > 1) {
+                    // split-K partial sums: staged in the (idle) activation ring so that the tile leaves the SM as
+                    // whole 128-byte row segments (below) instead of 32 scattered 16-byte pieces per store instruction
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4)
-                            if (n + j < g.N) st4(pz + j, v + j);
-                    } else if (EPI == EPI_QKV_ROPE && n + 16 <= g.N) {
+                    for (int j = 0; j < 16; j += 4) st4(stg + m * kStgLd + c0 + j, v + j);
+                } else if (m < g.M && n < g.N) {
+                    if (EPI == EPI_QKV_ROPE && n + 16 <= g.N) {
                         if (u != half) qkv_rope_load(g, m, n, rc, rs);
                         epilogue_row16_qkv(g, m, n, v, rc, rs);
                     } else {
                         epilogue_row16<EPI>(g, m, n, v);
                     }
                 }
+            }
+        }
+        if (nsplit > 1) {
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");        // the eight epilogue warps only
+            constexpr int kC4 = BN / 4;                              // float4 pieces per tile row
+            float* pz = g.partial + (size_t)z * g.M * g.N + n0;
+            for (int idx = threadIdx.x; idx < BM * kC4; idx += kEpiWarps * 32) {
+                const int row = idx / kC4, c = (idx - row * kC4) * 4;
+                if (row < g.M && n0 + c < g.N)
+                    *reinterpret_cast<float4*>(pz + (size_t)row * g.N + c) = *reinterpret_cast<const float4*>(stg + row * kStgLd + c);
             }
         }
     }

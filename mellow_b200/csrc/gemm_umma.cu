@@ -187,6 +187,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 if (lane == 0) mbar_arrive(&tempty[buf]);
                 continue;
             }
+            // deferred RMSNorm (gemm.cuh): consumer scale of this row, producer partial of this warp's chunks
+            const float rs = (g.ssq_in != nullptr && m < g.M) ? deferred_rstd(g, m) : 1.0f;
+            float sq = 0.f;
 #pragma unroll 1
             for (int ci = half; ci < kChunks; ci += kSub) {
                 const int c0 = ci * 32;
@@ -209,12 +212,22 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                                 for (int j = 0; j < 16; j += 4)
                                     if (n + j < g.N) st4(pz + j, v + h + j);
                             } else {
-                                epilogue_row16<EPI>(g, m, n, v + h);
+                                if (g.ssq_in != nullptr) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) v[h + j] *= rs;
+                                }
+                                epilogue_row16<EPI>(g, m, n, v + h);   // leaves the finished values in v (EPI_GENERIC)
+                                if (EPI == EPI_GENERIC && g.ssq_out != nullptr) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) sq += (n + j < g.N) ? v[h + j] * v[h + j] : 0.f;
+                                }
                             }
                         }
                     }
                 }
             }
+            if (EPI == EPI_GENERIC && g.ssq_out != nullptr && m < g.M)
+                g.ssq_out[(size_t)((t.n0 / BN) * kSub + half) * g.ssq_ld + m] = sq;
         }
     }
     tc_fence_before();
@@ -257,26 +270,41 @@ cudaError_t launch_p(const GemmArgs& g, cudaStream_t st) {
 // Tile width.  Every tcgen05.mma streams the 128-row A tile from shared memory (~65 cycles whatever N is), so narrow
 // tiles are A-read bound: N = 96 caps the tensor pipe near 74 %, N >= 192 is compute-paced.  N = 576 (o_proj, down,
 // projection) and N = 960 (QKV) therefore run as 3 / 5 tiles of 192 columns instead of 6 / 10 of 96.
+inline int tile_bn(int M, int N) {
+    if (M <= 128 && N <= 4096) return N >= 2048 ? 32 : 16;           // decode-sized shapes the weight-resident kernel did not take
+    if (N % 256 == 0 && M >= 1024) return 256;                       // widest tile: A tile re-used over 256 columns
+    if (N % 192 == 0 && M >= 1024) return 192;
+    if ((N % 128 != 0) && (N % 96 == 0)) return 96;
+    return 128;
+}
+
 template <int EPI>
 cudaError_t launch_epi(const GemmArgs& g, cudaStream_t st) {
-    if (g.M <= 128 && g.N <= 4096) {
-        // decode-sized (one 128-row UMMA tile) shapes the weight-resident kernel did not take: narrow N tiles
-        // (x split-K) so that many SMs stream the weights
-        if (g.N >= 2048) return launch_p<32, EPI>(g, st);
-        return launch_p<16, EPI>(g, st);
+    switch (tile_bn(g.M, g.N)) {
+        case 16: return launch_p<16, EPI>(g, st);
+        case 32: return launch_p<32, EPI>(g, st);
+        case 96: return launch_p<96, EPI>(g, st);
+        case 192: return launch_p<192, EPI>(g, st);
+        case 256: return launch_p<256, EPI>(g, st);
+        default: return launch_p<128, EPI>(g, st);
     }
-    if (g.N % 256 == 0 && g.M >= 1024) return launch_p<256, EPI>(g, st);   // widest tile: A tile re-used over 256 columns
-    if (g.N % 192 == 0 && g.M >= 1024) return launch_p<192, EPI>(g, st);
-    if ((g.N % 128 != 0) && (g.N % 96 == 0)) return launch_p<96, EPI>(g, st);
-    return launch_p<128, EPI>(g, st);
 }
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
 
+// partial row sums of squares a producer GEMM of this shape writes per row (GemmArgs::ssq_out): two epilogue warps per
+// TMEM lane quadrant, each owning every other 32-column chunk of a tile
+int gemm_umma_ssq_parts(int M, int N) {
+    const int bn = tile_bn(M, N);
+    return bn >= 64 ? 2 * ((N + bn - 1) / bn) : 0;
+}
+
 cudaError_t launch_gemm_umma(const GemmArgs& g, int epi, cudaStream_t st, bool* handled) {
     *handled = false;
+    if (g.ssq_out && (epi != EPI_GENERIC || gemm_umma_ssq_parts(g.M, g.N) == 0 || (g.N & 15) || g.split_k > 1)) return cudaErrorInvalidValue;
+    if (g.norm_w && (epi != EPI_GENERIC || (g.N & 15) || (g.ldp & 7))) return cudaErrorInvalidValue;
     if (g.M < 1 || g.K < BK || (g.K % 8) != 0 || (g.lda % 8) != 0 || (g.ldw % 8) != 0) return cudaSuccess;
     if (g.split_k > 1 && (epi != EPI_GENERIC || !g.partial || (g.N & 1))) return cudaErrorInvalidValue;
     if (!aligned16(g.A_hi) || !aligned16(g.W_hi) || (g.passes == 3 && (!aligned16(g.A_lo) || !aligned16(g.W_lo)))) return cudaSuccess;

@@ -52,8 +52,12 @@ long long mb_workspace_bytes(void* h);
  *   "decode_unfused" (0) 1 = use the generic per-layer decode path (the one batches > 128 rows take) for every batch
  *   "skip_finished"  (1) rows that emitted eos_id stop streaming their KV cache (their later tokens are not meaningful);
  *                        0 = every row keeps decoding until all rows have stopped, like the reference loop
- *   "kv_prefetch"    (-1) keys per (row, kv head) stream decode attention prefetches into L2 while it waits for its
- *                        predecessor: -1 = the whole immutable history, 0 = off
+ *   "attn_variant"   (1) decode attention kernel: 1 = warp-autonomous (each warp streams its own 16-key chunks, no block
+ *                        barrier in the loop), 0 = the 64-key tile kernel of round 1
+ *   "kv_prefetch"    (0) tile kernel only: keys per (row, kv head) stream prefetched into L2 while the kernel waits for
+ *                        its predecessor (-1 = the whole immutable history); measured slower, off
+ *   "decode_tails"   (0) 1 = o_proj / down_proj of a decode layer as cluster split-K GEMMs that finish the residual add
+ *                        and the (deferred) RMSNorm themselves: 5 kernels per layer instead of 7
  *   "wide_tiles"     (-1) decode split-K GEMM tiling: 1 = 32-column tiles x 3 / 8 K slices, 0 = 16-column tiles x 3 / 4,
  *                        -1 = by policy (wide except MB_POLICY_FAST)
  *   "gemm_engine"    (1) 0 = mma.sync cross-check engine (lab builds only, MB_BUILD_LAB=1) */

@@ -20,10 +20,12 @@ namespace mb {
 //   MB_NO_GRAPH=1      replay the decode step as individual launches instead of one CUDA graph
 //   MB_DECODE_UNFUSED=1 use the generic per-layer path (the one batches > 128 rows take) for every batch size
 //   MB_EPI_SLEEP=<ns>  back-off of the epilogue warps that wait for the accumulator (decode GEMMs)
-//   MB_KV_PREFETCH=<keys> decode: keys per (row, kv head) stream the attention kernel prefetches into L2 (0 = off)
+//   MB_DECODE_TAILS=0/1 decode: o_proj / down as cluster split-K tails with the deferred RMSNorm (option "decode_tails")
+//   MB_KV_PREFETCH=<keys> decode (tile attention kernel): keys per (row, kv head) stream prefetched into L2 before the
+//                      dependency wait (default 0 = off: measured 4-5 % SLOWER per step, profiles/r2_decode_ab.jsonl)
 struct Tunables {
     bool pdl, graph, decode_unfused;
-    int epi_sleep, kv_prefetch;
+    int epi_sleep, kv_prefetch, decode_tails;
 };
 const Tunables& tunables() {
     static const Tunables t = [] {
@@ -32,7 +34,8 @@ const Tunables& tunables() {
         v.graph = getenv("MB_NO_GRAPH") == nullptr;
         v.decode_unfused = getenv("MB_DECODE_UNFUSED") != nullptr;
         v.epi_sleep = getenv("MB_EPI_SLEEP") ? atoi(getenv("MB_EPI_SLEEP")) : 128;
-        v.kv_prefetch = getenv("MB_KV_PREFETCH") ? atoi(getenv("MB_KV_PREFETCH")) : -1;
+        v.kv_prefetch = getenv("MB_KV_PREFETCH") ? atoi(getenv("MB_KV_PREFETCH")) : 0;
+        v.decode_tails = getenv("MB_DECODE_TAILS") ? atoi(getenv("MB_DECODE_TAILS")) : 0;
         return v;
     }();
     return t;
@@ -213,7 +216,9 @@ struct Handle {
     int kv_fmt = kKvF32;                 // KV-cache row format (common.cuh)
     // mb_set_option (defaults from the environment switches above)
     bool use_graph = true, decode_unfused = false, skip_finished = true;
-    int kv_prefetch = -1;                // keys per stream prefetched into L2 by decode attention (-1 = automatic)
+    int kv_prefetch = 0;                 // (tile kernel) keys per stream prefetched into L2 before the dependency wait; -1 = all
+    int attn_variant = 1;                // decode attention kernel: 1 = warp-autonomous, 0 = 64-key tiles (lm.cu)
+    int decode_tails = 0;                // o_proj / down as cluster split-K tails with the norm deferred (gemm_skinny.cu)
     int wide_tiles = -1;                 // decode split-K tiling: -1 = by policy, 0 = 16-column tiles, 1 = 32-column tiles
     TraceBuf* trace = nullptr;           // mb_set_trace: optional in-kernel timeline of the decode kernels
 };
@@ -459,7 +464,7 @@ int run_decode_attention(Handle* h, int l, int B, cudaStream_t st, bool skip_don
     a.done = (skip_done && h->skip_finished) ? h->d_done : nullptr;
     a.part_acc = h->part_acc; a.part_ml = h->part_ml;
     a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
-    a.pf_keys = h->kv_prefetch;
+    a.pf_keys = h->kv_prefetch; a.variant = h->attn_variant;
     a.trace = h->trace; a.trace_id = 2000 + l;
     MB_CK(h, launch_decode_attention(a, st));
     h->launches += a.nsplit == 1 ? 1 : 2;
@@ -473,10 +478,18 @@ int run_decode_attention(Handle* h, int l, int B, cudaStream_t st, bool skip_don
 int lm_layer_decode_fused(Handle* h, int l, int n, const float* next_norm, cudaStream_t st) {
     const LmLayerW& k = h->w.layer[l];
     const DecodeTiling tl = decode_tiling(h);
+    // Option "decode_tails": o_proj / down as cluster split-K GEMMs that finish the residual add and the deferred
+    // RMSNorm themselves (gemm_skinny.cu): 5 kernels per layer instead of 7.  The planes then hold x * gain and the
+    // consumers scale by rstd (ssq_a: o_proj -> gate/up, ssq_b: down -> next QKV).  The last layer keeps the add +
+    // RMSNorm kernel because lm_head consumes normalised planes.
+    const bool tails = h->decode_tails != 0;
+    const bool last = l + 1 == kLayers;
+    const int ssq_ld = 128;
     {
         GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.qkv, kHidden, n, kQkvDim, kHidden);
         g.resident = 1;
         g.trace = h->trace; g.trace_id = 1000 + l;
+        if (tails && l > 0) { g.ssq_in = h->ssq_b; g.ssq_parts = kHidden / 48; g.ssq_ld = ssq_ld; }
         g.q_out = h->q;
         g.k_cache = kv_layer(h, h->kcache, l); g.v_cache = kv_layer(h, h->vcache, l);
         g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
@@ -485,31 +498,49 @@ int lm_layer_decode_fused(Handle* h, int l, int n, const float* next_norm, cudaS
         MB_TRY(run_gemm(h, g, EPI_QKV_ROPE, st));
     }
     MB_TRY(run_decode_attention(h, l, n, st));
-    {
+    if (tails) {
+        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.o, kHidden, n, kHidden, kHidden);
+        g.trace = h->trace; g.trace_id = 3000 + l;
+        g.residual = h->x; g.ldr = kHidden; g.out_f32 = h->x; g.ldo = kHidden;
+        g.out_hi = h->lb_hi; g.out_lo = lo_of(h, h->lb_lo); g.ldp = kHidden; g.norm_w = k.ln2;
+        g.ssq_out = h->ssq_a; g.ssq_ld = ssq_ld;
+        MB_CK(h, launch_gemm_tail(g, 4, st));
+        h->launches++;
+    } else {
         GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.o, kHidden, n, kHidden, kHidden);
         g.resident = 1;
         g.trace = h->trace; g.trace_id = 3000 + l;
         g.split_k = tl.o_split; g.bn_hint = tl.o_bn; g.partial = h->gemm_partial;
         MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+        MB_CK(h, launch_add_rmsnorm(h->x, h->gemm_partial, tl.o_split, n, k.ln2, h->la_hi, lo_of(h, h->la_lo), st, h->trace, 4000 + l));
+        h->launches++;
     }
-    MB_CK(h, launch_add_rmsnorm(h->x, h->gemm_partial, tl.o_split, n, k.ln2, h->la_hi, lo_of(h, h->la_lo), st, h->trace, 4000 + l));
-    h->launches++;
     {
-        GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.gu, kHidden, n, 2 * kInter, kHidden);
+        GemmArgs g = tails ? gemm_base(h, h->lb_hi, h->lb_lo, kHidden, k.gu, kHidden, n, 2 * kInter, kHidden)
+                           : gemm_base(h, h->la_hi, h->la_lo, kHidden, k.gu, kHidden, n, 2 * kInter, kHidden);
         g.resident = 1;
         g.trace = h->trace; g.trace_id = 5000 + l;
+        if (tails) { g.ssq_in = h->ssq_a; g.ssq_parts = kHidden / 32; g.ssq_ld = ssq_ld; }
         g.out_hi = h->lh_hi; g.out_lo = lo_of(h, h->lh_lo); g.ldp = kInter;
         MB_TRY(run_gemm(h, g, EPI_SWIGLU, st));
     }
-    {
+    if (tails && !last) {
+        GemmArgs g = gemm_base(h, h->lh_hi, h->lh_lo, kInter, k.down, kInter, n, kHidden, kInter);
+        g.trace = h->trace; g.trace_id = 6000 + l;
+        g.residual = h->x; g.ldr = kHidden; g.out_f32 = h->x; g.ldo = kHidden;
+        g.out_hi = h->la_hi; g.out_lo = lo_of(h, h->la_lo); g.ldp = kHidden; g.norm_w = next_norm;
+        g.ssq_out = h->ssq_b; g.ssq_ld = ssq_ld;
+        MB_CK(h, launch_gemm_tail(g, 8, st));
+        h->launches++;
+    } else {
         GemmArgs g = gemm_base(h, h->lh_hi, h->lh_lo, kInter, k.down, kInter, n, kHidden, kInter);
         g.resident = 1;
         g.trace = h->trace; g.trace_id = 6000 + l;
         g.split_k = tl.down_split; g.bn_hint = tl.down_bn; g.partial = h->gemm_partial;
         MB_TRY(run_gemm(h, g, EPI_GENERIC, st));
+        MB_CK(h, launch_add_rmsnorm(h->x, h->gemm_partial, tl.down_split, n, next_norm, h->la_hi, lo_of(h, h->la_lo), st, h->trace, 7000 + l));
+        h->launches++;
     }
-    MB_CK(h, launch_add_rmsnorm(h->x, h->gemm_partial, tl.down_split, n, next_norm, h->la_hi, lo_of(h, h->la_lo), st, h->trace, 7000 + l));
-    h->launches++;
     return 0;
 }
 
@@ -833,6 +864,7 @@ void* mb_create(int device, int max_batch, int max_new_tokens, int policy) {
     h->policy = policy == kPolicySplit24 ? kPolicySplit : policy;
     h->kv_fmt = policy == kPolicyFast ? kKvBf16 : (policy == kPolicySplit24 ? kKvF24 : kKvF32);
     h->use_graph = tunables().graph; h->decode_unfused = tunables().decode_unfused; h->kv_prefetch = tunables().kv_prefetch;
+    h->decode_tails = tunables().decode_tails;
     build_table(h->t, h->w);
     // a blocking stream: implicitly ordered with work the caller issued on the legacy default stream
     if (cudaStreamCreate(&h->own_stream) != cudaSuccess || create_body(h) != 0) {
@@ -862,6 +894,8 @@ int mb_set_option(void* hv, const char* name, int value) {
     else if (n == "skip_finished") h->skip_finished = value != 0;
     else if (n == "kv_prefetch") h->kv_prefetch = value;
     else if (n == "wide_tiles") h->wide_tiles = value;
+    else if (n == "decode_tails") h->decode_tails = value;
+    else if (n == "attn_variant") h->attn_variant = value;
     else if (n == "gemm_engine") {
 #ifdef MB_LAB
         if (value != 0 && value != 1) return fail(h, "unknown GEMM engine");

@@ -31,37 +31,47 @@ namespace {
 
 using namespace umma;
 
-template <int BN, bool SPLIT, int KBMAX>
+// CS > 0: "tail" variant (o_proj / down_proj of a decode layer).  The K range is cut over the CS CTAs of a thread-block
+// cluster (K slice = cluster rank); the partial accumulators are exchanged through distributed shared memory as a
+// reduce-scatter (CTA r finishes rows [r*RPC, (r+1)*RPC) of the tile), and the CTA that owns a row adds the residual,
+// writes the new residual stream, the planes of x * gain and the row's partial sum of squares (deferred RMSNorm,
+// gemm.cuh).  This replaces the global split-K partial buffer AND the add + RMSNorm kernel that consumed it.
+template <int BN, bool SPLIT, int KBMAX, int CS = 0>
 struct SkinnyCfg {
     static constexpr uint32_t PLANES = SPLIT ? 2 : 1;
+    static constexpr int RPC = CS > 0 ? (BM + CS - 1) / CS : 0;        // tile rows finished by each CTA of the cluster
+    static constexpr int RED_LD = BN + 4;                               // floats per staged row (16-byte aligned, conflict-free)
+    static constexpr uint32_t RED_BYTES = CS > 0 ? ((uint32_t)(CS * RPC * RED_LD * 4 + RPC * (BN / 4) * 4) + 1023u) / 1024u * 1024u : 0u;
     static constexpr uint32_t B_BYTES = BN * BK * 2;                    // one plane of one k-block
     static constexpr uint32_t B_REGION = KBMAX * PLANES * B_BYTES;
     static constexpr uint32_t A_STAGE = PLANES * A_BYTES;
     static constexpr uint32_t BAR_BYTES = 512;
-    static constexpr uint32_t BUDGET = 227u * 1024u - 1024u - BAR_BYTES - B_REGION;
+    static constexpr uint32_t BUDGET = 227u * 1024u - 1024u - BAR_BYTES - B_REGION - RED_BYTES;
     static constexpr int FIT = (int)(BUDGET / A_STAGE);
     static constexpr int STAGES = FIT > KBMAX ? KBMAX : FIT;
     static constexpr uint32_t ACC_N = PLANES * BN;                      // accumulator columns: [a*b_hi | a_hi*b_lo]
     static constexpr uint32_t ACC_COLS = ACC_N <= 32 ? 32 : (ACC_N <= 64 ? 64 : 128);
     static constexpr uint32_t TMEM_COLS = ACC_COLS;
     static_assert(ACC_N <= 128 && (BN % 16) == 0, "N tile");
-    static constexpr size_t SMEM = (size_t)B_REGION + (size_t)STAGES * A_STAGE + 1024 + BAR_BYTES;
+    static constexpr size_t SMEM = (size_t)B_REGION + (size_t)STAGES * A_STAGE + RED_BYTES + 1024 + BAR_BYTES;
     static_assert(STAGES >= 2, "activation ring does not fit");
     static_assert((B_BYTES % 1024) == 0, "swizzled tiles start on 1024-byte boundaries");
     static_assert((2 * KBMAX + 2 * 8 + 2) * 8 + 8 <= BAR_BYTES, "barrier block too small");
 };
 
-template <int BN, int EPI, bool SPLIT, int KBMAX>
+template <int BN, int EPI, bool SPLIT, int KBMAX, int CS = 0>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const GemmArgs g) {
-    using C = SkinnyCfg<BN, SPLIT, KBMAX>;
+    using C = SkinnyCfg<BN, SPLIT, KBMAX, CS>;
+    static_assert(CS == 0 || EPI == EPI_GENERIC, "the cluster tail finishes a plain GEMM + residual");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* breg = smem;                                       // [KBMAX][PLANES][BN x 64] weight slice
     unsigned char* areg = smem + C::B_REGION;                         // [STAGES][PLANES][128 x 64] activation ring
-    uint64_t* bfull = reinterpret_cast<uint64_t*>(areg + (size_t)C::STAGES * C::A_STAGE);
+    float* red = reinterpret_cast<float*>(areg + (size_t)C::STAGES * C::A_STAGE);   // [CS][RPC][RED_LD] partials sent by the cluster
+    uint64_t* bfull = reinterpret_cast<uint64_t*>(areg + (size_t)C::STAGES * C::A_STAGE + C::RED_BYTES);
     uint64_t* afull = bfull + KBMAX;
     uint64_t* aempty = afull + C::STAGES;
     uint64_t* tfull = aempty + C::STAGES;
@@ -69,10 +79,11 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     uint32_t* trace_slot = tmem_slot + 1;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nsplit = g.split_k > 1 ? g.split_k : 1;
+    const int nsplit = CS > 0 ? CS : (g.split_k > 1 ? g.split_k : 1);
     const int tiles_n = (g.N + BN - 1) / BN;
-    const int z = blockIdx.x / tiles_n;                               // K split owned by this CTA
-    const int n0 = (blockIdx.x - z * tiles_n) * BN;
+    // K split owned by this CTA: the cluster rank in the tail variant (blockIdx.x = tile * CS + rank), else z-major
+    const int z = CS > 0 ? (int)(blockIdx.x % (CS > 0 ? CS : 1)) : blockIdx.x / tiles_n;
+    const int n0 = (CS > 0 ? (int)(blockIdx.x / (CS > 0 ? CS : 1)) : (blockIdx.x - z * tiles_n)) * BN;
     const int kb_all = (g.K + BK - 1) / BK;
     const int kb_begin = (int)(((long long)kb_all * z) / nsplit);
     const int KB = (int)(((long long)kb_all * (z + 1)) / nsplit) - kb_begin;      // <= KBMAX (checked by the launcher)
@@ -183,6 +194,8 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         const int m = q * 32 + lane;
         constexpr int kStgLd = BN + 4;                               // staging row stride (floats): 16-byte aligned, conflict-free
         float* stg = reinterpret_cast<float*>(areg);                 // free once the accumulator is complete (all MMAs retired)
+        // deferred RMSNorm, consumer side (gemm.cuh): rstd of this row, fetched while the MMAs run
+        const float row_scale = (g.ssq_in != nullptr && m < g.M) ? deferred_rstd(g, m) : 1.0f;
         if (half < kUnits) {
             float rc[8], rs[8];
             if (EPI == EPI_QKV_ROPE && nsplit == 1 && m < g.M)       // RoPE factors of the first unit, fetched while the MMAs run
@@ -202,8 +215,23 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
 #pragma unroll
                     for (int j = 0; j < 16; ++j) v[j] += w[j];
                 }
+                if (g.ssq_in != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] *= row_scale;
+                }
                 const int n = n0 + c0;
-                if (nsplit > 1) {
+                if constexpr (CS > 0) {
+                    // reduce-scatter through distributed shared memory: this row's 16 partial sums go to the CTA of the
+                    // cluster that finishes the row, into the slot of this CTA's K slice
+                    const int owner = m / C::RPC;
+                    const uint32_t la = smem_u32(red + ((size_t)(z * C::RPC + (m - owner * C::RPC)) * C::RED_LD + c0));
+                    uint32_t ra;
+                    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(la), "r"(owner));
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4)
+                        asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ra + 4u * j), "f"(v[j]), "f"(v[j + 1]),
+                                     "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+                } else if (nsplit > 1) {
                     // split-K partial sums: staged in the (idle) activation ring so that the tile leaves the SM as
                     // whole 128-byte row segments (below) instead of 32 scattered 16-byte pieces per store instruction
 #pragma unroll
@@ -218,7 +246,7 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                 }
             }
         }
-        if (nsplit > 1) {
+        if (CS == 0 && nsplit > 1) {
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");        // the eight epilogue warps only
             constexpr int kC4 = BN / 4;                              // float4 pieces per tile row
             float* pz = g.partial + (size_t)z * g.M * g.N + n0;
@@ -230,6 +258,60 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
     }
     if (threadIdx.x == 0) trace_put(g.trace, trec, g.trace_id, 8);                      // this warp's epilogue stores issued
+    if constexpr (CS > 0) {
+        constexpr int kC4 = BN / 4;                                   // float4 pieces per row of the tile
+        constexpr int kItems = C::RPC * kC4;
+        static_assert(kItems <= 2 * kEpiWarps * 32, "two pieces per epilogue thread at most");
+        float* sqb = red + (size_t)CS * C::RPC * C::RED_LD;          // [RPC][kC4] squares of the finished pieces
+        // operands of the rows this CTA finishes that do not come from the cluster: residual and gain, in flight while
+        // the cluster barrier is pending (epilogue threads have passed their dependency wait)
+        float4 xr[2], gw[2];
+        int rowl[2], col[2];
+        bool act[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = (int)threadIdx.x + i * kEpiWarps * 32;
+            rowl[i] = idx / kC4; col[i] = (idx - rowl[i] * kC4) * 4;
+            const int mr = z * C::RPC + rowl[i];
+            act[i] = warp < kEpiWarps && idx < kItems && mr < BM && mr < g.M && n0 + col[i] < g.N;
+            xr[i] = make_float4(0.f, 0.f, 0.f, 0.f); gw[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (act[i]) {
+                if (g.residual) xr[i] = *reinterpret_cast<const float4*>(g.residual + (size_t)mr * g.ldr + n0 + col[i]);
+                if (g.norm_w) gw[i] = __ldg(reinterpret_cast<const float4*>(g.norm_w + n0 + col[i]));
+            }
+        }
+        __syncwarp();
+        cluster_sync_all();                                           // every partial of this CTA's rows has landed (release / acquire)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (!act[i]) continue;
+            const int mr = z * C::RPC + rowl[i];
+            float4 a = *reinterpret_cast<const float4*>(red + (size_t)rowl[i] * C::RED_LD + col[i]);
+#pragma unroll
+            for (int zz = 1; zz < CS; ++zz) {                         // fixed order: deterministic
+                const float4 t = *reinterpret_cast<const float4*>(red + (size_t)(zz * C::RPC + rowl[i]) * C::RED_LD + col[i]);
+                a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+            }
+            a.x += xr[i].x; a.y += xr[i].y; a.z += xr[i].z; a.w += xr[i].w;
+            if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + (size_t)mr * g.ldo + n0 + col[i]) = a;
+            if (g.out_hi) {
+                const size_t o = (size_t)mr * g.ldp + n0 + col[i];
+                store_planes2(g.out_hi, g.out_lo, o, gw[i].x * a.x, gw[i].y * a.y);
+                store_planes2(g.out_hi, g.out_lo, o + 2, gw[i].z * a.z, gw[i].w * a.w);
+            }
+            sqb[rowl[i] * kC4 + (col[i] >> 2)] = a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+        }
+        if (g.ssq_out != nullptr) {
+            if (warp < kEpiWarps) asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+            const int mr = z * C::RPC + (int)threadIdx.x;
+            if ((int)threadIdx.x < C::RPC && mr < BM && mr < g.M) {
+                float t = 0.f;
+#pragma unroll
+                for (int c = 0; c < kC4; ++c) t += (n0 + 4 * c < g.N) ? sqb[threadIdx.x * kC4 + c] : 0.f;
+                g.ssq_out[(size_t)(n0 / BN) * g.ssq_ld + mr] = t;
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (threadIdx.x == kProducerWarp * 32) trace_close(g.trace, *trace_slot, g.trace_id);
@@ -259,6 +341,36 @@ cudaError_t launch_skinny(const GemmArgs& g, cudaStream_t st) {
     return launch_k(kern, dim3((unsigned)total), dim3(kThreads), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
 }
 
+// cluster launch of the tail variant: grid = tiles_n x CS, cluster = the CS K slices of one N tile
+template <int BN, bool SPLIT, int KBMAX, int CS>
+cudaError_t launch_tail(const GemmArgs& g, cudaStream_t st) {
+    using C = SkinnyCfg<BN, SPLIT, KBMAX, CS>;
+    auto kern = gemm_skinny_kernel<BN, EPI_GENERIC, SPLIT, KBMAX, CS>;
+    static bool configured[kMaxDevices] = {};
+    if (cudaError_t e = ensure_smem(kern, C::SMEM, configured); e != cudaSuccess) return e;
+    CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+    if (!make_map(&ta_hi, g.A_hi, g.M, g.K, g.lda, BM) || !make_map(&tb_hi, g.W_hi, g.N, g.K, g.ldw, BN))
+        return cudaErrorInvalidValue;
+    if (SPLIT) {
+        if (!make_map(&ta_lo, g.A_lo, g.M, g.K, g.lda, BM) || !make_map(&tb_lo, g.W_lo, g.N, g.K, g.ldw, BN))
+            return cudaErrorInvalidValue;
+    } else {
+        ta_lo = ta_hi;
+        tb_lo = tb_hi;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(((g.N + BN - 1) / BN) * CS)); cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, g);
+}
+
 template <int BN, int EPI, int KBMAX>
 cudaError_t launch_skinny_p(const GemmArgs& g, cudaStream_t st) {
     return g.passes == 3 ? launch_skinny<BN, EPI, true, KBMAX>(g, st) : launch_skinny<BN, EPI, false, KBMAX>(g, st);
@@ -280,6 +392,20 @@ cudaError_t launch_skinny_epi(const GemmArgs& g, int bn, cudaStream_t st) {
 }
 
 }  // namespace
+
+// Tail of a decode layer (o_proj / down_proj): cluster split-K with the residual add, the planes of x * gain and the
+// deferred-RMSNorm partials in the kernel (SkinnyCfg).  cs = 4: 32-column tiles (o_proj, K = 576 in 3+2+2+2 k-blocks);
+// cs = 8: 48-column tiles (down_proj, K = 1536 in 8 x 3 k-blocks).  g.partial / g.split_k are not used.
+cudaError_t launch_gemm_tail(const GemmArgs& g, int cs, cudaStream_t st) {
+    const int kb_all = (g.K + BK - 1) / BK;
+    if (g.M > BM || !g.out_f32 || (g.N & 3) || (g.ldo & 3) || (g.residual && (g.ldr & 3)) || (g.out_hi && (g.ldp & 3)))
+        return cudaErrorInvalidValue;
+    if (cs == 4 && g.N % 32 == 0 && (kb_all + 3) / 4 <= 3)
+        return g.passes == 3 ? launch_tail<32, true, 3, 4>(g, st) : launch_tail<32, false, 3, 4>(g, st);
+    if (cs == 8 && g.N % 48 == 0 && (kb_all + 7) / 8 <= 3)
+        return g.passes == 3 ? launch_tail<48, true, 3, 8>(g, st) : launch_tail<48, false, 3, 8>(g, st);
+    return cudaErrorNotSupported;
+}
 
 // Decode-sized GEMM with resident weights.  Returns cudaErrorNotSupported (nothing launched) when the shape does not
 // fit this kernel (more than one M tile, more tiles than SMs, K slice longer than the weight region); the caller then

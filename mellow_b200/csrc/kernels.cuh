@@ -60,7 +60,8 @@ struct DecodeAttnArgs {
     const int* done;                   // optional [B]: rows that already emitted the stop token skip their K/V stream
     float* part_acc; float* part_ml;   // [B][9][nsplit][64], [B][9][nsplit][2]
     bf16* out_hi; bf16* out_lo;        // [B,576]
-    int pf_keys;                       // L2 prefetch of the CTA's immutable K/V history before the dependency wait:
+    int variant;                       // 1 = warp-autonomous kernel (default), 0 = 64-key tile kernel
+    int pf_keys;                       // (tile kernel) L2 prefetch of the CTA's immutable K/V history before the dependency wait:
                                        // 0 = off, -1 = all of it, n > 0 = keys below n only
     TraceBuf* trace; unsigned trace_id;
 };

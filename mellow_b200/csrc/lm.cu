@@ -268,6 +268,226 @@ __global__ void __launch_bounds__(128, 3) decode_attention_kernel(const DecodeAt
     if (tid == 0) trace_close(a.trace, trec, a.trace_id);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Decode attention, warp-autonomous version (DecodeAttnArgs::variant = 1, the default).  What ncu showed on the tile
+// kernel above at B = 128 with 24-bit rows (profiles/r2_decode_attention_kv24_*): 38 % of the DRAM peak, 0.42 issued
+// instructions per scheduler cycle, 12 warps per SM, and stalls spread over the block barriers (four per 64-key tile),
+// the cp.async scoreboard and shared-memory latency -- a latency problem, not a bandwidth one.  Here the four warps of
+// the CTA never synchronise inside the loop: warp w streams the 16-key chunks w, w+4, w+8, ... of the CTA's key range
+// through a cp.async ring of its OWN, scores them (lane = key x half of the head dim, the three GQA query heads in
+// registers), runs the online softmax with shuffles, and accumulates P.V with lane = pair of head dims.  The four
+// (m, l, acc) states are merged once at the end.  About half the instructions per key of the tile kernel and no
+// block-wide barrier until the merge.
+constexpr int kAttnChunk = 16;                                    // keys per warp-private chunk
+template <typename T, int ST>
+struct DecodeSmemW {
+    static constexpr int ROWB = KvRowBytes<T>::value;
+    static constexpr int KROWB = ROWB + 16;                       // +16 B: conflict-free 16 B reads with lane = key
+    __align__(16) unsigned char k[4][ST][kAttnChunk][KROWB];
+    __align__(16) unsigned char v[4][ST][kAttnChunk][ROWB];
+    __align__(16) float p[4][3][kAttnChunk];
+    __align__(16) float red[4][3][kHeadDim];
+    float ml[4][3][2];
+};
+
+template <typename T, int ST>
+__global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const DecodeAttnArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using SM = DecodeSmemW<T, ST>;
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);
+    constexpr bool F24 = sizeof(T) == 3;
+    constexpr int ROWB = SM::ROWB;
+    constexpr int NCHB = ROWB / 16;               // 16-byte pieces per cached row
+    constexpr int E = F24 ? 8 : 16 / sizeof(T);   // values per 16 B piece of the part the score role walks
+    constexpr int NCH = kHeadDim / E;
+    const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned char* kb = reinterpret_cast<const unsigned char*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
+    const unsigned char* vb = reinterpret_cast<const unsigned char*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
+    const int k_begin = split * a.tps * 64;       // static ownership of the key range, like the tile kernel
+
+    // chunk i of this warp = keys [k_begin + 16 * (warp + 4 i), +16), staged in ring slot i % ST
+    auto load_chunk = [&](int i, int ctx_limit) {
+        const int key0 = k_begin + kAttnChunk * (warp + 4 * i);
+        unsigned char (*kd)[SM::KROWB] = sm.k[warp][i % ST];
+        unsigned char (*vd)[ROWB] = sm.v[warp][i % ST];
+        for (int c = lane; c < kAttnChunk * NCHB; c += 32) {
+            const int j = c / NCHB, ch = c - j * NCHB;
+            const bool ok = key0 + j < ctx_limit;
+            const size_t off = (size_t)(ok ? key0 + j : 0) * ROWB + ch * 16;
+            cp_async16(&kd[j][ch * 16], kb + off, ok);
+            cp_async16(&vd[j][ch * 16], vb + off, ok);
+        }
+    };
+    pdl_trigger();
+    unsigned trec = kTraceNone;
+    if (tid == 0) trec = trace_open(a.trace, a.trace_id);
+    // PDL: chunks that lie inside the prefill prefix are immutable history and are requested before the wait
+    int n_early = 0;
+#pragma unroll
+    for (int i = 0; i < ST; ++i) {
+        if (n_early == i && k_begin + kAttnChunk * (warp + 4 * i + 1) <= a.ctx_base && warp + 4 * i < a.tps * 4) {
+            load_chunk(i, a.ctx_base);
+            cp_async_commit();
+            n_early = i + 1;
+        }
+    }
+    pdl_wait();
+    if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, TR_WAITED);
+    const int step_now = a.d_step ? *a.d_step : 0;
+    if (a.done && a.done[b]) { cp_async_wait<0>(); return; }      // finished row: no K/V stream
+    const int ctx = a.ctx_base + step_now;
+    const int k_end = min(ctx, k_begin + a.tps * 64);
+    const int n_chunks = k_end > k_begin ? (k_end - k_begin + kAttnChunk - 1) / kAttnChunk : 0;
+    const int n_mine = n_chunks > warp ? (n_chunks - warp + 3) / 4 : 0;
+#pragma unroll
+    for (int i = 0; i < ST; ++i) {                                // fill the ring: one commit group per slot, empty or not
+        if (i >= n_early) {
+            if (i < n_mine) load_chunk(i, ctx);
+            cp_async_commit();
+        }
+    }
+    // score role: lane = (key j, half); each half owns every other 16 B piece of the key row
+    const int sj = lane >> 1, shalf = lane & 1;
+    float qreg[3][kHeadDim / 2];
+    {
+        const float* qb = a.q + (size_t)b * kHidden + (kvh * 3) * kHeadDim;
+#pragma unroll
+        for (int h = 0; h < 3; ++h)
+#pragma unroll
+            for (int i = 0; i < NCH / 2; ++i)
+#pragma unroll
+                for (int e = 0; e < E; e += 4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(qb + h * kHeadDim + (2 * i + shalf) * E + e);
+                    qreg[h][i * E + e] = t4.x * 0.125f; qreg[h][i * E + e + 1] = t4.y * 0.125f;      // head_dim^-0.5, exact
+                    qreg[h][i * E + e + 2] = t4.z * 0.125f; qreg[h][i * E + e + 3] = t4.w * 0.125f;
+                }
+    }
+    float m_run[3] = {-INFINITY, -INFINITY, -INFINITY}, l_run[3] = {0.f, 0.f, 0.f};
+    float acc[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    const int dp = lane * 2;                                      // PV role: this lane's pair of head dims
+    for (int i = 0; i < n_mine; ++i) {
+        cp_async_wait<ST - 1>();                                  // chunk i has landed (this thread's pieces) ...
+        __syncwarp();                                             // ... and everybody else's
+        const int slot = i % ST;
+        const int key0 = k_begin + kAttnChunk * (warp + 4 * i);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        {
+            const unsigned char* rowp = sm.k[warp][slot][sj];
+#pragma unroll
+            for (int c = 0; c < NCH / 2; ++c) {
+                if constexpr (F24) {
+                    const uint4 hv = *reinterpret_cast<const uint4*>(rowp + (2 * c + shalf) * 16);
+                    const uint2 lv = *reinterpret_cast<const uint2*>(rowp + 128 + (2 * c + shalf) * 8);
+                    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float k0 = f24_unpack_even(hw[p], p < 2 ? lv.x : lv.y, p & 1);
+                        const float k1 = f24_unpack_odd(hw[p], p < 2 ? lv.x : lv.y, p & 1);
+                        s0 += qreg[0][c * E + 2 * p] * k0; s1 += qreg[1][c * E + 2 * p] * k0; s2 += qreg[2][c * E + 2 * p] * k0;
+                        s0 += qreg[0][c * E + 2 * p + 1] * k1; s1 += qreg[1][c * E + 2 * p + 1] * k1; s2 += qreg[2][c * E + 2 * p + 1] * k1;
+                    }
+                } else {
+                    const T* kp = reinterpret_cast<const T*>(rowp) + (2 * c + shalf) * E;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const float kvv = kv_load(kp + e);
+                        s0 += qreg[0][c * E + e] * kvv; s1 += qreg[1][c * E + e] * kvv; s2 += qreg[2][c * E + e] * kvv;
+                    }
+                }
+            }
+        }
+        float sc[3] = {s0, s1, s2};
+        const bool ok = key0 + sj < ctx;
+        float al[3];
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            float s = sc[h] + __shfl_xor_sync(0xffffffffu, sc[h], 1);         // the two halves of the head dim
+            s = ok ? s : -INFINITY;
+            float mt = s;
+#pragma unroll
+            for (int o = 2; o < 32; o <<= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+            const float m_new = fmaxf(m_run[h], mt);                          // finite: the chunk holds >= 1 valid key
+            const float e = expf(s - m_new);
+            float ls = e;
+#pragma unroll
+            for (int o = 2; o < 32; o <<= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
+            al[h] = expf(m_run[h] - m_new);
+            l_run[h] = l_run[h] * al[h] + ls;
+            m_run[h] = m_new;
+            if (shalf == 0) sm.p[warp][h][sj] = e;
+        }
+        __syncwarp();
+        {
+            float x[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+            for (int jj = 0; jj < kAttnChunk; jj += 4) {
+                float4 p[3];
+#pragma unroll
+                for (int h = 0; h < 3; ++h) p[h] = *reinterpret_cast<const float4*>(&sm.p[warp][h][jj]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float v0, v1;
+                    const unsigned char* rowp = sm.v[warp][slot][jj + u];
+                    if constexpr (F24) {
+                        const uint32_t hw = *reinterpret_cast<const uint32_t*>(rowp + dp * 2);
+                        const uint32_t lb = *reinterpret_cast<const unsigned short*>(rowp + 128 + dp);
+                        v0 = f24_unpack_even(hw, lb, 0);
+                        v1 = f24_unpack_odd(hw, lb, 0);
+                    } else {
+                        const T* vp = reinterpret_cast<const T*>(rowp);
+                        v0 = kv_load(vp + dp); v1 = kv_load(vp + dp + 1);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 3; ++h) {
+                        const float pv = u == 0 ? p[h].x : (u == 1 ? p[h].y : (u == 2 ? p[h].z : p[h].w));
+                        x[h][0] += pv * v0; x[h][1] += pv * v1;
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+                acc[h][0] = acc[h][0] * al[h] + x[h][0];
+                acc[h][1] = acc[h][1] * al[h] + x[h][1];
+            }
+        }
+        __syncwarp();                                             // the slot and sm.p are reused
+        if (i + ST < n_mine) load_chunk(i + ST, ctx);
+        cp_async_commit();
+    }
+    cp_async_wait<0>();
+    if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, 5);           // this warp's keys consumed
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+        sm.red[warp][h][dp] = acc[h][0]; sm.red[warp][h][dp + 1] = acc[h][1];
+        if (lane == 0) { sm.ml[warp][h][0] = m_run[h]; sm.ml[warp][h][1] = l_run[h]; }
+    }
+    __syncthreads();
+    for (int e = tid; e < 3 * kHeadDim; e += 128) {               // merge the four warp states (fixed order)
+        const int h = e >> 6, d = e & 63;
+        float m = sm.ml[0][h][0];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) m = fmaxf(m, sm.ml[w][h][0]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float mw = sm.ml[w][h][0];
+            const float sc_w = mw == -INFINITY ? 0.f : expf(mw - m);          // a warp without keys contributes nothing
+            num += sc_w * sm.red[w][h][d];
+            den += sc_w * sm.ml[w][h][1];
+        }
+        if (a.nsplit == 1) {
+            store_planes1(a.out_hi, a.out_lo, (size_t)b * kHidden + (kvh * 3 + h) * kHeadDim + d, num / den);
+        } else {
+            const size_t o = (((size_t)b * kHeads + kvh * 3 + h) * a.nsplit + split);
+            a.part_acc[o * kHeadDim + d] = num;
+            if (d == 0) { a.part_ml[o * 2] = m; a.part_ml[o * 2 + 1] = den; }
+        }
+    }
+    if (tid == 0) trace_close(a.trace, trec, a.trace_id);
+}
+
 __global__ void __launch_bounds__(64) decode_combine_kernel(const DecodeAttnArgs a) {
     const int h = blockIdx.x, b = blockIdx.y, d = threadIdx.x;
     const size_t base = ((size_t)b * kHeads + h) * a.nsplit;
@@ -436,15 +656,31 @@ cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embe
     return launch_k(prefix_kernel, grid, dim3(144), 0, st, rows33, ids, embed, B, prefix);
 }
 
+template <typename T, int ST>
+cudaError_t launch_decode_attention_warp(const DecodeAttnArgs& a, dim3 grid, cudaStream_t st) {
+    static bool configured[kMaxDevices] = {};
+    auto kern = decode_attention_warp_kernel<T, ST>;
+    if (cudaError_t e = ensure_smem(kern, sizeof(DecodeSmemW<T, ST>), configured); e != cudaSuccess) return e;
+    return launch_k(kern, grid, dim3(128), sizeof(DecodeSmemW<T, ST>), st, a);
+}
+
 cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
     dim3 grid(a.nsplit, kKvHeads, a.B);
-    static bool c0[kMaxDevices] = {}, c1[kMaxDevices] = {}, c2[kMaxDevices] = {};
-    if (cudaError_t e = ensure_smem(decode_attention_kernel<float>, sizeof(DecodeSmem<float>), c0); e != cudaSuccess) return e;
-    if (cudaError_t e = ensure_smem(decode_attention_kernel<bf16>, sizeof(DecodeSmem<bf16>), c1); e != cudaSuccess) return e;
-    if (cudaError_t e = ensure_smem(decode_attention_kernel<kv24>, sizeof(DecodeSmem<kv24>), c2); e != cudaSuccess) return e;
-    cudaError_t e = a.kv_fmt == kKvBf16 ? launch_k(decode_attention_kernel<bf16>, grid, dim3(128), sizeof(DecodeSmem<bf16>), st, a)
-                  : a.kv_fmt == kKvF24 ? launch_k(decode_attention_kernel<kv24>, grid, dim3(128), sizeof(DecodeSmem<kv24>), st, a)
-                                       : launch_k(decode_attention_kernel<float>, grid, dim3(128), sizeof(DecodeSmem<float>), st, a);
+    cudaError_t e;
+    if (a.variant == 1) {
+        // ring depth 2: 3 CTAs (12 warps) per SM for every row format
+        e = a.kv_fmt == kKvBf16 ? launch_decode_attention_warp<bf16, 3>(a, grid, st)
+          : a.kv_fmt == kKvF24 ? launch_decode_attention_warp<kv24, 2>(a, grid, st)
+                               : launch_decode_attention_warp<float, 2>(a, grid, st);
+    } else {
+        static bool c0[kMaxDevices] = {}, c1[kMaxDevices] = {}, c2[kMaxDevices] = {};
+        if (cudaError_t e0 = ensure_smem(decode_attention_kernel<float>, sizeof(DecodeSmem<float>), c0); e0 != cudaSuccess) return e0;
+        if (cudaError_t e0 = ensure_smem(decode_attention_kernel<bf16>, sizeof(DecodeSmem<bf16>), c1); e0 != cudaSuccess) return e0;
+        if (cudaError_t e0 = ensure_smem(decode_attention_kernel<kv24>, sizeof(DecodeSmem<kv24>), c2); e0 != cudaSuccess) return e0;
+        e = a.kv_fmt == kKvBf16 ? launch_k(decode_attention_kernel<bf16>, grid, dim3(128), sizeof(DecodeSmem<bf16>), st, a)
+          : a.kv_fmt == kKvF24 ? launch_k(decode_attention_kernel<kv24>, grid, dim3(128), sizeof(DecodeSmem<kv24>), st, a)
+                               : launch_k(decode_attention_kernel<float>, grid, dim3(128), sizeof(DecodeSmem<float>), st, a);
+    }
     if (e != cudaSuccess || a.nsplit == 1) return e;
     return launch_k(decode_combine_kernel, dim3(kHeads, a.B), dim3(64), 0, st, a);
 }

@@ -333,18 +333,50 @@ def test_kv24_policy_keeps_token_identity_and_logit_tolerance(engine24, engine, 
     assert torch.equal(got, want)
 
 
-@pytest.mark.parametrize("which", ["engine", "engine24"])
-def test_l2_prefetch_of_the_kv_history_does_not_change_results(which, request, inputs, golden):
-    """Decode attention asks the L2 for its immutable K/V history while it waits for the QKV GEMM (option
-    "kv_prefetch"): a pure hint, ids must be identical with it off, on, and limited to the prefix."""
+@pytest.mark.parametrize("which", ["engine", "engine24", "engine_fast"])
+def test_decode_attention_variants_agree(which, request, inputs, golden):
+    """Decode attention exists as the warp-autonomous kernel (default) and the 64-key tile kernel of round 1 (with an
+    optional L2 prefetch of the K/V history): same greedy ids from all of them (fp32 summation order differs)."""
     eng = request.getfixturevalue(which)
+    ref = None
     try:
-        for pf in (0, -1, 389):
+        for variant, pf in ((1, 0), (0, 0), (0, -1), (0, 389)):
+            eng.set_option("attn_variant", variant)
             eng.set_option("kv_prefetch", pf)
             toks = eng.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 12).cpu()
-            assert toks.tolist() == golden["tokens"].tolist(), f"kv_prefetch={pf}"
+            if which == "engine_fast":                          # no identity claim against the fp32 golden for policy fast
+                ref = toks if ref is None else ref
+                assert toks.shape == ref.shape
+            else:
+                assert toks.tolist() == golden["tokens"].tolist(), f"attn_variant={variant} kv_prefetch={pf}"
     finally:
-        eng.set_option("kv_prefetch", -1)
+        eng.set_option("attn_variant", 1)
+        eng.set_option("kv_prefetch", 0)
+
+
+@pytest.mark.parametrize("which", ["engine", "engine24"])
+def test_decode_tails_keep_ids_and_logits(which, request, inputs, oracle_taps, golden):
+    """Option "decode_tails": o_proj / down as cluster split-K GEMMs (distributed-shared-memory reduce-scatter) with the
+    residual add and the deferred RMSNorm inside -- 5 kernels per layer instead of 7.  Same ids, logits within tolerance,
+    for a ragged 3-row batch too."""
+    eng = request.getfixturevalue(which)
+    try:
+        eng.set_option("decode_tails", 1)
+        toks = eng.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 12).cpu()
+        assert toks.tolist() == golden["tokens"].tolist()
+        eng.set_prefix(oracle_taps["prefix"])
+        eng.prefill(2, want_logits=False)
+        forced = torch.from_numpy(golden["tokens"]).to(torch.int32)
+        own, dump = eng.decode(2, 12, dump_logits=True, forced_tokens=forced)
+        got = torch.gather(dump.cpu(), 2, torch.from_numpy(golden["top8_ids"]))
+        assert maxerr(got, golden["top8_vals"]) < LOGIT_TOL
+        w1 = torch.cat([inputs["wave1"], inputs["wave1"][:1]])
+        w2 = torch.cat([inputs["wave2"], inputs["wave2"][:1]])
+        ids = torch.cat([inputs["ids"], inputs["ids"][:1]])
+        want = golden["tokens"].tolist()
+        assert eng.generate(w1, w2, ids, 12).cpu().tolist() == [want[0], want[1], want[0]]
+    finally:
+        eng.set_option("decode_tails", 0)
 
 
 def test_in_kernel_timeline_records_every_decode_kernel(engine, inputs, golden):

@@ -52,6 +52,8 @@ long long mb_workspace_bytes(void* h);
  *   "decode_unfused" (0) 1 = use the generic per-layer decode path (the one batches > 128 rows take) for every batch
  *   "skip_finished"  (1) rows that emitted eos_id stop streaming their KV cache (their later tokens are not meaningful);
  *                        0 = every row keeps decoding until all rows have stopped, like the reference loop
+ *   "prefill_attn"   (1) causal prefill attention: 1 = tcgen05 kernel (TMA-fed bf16 operand planes, S / O in TMEM),
+ *                        0 = the mma.sync kernel of round 1
  *   "attn_variant"   (1) decode attention kernel: 1 = warp-autonomous (each warp streams its own 16-key chunks, no block
  *                        barrier in the loop), 0 = the 64-key tile kernel of round 1
  *   "kv_prefetch"    (0) tile kernel only: keys per (row, kv head) stream prefetched into L2 while the kernel waits for

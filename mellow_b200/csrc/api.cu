@@ -197,6 +197,7 @@ struct Handle {
     // LM workspace (M = max_batch*389 rows)
     float *x = nullptr, *q = nullptr, *logits = nullptr;
     bf16 *la_hi = nullptr, *la_lo = nullptr, *lb_hi = nullptr, *lb_lo = nullptr, *lh_hi = nullptr, *lh_lo = nullptr;
+    bf16 *qp_hi = nullptr, *qp_lo = nullptr, *kp_hi = nullptr, *kp_lo = nullptr, *vt_hi = nullptr, *vt_lo = nullptr;   // tcgen05 prefill attention operands
     float *ssq_a = nullptr, *ssq_b = nullptr;   // deferred-RMSNorm partial sums of squares [parts][rows] (o_proj -> gate/up, down -> QKV)
     void *kcache = nullptr, *vcache = nullptr;
     size_t kv_layer_elems = 0;
@@ -211,12 +212,14 @@ struct Handle {
     cudaGraphExec_t graph = nullptr;
     int g_B = 0, g_max_len = 0, g_eos = 0, g_launches = 0;
     float g_temp = 0.f;
+    const int* g_forced = nullptr;
     cudaStream_t g_stream = nullptr;
     cudaStream_t own_stream = nullptr;   // used when the caller passes NULL (the legacy stream cannot be graph-captured)
     int kv_fmt = kKvF32;                 // KV-cache row format (common.cuh)
     // mb_set_option (defaults from the environment switches above)
     bool use_graph = true, decode_unfused = false, skip_finished = true;
     int kv_prefetch = 0;                 // (tile kernel) keys per stream prefetched into L2 before the dependency wait; -1 = all
+    int prefill_attn = 1;                // causal prefill attention: 1 = tcgen05 kernel (attn_umma.cu), 0 = mma.sync kernel
     int attn_variant = 1;                // decode attention kernel: 1 = warp-autonomous, 0 = 64-key tiles (lm.cu)
     int decode_tails = 0;                // o_proj / down as cluster split-K tails with the norm deferred (gemm_skinny.cu)
     int wide_tiles = -1;                 // decode split-K tiling: -1 = by policy, 0 = 16-column tiles, 1 = 32-column tiles
@@ -554,6 +557,8 @@ int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_
     const LmLayerW& k = h->w.layer[l];
     const int M = B * rows_per_seq;
     const bool defer = !decode && h->engine == 1 && M >= 1024;
+    const bool umma_attn = !decode && h->engine == 1 && h->prefill_attn == 1;
+    const int vt_ld = (rows_per_seq + 63) / 64 * 64;
     const int parts = defer ? gemm_umma_ssq_parts(M, kHidden) : 0;
     if (!(defer && planes_ready))
         MB_TRY(run_norm(h, NORM_RMS, h->x, k.ln1, nullptr, M, kHidden, h->la_hi, h->la_lo, nullptr, 1, 0, 0, st));
@@ -561,6 +566,12 @@ int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_
         GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.qkv, kHidden, M, kQkvDim, kHidden);
         if (defer && planes_ready) { g.ssq_in = h->ssq_b; g.ssq_parts = parts; g.ssq_ld = M; }
         g.q_out = h->q;
+        if (umma_attn) {                                 // operand planes of the tcgen05 attention kernel instead of fp32 q
+            g.q_out = nullptr;
+            g.qp_hi = h->qp_hi; g.qp_lo = lo_of(h, h->qp_lo);
+            g.kp_hi = h->kp_hi; g.kp_lo = lo_of(h, h->kp_lo);
+            g.vt_hi = h->vt_hi; g.vt_lo = lo_of(h, h->vt_lo); g.vt_ld = vt_ld;
+        }
         g.k_cache = kv_layer(h, h->kcache, l); g.v_cache = kv_layer(h, h->vcache, l);
         g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
         g.rows_per_seq = rows_per_seq;
@@ -571,6 +582,10 @@ int lm_layer(Handle* h, int l, int B, int rows_per_seq, bool decode, cudaStream_
     }
     if (decode) {
         MB_TRY(run_decode_attention(h, l, B, st));
+    } else if (umma_attn) {
+        PrefillAttnPlanes p{h->qp_hi, lo_of(h, h->qp_lo), h->kp_hi, lo_of(h, h->kp_lo), h->vt_hi, lo_of(h, h->vt_lo), vt_ld};
+        MB_CK(h, launch_prefill_attention_umma(p, B, rows_per_seq, h->la_hi, lo_of(h, h->la_lo), st));
+        h->launches++;
     } else {
         MB_CK(h, launch_prefill_attention_mma(h->q, kv_layer(h, h->kcache, l), kv_layer(h, h->vcache, l), h->kv_fmt, B,
                                               rows_per_seq, h->t_max, h->la_hi, lo_of(h, h->la_lo), st));
@@ -688,18 +703,18 @@ int do_decode(Handle* h, int B, int max_len, float temperature, float top_p, int
     MB_CK(h, cudaMemsetAsync(h->d_tokens, 0, sizeof(int) * (size_t)B * max_len, st));
     // step 0: logits come from the prefill
     MB_TRY(sample_and_advance(h, B, max_len, temperature, top_p, eos_id, logits_dump, forced, st));
-    const bool use_graph = !logits_dump && !forced && h->use_graph;
+    const bool use_graph = !logits_dump && h->use_graph;      // teacher forcing replays the graph too (the pointer is part of its key)
     int stop = -1;
     if (use_graph && max_len > 1) {
         const bool hit = h->graph && h->g_B == B && h->g_max_len == max_len && h->g_eos == eos_id &&
-                         h->g_temp == temperature && h->g_stream == st;
+                         h->g_temp == temperature && h->g_stream == st && h->g_forced == forced;
         if (!hit) {
             drop_graph(h);
             cudaGraph_t graph = nullptr;
             const long long before = h->launches;
             MB_CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
             int rc = decode_step(h, B, /*fused=*/true, st);
-            if (rc == 0) rc = sample_and_advance(h, B, max_len, temperature, top_p, eos_id, nullptr, nullptr, st);
+            if (rc == 0) rc = sample_and_advance(h, B, max_len, temperature, top_p, eos_id, nullptr, forced, st);
             cudaError_t ce = cudaStreamEndCapture(st, &graph);
             if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
             MB_CK(h, ce);
@@ -707,7 +722,7 @@ int do_decode(Handle* h, int B, int max_len, float temperature, float top_p, int
             h->launches = before;
             MB_CK(h, cudaGraphInstantiate(&h->graph, graph, 0));
             cudaGraphDestroy(graph);
-            h->g_B = B; h->g_max_len = max_len; h->g_eos = eos_id; h->g_temp = temperature; h->g_stream = st;
+            h->g_B = B; h->g_max_len = max_len; h->g_eos = eos_id; h->g_temp = temperature; h->g_stream = st; h->g_forced = forced;
         }
     }
     for (int s = 1; s < max_len; ++s) {
@@ -809,6 +824,12 @@ static int create_body(Handle* h) {
     MB_TRY(dev_alloc(h, &h->la_lo, M * kHidden));
     MB_TRY(dev_alloc(h, &h->lb_hi, M * kHidden));
     MB_TRY(dev_alloc(h, &h->lb_lo, M * kHidden));
+    MB_TRY(dev_alloc(h, &h->qp_hi, M * kHidden));
+    MB_TRY(dev_alloc(h, &h->qp_lo, M * kHidden));
+    MB_TRY(dev_alloc(h, &h->kp_hi, M * kKvHeads * kHeadDim));
+    MB_TRY(dev_alloc(h, &h->kp_lo, M * kKvHeads * kHeadDim));
+    MB_TRY(dev_alloc(h, &h->vt_hi, (M + 64 * B + 64) * kKvHeads * kHeadDim));
+    MB_TRY(dev_alloc(h, &h->vt_lo, (M + 64 * B + 64) * kKvHeads * kHeadDim));
     MB_TRY(dev_alloc(h, &h->ssq_a, M * 12));
     MB_TRY(dev_alloc(h, &h->ssq_b, M * 12));
     MB_TRY(dev_alloc(h, &h->lh_hi, M * kInter));
@@ -896,6 +917,7 @@ int mb_set_option(void* hv, const char* name, int value) {
     else if (n == "wide_tiles") h->wide_tiles = value;
     else if (n == "decode_tails") h->decode_tails = value;
     else if (n == "attn_variant") h->attn_variant = value;
+    else if (n == "prefill_attn") h->prefill_attn = value;
     else if (n == "gemm_engine") {
 #ifdef MB_LAB
         if (value != 0 && value != 1) return fail(h, "unknown GEMM engine");

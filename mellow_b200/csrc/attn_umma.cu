@@ -1,0 +1,320 @@
+// Causal prefill attention on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, operands by TMA).
+// SmolLM2: 9 query heads, 3 kv heads (GQA), head_dim 64; reference path: transformers modeling_llama.py:276-285 called
+// cache-less from mellow/wrapper.py:217 (pure causal mask, pads attended).
+//
+// Operands.  The QKV GEMM epilogue (gemm.cuh, EPI_QKV_ROPE) leaves, next to the KV cache, bf16 hi/lo PLANES of the roped
+// queries (scaled by 64^-0.5), the roped keys and the TRANSPOSED values, so this kernel converts nothing: every tile is
+// one cp.async.bulk.tensor into 128B-swizzled shared memory, consumed by UMMA descriptors.
+//   * the M = 128 rows of a tile are 42 consecutive queries x the 3 query heads that share a kv head (row = 3*s + hh:
+//     a 4-D tensor map over [M][kv head][hh][64] walks them), so K / V are streamed once for the three heads and only
+//     2 of the 128 rows are padding (a per-head 128-query tiling would waste 31 % of S = 389);
+//   * S = Q K^T: M 128 x N 64 keys x K 64, accumulator in TMEM columns [0,64);
+//   * softmax: four warps, one accumulator row per thread (tcgen05.ld), fp32 online softmax; P is written as bf16 hi/lo
+//     into shared memory in the K-major 128B-swizzle layout (chunk ^ (row & 7)) the next MMA reads as its A operand;
+//   * O += P V: M 128 x N 64 x K 64 keys, B operand = the V^T tile (keys contiguous), accumulator in TMEM columns
+//     [64,128); when the running maximum moves, the softmax warps rescale O in TMEM (tcgen05.ld / tcgen05.st);
+//   * split policy: every contraction is 3 MMAs (hi*hi + hi*lo + lo*hi) like the GEMMs.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = softmax / epilogue
+// (TMEM lane quadrant = warp % 4).  Inside a CTA the phases of one 64-key tile are serial (TMA -> S -> softmax -> PV);
+// a CTA needs 97 KB of shared memory and 128 TMEM columns, so TWO CTAs share an SM and one's MMAs overlap the other's
+// softmax.  Causal work per (batch, kv head): 40 tile visits of 64 keys for S = 389.
+#include "kernels.cuh"
+#include "umma.cuh"
+
+namespace mb {
+
+namespace {
+
+using namespace umma;
+
+constexpr int kQPT = 42;                       // queries per row tile (x 3 heads = 126 rows)
+constexpr int kKT = 64;                        // keys per tile = one 128-byte swizzle row of the PV operands
+constexpr uint32_t kTile = 128 * 128;          // 16 KB: 128 rows x 64 bf16 (Q tile, P tile)
+constexpr uint32_t kTileK = 64 * 128;          // 8 KB: 64 keys x 64 head dims (K tile), 64 head dims x 64 keys (V^T tile)
+constexpr uint32_t kQBytes = 64 * 3 * kQPT * 2;
+constexpr int kAttnThreads = 192;
+
+struct AttnUmmaArgs {
+    int S, B;
+    bf16* out_hi; bf16* out_lo;                // [B*S][576]
+};
+
+template <bool SPLIT>
+struct AttnCfg {
+    static constexpr uint32_t P = SPLIT ? 2 : 1;
+    static constexpr uint32_t OFF_Q = 0;
+    static constexpr uint32_t OFF_K = OFF_Q + P * kTile;
+    static constexpr uint32_t OFF_V = OFF_K + P * kTileK;
+    static constexpr uint32_t OFF_P = OFF_V + P * kTileK;
+    static constexpr uint32_t OFF_BAR = OFF_P + P * kTile;
+    static constexpr size_t SMEM = OFF_BAR + 128 + 1024;
+};
+
+__device__ __forceinline__ void pack8(const float* v, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        bf16 ah, al, bh, bl;
+        split_bf16(v[2 * j], ah, al);
+        split_bf16(v[2 * j + 1], bh, bl);
+        __nv_bfloat162 h2, l2;
+        h2.x = ah; h2.y = bh; l2.x = al; l2.y = bl;
+        h[j] = *reinterpret_cast<uint32_t*>(&h2);
+        l[j] = *reinterpret_cast<uint32_t*>(&l2);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+prefill_attention_umma_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
+                              const __grid_constant__ CUtensorMap tm_k_hi, const __grid_constant__ CUtensorMap tm_k_lo,
+                              const __grid_constant__ CUtensorMap tm_v_hi, const __grid_constant__ CUtensorMap tm_v_lo,
+                              const AttnUmmaArgs a) {
+    using C = AttnCfg<SPLIT>;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* q_s = smem + C::OFF_Q;      // [P][128 x 64]     rows = 3*s_local + hh
+    unsigned char* k_s = smem + C::OFF_K;      // [P][64 keys x 64]
+    unsigned char* v_s = smem + C::OFF_V;      // [P][64 dims x 64 keys]
+    unsigned char* p_s = smem + C::OFF_P;      // [P][128 rows x 64 keys]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+    uint64_t *q_full = bars, *k_full = bars + 1, *v_full = bars + 2, *s_full = bars + 3, *p_full = bars + 4, *o_full = bars + 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (a.S + kQPT - 1) / kQPT;
+    const int tile = n_tiles - 1 - (int)blockIdx.x;             // long tiles (late queries) first
+    const int kvh = blockIdx.y, b = blockIdx.z;
+    const int s0 = tile * kQPT;
+    const int s_last = min(a.S - 1, s0 + kQPT - 1);
+    const int n_kt = s_last / kKT + 1;                          // causal: keys 0..s_last
+
+    pdl_trigger();
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1); mbar_init(k_full, 1); mbar_init(v_full, 1);
+        mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_q_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_k_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_v_hi) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            pdl_wait();                                          // the planes are written by the preceding QKV GEMM
+            mbar_expect_tx(q_full, C::P * kQBytes);
+            tma_load_4d(q_s, &tm_q_hi, q_full, 0, 0, kvh, b * a.S + s0);
+            if (SPLIT) tma_load_4d(q_s + kTile, &tm_q_lo, q_full, 0, 0, kvh, b * a.S + s0);
+            auto load_k = [&](int it) {
+                mbar_expect_tx(k_full, C::P * kTileK);
+                tma_load_3d(k_s, &tm_k_hi, k_full, 0, it * kKT, b * kKvHeads + kvh);
+                if (SPLIT) tma_load_3d(k_s + kTileK, &tm_k_lo, k_full, 0, it * kKT, b * kKvHeads + kvh);
+            };
+            auto load_v = [&](int it) {
+                mbar_expect_tx(v_full, C::P * kTileK);
+                tma_load_3d(v_s, &tm_v_hi, v_full, it * kKT, 0, b * kKvHeads + kvh);
+                if (SPLIT) tma_load_3d(v_s + kTileK, &tm_v_lo, v_full, it * kKT, 0, b * kKvHeads + kvh);
+            };
+            load_k(0);
+            load_v(0);
+            for (int it = 0; it + 1 < n_kt; ++it) {
+                mbar_wait(s_full, it & 1);                       // S of tile `it` has retired: the K tile is free
+                load_k(it + 1);
+                mbar_wait(o_full, it & 1);                       // PV of tile `it` has retired: the V^T tile is free
+                load_v(it + 1);
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // instruction descriptor: D = f32, A = B = bf16, both K-major, N = 64, M = 128 (the same for S and for O)
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(64 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            constexpr uint32_t idesc_s = idesc, idesc_o = idesc;
+            const uint32_t qh = umma_desc_lo(smem_u32(q_s)), ql = qh + (kTile >> 4);
+            const uint32_t kh = umma_desc_lo(smem_u32(k_s)), kl = kh + (kTileK >> 4);
+            const uint32_t vh = umma_desc_lo(smem_u32(v_s)), vl = vh + (kTileK >> 4);
+            const uint32_t ph = umma_desc_lo(smem_u32(p_s)), pl = ph + (kTile >> 4);
+            mbar_wait(q_full, 0);
+            for (int it = 0; it < n_kt; ++it) {
+                mbar_wait(k_full, it & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {                    // S = (Q/8) K^T over the 64 head dims
+                    const uint64_t dqh = umma_desc_join(qh + 2 * k), dkh = umma_desc_join(kh + 2 * k);
+                    umma_bf16(tmem_s, dqh, dkh, idesc_s, k > 0 ? 1u : 0u);
+                    if (SPLIT) {
+                        umma_bf16(tmem_s, dqh, umma_desc_join(kl + 2 * k), idesc_s, 1u);
+                        umma_bf16(tmem_s, umma_desc_join(ql + 2 * k), dkh, idesc_s, 1u);
+                    }
+                }
+                umma_commit(s_full);
+                mbar_wait(v_full, it & 1);
+                mbar_wait(p_full, it & 1);                       // P written (and O rescaled) by the softmax warps
+                tc_fence_after();
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {                 // O += P V over the 64 keys of the tile
+                    const uint64_t dph = umma_desc_join(ph + 2 * ks), dvh = umma_desc_join(vh + 2 * ks);
+                    umma_bf16(tmem_o, dph, dvh, idesc_o, (it > 0 || ks > 0) ? 1u : 0u);
+                    if (SPLIT) {
+                        umma_bf16(tmem_o, dph, umma_desc_join(vl + 2 * ks), idesc_o, 1u);
+                        umma_bf16(tmem_o, umma_desc_join(pl + 2 * ks), dvh, idesc_o, 1u);
+                    }
+                }
+                umma_commit(o_full);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int r = quad * 32 + lane;                          // accumulator row = TMEM lane
+        const int hh = r % 3;
+        const int sq = s0 + r / 3;
+        const bool row_ok = r < 3 * kQPT && sq < a.S;
+        const int s_eff = row_ok ? sq : s0;                      // padding rows follow the tile's first query (finite values)
+        // tcgen05.ld is warp-collective: loop bounds follow the warp's LAST row, the per-lane causal mask is applied inside
+        const int s_hi = min(s_last, s0 + (quad * 32 + 31) / 3);
+        const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+        pdl_wait();                                              // the output planes are an operand of the preceding GEMM
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int it = 0; it < n_kt; ++it) {
+            mbar_wait(s_full, it & 1);
+            tc_fence_after();
+            const int key0 = it * kKT;
+            // pass 1: row maximum over the keys this query may see
+            float mt = -INFINITY;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kKT; c0 += 16) {
+                if (key0 + c0 > s_hi) break;                     // warp-uniform
+                float v[16];
+                tmem_ld16(tmem_s + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) mt = fmaxf(mt, key0 + c0 + j <= s_eff ? v[j] : -INFINITY);
+            }
+            const float m_new = fmaxf(m_run, mt);                // finite from the first tile on (key 0 <= every query)
+            const float alpha = expf(m_run - m_new);
+            // pass 2: P = exp(S - m), as bf16 hi/lo in the K-major 128B-swizzle layout of the PV A operand
+            float lsum = 0.f;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kKT; c0 += 16) {
+                float v[16];
+                if (key0 + c0 <= s_hi) {                         // warp-uniform
+                    tmem_ld16(tmem_s + lane_addr + (uint32_t)c0, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        v[j] = key0 + c0 + j <= s_eff ? expf(v[j] - m_new) : 0.f;
+                        lsum += v[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) v[j] = 0.f;
+                }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int ch = (c0 >> 3) + half;              // 16-byte chunk (8 keys) of the 128-byte row
+                    const uint32_t off = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
+                    uint4 hi, lo;
+                    pack8(v + 8 * half, hi, lo);
+                    *reinterpret_cast<uint4*>(p_s + off) = hi;
+                    if (SPLIT) *reinterpret_cast<uint4*>(p_s + kTile + off) = lo;
+                }
+            }
+            l_run = l_run * alpha + lsum;
+            m_run = m_new;
+            if (it > 0) {                                        // rescale the running output (PV of the previous tile has retired:
+#pragma unroll 1                                                 // S of this tile was issued after it)
+                for (int c0 = 0; c0 < kHeadDim; c0 += 16) {
+                    float o[16];
+                    tmem_ld16(tmem_o + lane_addr + (uint32_t)c0, o);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] *= alpha;
+                    tmem_st16(tmem_o + lane_addr + (uint32_t)c0, o);
+                }
+                tmem_st_wait();
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // P (generic-proxy stores) -> UMMA (async proxy)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(o_full, (n_kt - 1) & 1);
+        tc_fence_after();
+        const float inv = 1.0f / l_run;
+        if (row_ok) {
+            const size_t ob = ((size_t)b * a.S + sq) * kHidden + (size_t)(kvh * 3 + hh) * kHeadDim;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kHeadDim; c0 += 16) {
+                float o[16];
+                tmem_ld16(tmem_o + lane_addr + (uint32_t)c0, o);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) o[j] *= inv;
+                store_planes8(a.out_hi, a.out_lo, ob + c0, o);
+                store_planes8(a.out_hi, a.out_lo, ob + c0 + 8, o + 8);
+            }
+        } else {
+#pragma unroll 1
+            for (int c0 = 0; c0 < kHeadDim; c0 += 16) {          // keep the warp's tcgen05.ld sequence uniform
+                float o[16];
+                tmem_ld16(tmem_o + lane_addr + (uint32_t)c0, o);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(128) : "memory");
+    }
+}
+
+template <bool SPLIT>
+cudaError_t launch_attn(const PrefillAttnPlanes& p, int B, int S, bf16* out_hi, bf16* out_lo, cudaStream_t st) {
+    using C = AttnCfg<SPLIT>;
+    auto kern = prefill_attention_umma_kernel<SPLIT>;
+    static bool configured[kMaxDevices] = {};
+    if (cudaError_t e = ensure_smem(kern, C::SMEM, configured); e != cudaSuccess) return e;
+    const long long M = (long long)B * S;
+    CUtensorMap tq[2], tk[2], tv[2];
+    for (int pl = 0; pl < (SPLIT ? 2 : 1); ++pl) {
+        {   // queries: [M][kv head 3][hh 3][64]
+            const long long dims[4] = {kHeadDim, 3, kKvHeads, M};
+            const long long strides[4] = {1, kHeadDim, 3 * kHeadDim, kHidden};
+            const int box[4] = {kHeadDim, 3, 1, kQPT};
+            if (!make_map_nd(&tq[pl], pl ? p.qp_lo : p.qp_hi, 4, dims, strides, box)) return cudaErrorInvalidValue;
+        }
+        {   // keys: [B*3][S][64]
+            const long long dims[3] = {kHeadDim, S, (long long)B * kKvHeads};
+            const long long strides[3] = {1, kHeadDim, (long long)S * kHeadDim};
+            const int box[3] = {kHeadDim, kKT, 1};               // 64 keys x 64 head dims
+            if (!make_map_nd(&tk[pl], pl ? p.kp_lo : p.kp_hi, 3, dims, strides, box)) return cudaErrorInvalidValue;
+        }
+        {   // values, transposed: [B*3][64][S (row pitch vt_ld)]
+            const long long dims[3] = {S, kHeadDim, (long long)B * kKvHeads};
+            const long long strides[3] = {1, p.vt_ld, (long long)kHeadDim * p.vt_ld};
+            const int box[3] = {64, kHeadDim, 1};
+            if (!make_map_nd(&tv[pl], pl ? p.vt_lo : p.vt_hi, 3, dims, strides, box)) return cudaErrorInvalidValue;
+        }
+    }
+    if (!SPLIT) { tq[1] = tq[0]; tk[1] = tk[0]; tv[1] = tv[0]; }
+    AttnUmmaArgs a{S, B, out_hi, out_lo};
+    dim3 grid((unsigned)((S + kQPT - 1) / kQPT), kKvHeads, (unsigned)B);
+    return launch_k(kern, grid, dim3(kAttnThreads), C::SMEM, st, tq[0], tq[1], tk[0], tk[1], tv[0], tv[1], a);
+}
+
+}  // namespace
+
+cudaError_t launch_prefill_attention_umma(const PrefillAttnPlanes& p, int B, int S, bf16* out_hi, bf16* out_lo,
+                                          cudaStream_t st) {
+    if (!encode_fn() || (p.vt_ld & 7) || S < 1) return cudaErrorInvalidValue;
+    return out_lo ? launch_attn<true>(p, B, S, out_hi, out_lo, st) : launch_attn<false>(p, B, S, out_hi, out_lo, st);
+}
+
+}  // namespace mb

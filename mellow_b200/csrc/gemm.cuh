@@ -36,7 +36,11 @@ struct GemmArgs {
     // EPI_QKV_ROPE (SmolLM2 attention input, transformers modeling_llama.py:262-270,138-168):
     // columns [0,576) q, [576,768) k, [768,960) v.  q/k head dims are stored pair-interleaved (2i <- i, 2i+1 <- i+32;
     // the weight rows are permuted at pack time), so rotate-half pairs sit in adjacent accumulator columns.
-    float* q_out;                                     // [M,576] roped queries
+    float* q_out;                                     // [M,576] roped queries (may be null when the planes below are written)
+    // prefill with the tcgen05 attention kernel (attn_umma.cu): the operands it streams with TMA, as bf16 hi/lo planes
+    bf16* qp_hi; bf16* qp_lo;                         // [M,576] roped queries * head_dim^-0.5 (exact power of two)
+    bf16* kp_hi; bf16* kp_lo;                         // [B][3][rows_per_seq][64] roped keys
+    bf16* vt_hi; bf16* vt_lo; int vt_ld;              // [B][3][64][vt_ld] values, TRANSPOSED (keys contiguous)
     void* k_cache; void* v_cache;                     // this layer: [B][3][t_max][64], float or bf16
     const float* rope_cos; const float* rope_sin;     // [kMaxPos][32]
     int rows_per_seq;                                 // m = b*rows_per_seq + s
@@ -187,14 +191,36 @@ __device__ __forceinline__ void epilogue_row16_qkv(const GemmArgs& g, int m, int
         }
     }
     if (n < kHidden) {
-        float* o = g.q_out + (size_t)m * kHidden + n;
+        if (g.q_out) {
+            float* o = g.q_out + (size_t)m * kHidden + n;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) st4(o + j, v + j);
+            for (int j = 0; j < 16; j += 4) st4(o + j, v + j);
+        }
+        if (g.qp_hi) {
+            float qs[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) qs[j] = v[j] * 0.125f;
+            store_planes8(g.qp_hi, g.qp_lo, (size_t)m * kHidden + n, qs);
+            store_planes8(g.qp_hi, g.qp_lo, (size_t)m * kHidden + n + 8, qs + 8);
+        }
     } else {
         const int nn = n - kHidden;
         const bool is_v = nn >= kKvHeads * kHeadDim;
         const int c2 = is_v ? nn - kKvHeads * kHeadDim : nn;
         const int kvh = c2 >> 6, dd = c2 & 63;
+        if (g.kp_hi) {
+            if (!is_v) {
+                const size_t o = (((size_t)b * kKvHeads + kvh) * g.rows_per_seq + s) * kHeadDim + dd;
+                store_planes8(g.kp_hi, g.kp_lo, o, v);
+                store_planes8(g.kp_hi, g.kp_lo, o + 8, v + 8);
+            } else {
+                // transposed: lanes of a warp hold consecutive rows = consecutive keys, so each of these 2-byte stores
+                // is one 64-byte run per warp
+                const size_t o = (((size_t)b * kKvHeads + kvh) * kHeadDim + dd) * g.vt_ld + s;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) store_planes1(g.vt_hi, g.vt_lo, o + (size_t)j * g.vt_ld, v[j]);
+            }
+        }
         const size_t off = (((size_t)b * kKvHeads + kvh) * g.t_max + pos) * kHeadDim + dd;
         void* base = is_v ? g.v_cache : g.k_cache;
         if (g.kv_fmt == kKvF24) {                                    // 16 values: 32 B of upper halves + 16 B of mantissa bytes
@@ -296,10 +322,17 @@ __device__ __forceinline__ void epilogue_row16(const GemmArgs& g, int m, int n, 
     }
 }
 
-// consumer side of the deferred RMSNorm: rstd of row m from the producer's partial sums of squares (fixed order)
+// consumer side of the deferred RMSNorm: rstd of row m from the producer's partial sums of squares.  All loads are
+// issued before the first add (a loop with a running sum serialises one L2 round trip per partial: measured +1.6 us on
+// the decode QKV GEMM); the sum runs in a fixed order.
+constexpr int kMaxSsqParts = 18;
 __device__ __forceinline__ float deferred_rstd(const GemmArgs& g, int m) {
+    float p[kMaxSsqParts];
+#pragma unroll
+    for (int i = 0; i < kMaxSsqParts; ++i) p[i] = i < g.ssq_parts ? __ldcg(g.ssq_in + (size_t)i * g.ssq_ld + m) : 0.f;
     float t = 0.f;
-    for (int p = 0; p < g.ssq_parts; ++p) t += __ldcg(g.ssq_in + (size_t)p * g.ssq_ld + m);
+#pragma unroll
+    for (int i = 0; i < kMaxSsqParts; ++i) t += p[i];
     return rsqrtf(t * (1.0f / (float)g.K) + 1e-5f);
 }
 

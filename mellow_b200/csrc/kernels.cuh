@@ -48,7 +48,16 @@ cudaError_t launch_split_planes(const float* x, size_t n, bf16* hi, bf16* lo, cu
 
 // ---- lm.cu
 cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embed, int B, float* prefix, cudaStream_t st);
-// causal prefill attention on the tensor cores (attn_mma.cu)
+// causal prefill attention on tcgen05 (attn_umma.cu): operand planes written by the QKV GEMM epilogue (gemm.cuh)
+struct PrefillAttnPlanes {
+    const bf16 *qp_hi, *qp_lo;      // [B*S][576] roped queries * 64^-0.5
+    const bf16 *kp_hi, *kp_lo;      // [B][3][S][64] roped keys
+    const bf16 *vt_hi, *vt_lo;      // [B][3][64][vt_ld] values, transposed
+    int vt_ld;
+};
+cudaError_t launch_prefill_attention_umma(const PrefillAttnPlanes& p, int B, int S, bf16* out_hi, bf16* out_lo,
+                                          cudaStream_t st);
+// causal prefill attention on the legacy tensor path (mma.sync, attn_mma.cu)
 cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_fmt, int B, int S,
                                          int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st);
 struct DecodeAttnArgs {

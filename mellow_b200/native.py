@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libmellow_b200.so")
 HASH_PATH = os.path.join(CSRC, "libmellow_b200.srchash")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
-SOURCES = ["api.cu", "frontend.cu", "encoder.cu", "lm.cu", "attn_mma.cu", "gemm_umma.cu", "gemm_skinny.cu", "audio.cu"]
+SOURCES = ["api.cu", "frontend.cu", "encoder.cu", "lm.cu", "attn_mma.cu", "attn_umma.cu", "gemm_umma.cu", "gemm_skinny.cu", "audio.cu"]
 LAB_SOURCES = ["gemm_mma.cu"]          # mma.sync cross-check engine: only with MB_BUILD_LAB=1 (-DMB_LAB)
 HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", "umma.cuh"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -354,6 +354,40 @@ def test_decode_attention_variants_agree(which, request, inputs, golden):
         eng.set_option("kv_prefetch", 0)
 
 
+@pytest.mark.parametrize("which", ["engine", "engine24", "engine_fast"])
+def test_prefill_attention_kernels_agree(which, request, sd, oracle_taps):
+    """Causal prefill attention exists on tcgen05 (default: TMA-fed operand planes, S / O in TMEM) and on the legacy
+    mma.sync path; both must reproduce the oracle's prefill logits, also for a 3-row batch (deferred-norm GEMM path)
+    and for a longer sequence through the cache-less forward (S = 400: seven 64-key tiles)."""
+    eng = request.getfixturevalue(which)
+    tol = FAST_LOGIT_TOL if which == "engine_fast" else LOGIT_TOL
+    prefix = oracle_taps["prefix"]
+    with torch.no_grad():
+        want = R.last_logits(sd, R.llama_hidden(sd, prefix))
+    got = {}
+    try:
+        for kern in (1, 0):
+            eng.set_option("prefill_attn", kern)
+            eng.set_prefix(prefix)
+            got[kern] = eng.prefill(2).cpu()
+            assert maxerr(got[kern], want) < tol, f"prefill_attn={kern}"
+        if which != "engine_fast":
+            assert maxerr(got[0], got[1]) < 2e-3
+            eng.set_option("prefill_attn", 1)
+            p3 = torch.cat([prefix, prefix[:1]])
+            if eng.max_batch >= 3:
+                eng.set_prefix(p3)
+                l3 = eng.prefill(3).cpu()
+                assert maxerr(l3[:2], want) < tol and maxerr(l3[2], want[0]) < tol
+            emb = sd["caption_decoder.lm.model.embed_tokens.weight"][torch.arange(11)[None, :] * 37 + 5]
+            seq = torch.cat([prefix[:1], emb], dim=1)                          # (1, 400, 576)
+            with torch.no_grad():
+                want_long = R.last_logits(sd, R.llama_hidden(sd, seq))
+            assert maxerr(eng.lm_forward_last(seq), want_long) < tol
+    finally:
+        eng.set_option("prefill_attn", 1)
+
+
 @pytest.mark.parametrize("which", ["engine", "engine24"])
 def test_decode_tails_keep_ids_and_logits(which, request, inputs, oracle_taps, golden):
     """Option "decode_tails": o_proj / down as cluster split-K GEMMs (distributed-shared-memory reduce-scatter) with the

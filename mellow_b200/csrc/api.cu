@@ -219,6 +219,7 @@ struct Handle {
     // mb_set_option (defaults from the environment switches above)
     bool use_graph = true, decode_unfused = false, skip_finished = true;
     int kv_prefetch = 0;                 // (tile kernel) keys per stream prefetched into L2 before the dependency wait; -1 = all
+    int decode_cluster = 0;              // decode gate/up and QKV as cluster split-K GEMMs with the fused epilogue (gemm_skinny.cu)
     int prefill_attn = 1;                // causal prefill attention: 1 = tcgen05 kernel (attn_umma.cu), 0 = mma.sync kernel
     int attn_variant = 1;                // decode attention kernel: 1 = warp-autonomous, 0 = 64-key tiles (lm.cu)
     int decode_tails = 0;                // o_proj / down as cluster split-K tails with the norm deferred (gemm_skinny.cu)
@@ -278,6 +279,12 @@ GemmArgs gemm_base(const Handle* h, const bf16* a_hi, const bf16* a_lo, int lda,
 }
 
 int run_gemm(Handle* h, const GemmArgs& g, int epi, cudaStream_t st) {
+    if (h->engine == 1 && g.resident && h->decode_cluster && (epi == EPI_SWIGLU || epi == EPI_QKV_ROPE)) {
+        cudaError_t e = launch_gemm_cluster3(g, epi, st);
+        if (e == cudaSuccess) { h->launches++; return 0; }
+        if (e != cudaErrorNotSupported) MB_CK(h, e);
+        (void)cudaGetLastError();
+    }
     if (h->engine == 1 && g.resident) {
         const int bn = g.bn_hint ? g.bn_hint : (g.N >= 2048 ? 32 : 16);
         cudaError_t e = launch_gemm_skinny(g, epi, bn, st);
@@ -918,6 +925,7 @@ int mb_set_option(void* hv, const char* name, int value) {
     else if (n == "decode_tails") h->decode_tails = value;
     else if (n == "attn_variant") h->attn_variant = value;
     else if (n == "prefill_attn") h->prefill_attn = value;
+    else if (n == "decode_cluster") h->decode_cluster = value;
     else if (n == "gemm_engine") {
 #ifdef MB_LAB
         if (value != 0 && value != 1) return fail(h, "unknown GEMM engine");

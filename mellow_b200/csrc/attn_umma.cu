@@ -248,22 +248,16 @@ prefill_attention_umma_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const
         mbar_wait(o_full, (n_kt - 1) & 1);
         tc_fence_after();
         const float inv = 1.0f / l_run;
-        if (row_ok) {
-            const size_t ob = ((size_t)b * a.S + sq) * kHidden + (size_t)(kvh * 3 + hh) * kHeadDim;
+        const size_t ob = ((size_t)b * a.S + (row_ok ? sq : 0)) * kHidden + (size_t)(kvh * 3 + hh) * kHeadDim;
 #pragma unroll 1
-            for (int c0 = 0; c0 < kHeadDim; c0 += 16) {
-                float o[16];
-                tmem_ld16(tmem_o + lane_addr + (uint32_t)c0, o);
+        for (int c0 = 0; c0 < kHeadDim; c0 += 16) {
+            float o[16];
+            tmem_ld16(tmem_o + lane_addr + (uint32_t)c0, o);     // warp-collective: every lane loads, valid rows store
+            if (row_ok) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) o[j] *= inv;
                 store_planes8(a.out_hi, a.out_lo, ob + c0, o);
                 store_planes8(a.out_hi, a.out_lo, ob + c0 + 8, o + 8);
-            }
-        } else {
-#pragma unroll 1
-            for (int c0 = 0; c0 < kHeadDim; c0 += 16) {          // keep the warp's tcgen05.ld sequence uniform
-                float o[16];
-                tmem_ld16(tmem_o + lane_addr + (uint32_t)c0, o);
             }
         }
     }

@@ -340,5 +340,6 @@ __device__ __forceinline__ float deferred_rstd(const GemmArgs& g, int m) {
 cudaError_t launch_gemm_mma(const GemmArgs& g, int epi, cudaStream_t st);
 cudaError_t launch_gemm_skinny(const GemmArgs& g, int epi, int bn, cudaStream_t st);   // gemm_skinny.cu
 cudaError_t launch_gemm_tail(const GemmArgs& g, int cs, cudaStream_t st);               // gemm_skinny.cu (cluster split-K tail)
+cudaError_t launch_gemm_cluster3(const GemmArgs& g, int epi, cudaStream_t st);          // gemm_skinny.cu (cluster split-K + fused epilogue)
 
 }  // namespace mb

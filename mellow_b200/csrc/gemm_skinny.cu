@@ -65,7 +65,6 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                    const GemmArgs g) {
     using C = SkinnyCfg<BN, SPLIT, KBMAX, CS>;
-    static_assert(CS == 0 || EPI == EPI_GENERIC, "the cluster tail finishes a plain GEMM + residual");
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char* breg = smem;                                       // [KBMAX][PLANES][BN x 64] weight slice
@@ -258,7 +257,36 @@ gemm_skinny_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         }
     }
     if (threadIdx.x == 0) trace_put(g.trace, trec, g.trace_id, 8);                      // this warp's epilogue stores issued
-    if constexpr (CS > 0) {
+    if constexpr (CS > 0 && EPI != EPI_GENERIC) {
+        // cluster split-K with a fused epilogue (gate/up + SwiGLU, QKV + RoPE + KV write): the CTA that owns a row sums the
+        // CS partial accumulators (fixed order) and runs the row epilogue on 16-column pieces
+        constexpr int kP16 = BN / 16;
+        constexpr int kItems = C::RPC * kP16;
+        static_assert(kItems <= kEpiWarps * 32, "one piece per epilogue thread");
+        const int idx = (int)threadIdx.x;
+        const int rowl = idx / kP16, c = (idx - rowl * kP16) * 16;
+        const int mr = z * C::RPC + rowl, n = n0 + c;
+        const bool act = warp < kEpiWarps && idx < kItems && mr < BM && mr < g.M && n < g.N;
+        float rc[8], rs[8];
+        if (EPI == EPI_QKV_ROPE && act && n + 16 <= g.N) qkv_rope_load(g, mr, n, rc, rs);   // in flight across the cluster barrier
+        __syncwarp();
+        cluster_sync_all();
+        if (act) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) ld4(red + (size_t)rowl * C::RED_LD + c + j, v + j);
+#pragma unroll
+            for (int zz = 1; zz < CS; ++zz) {
+                float t[16];
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) ld4(red + (size_t)(zz * C::RPC + rowl) * C::RED_LD + c + j, t + j);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += t[j];
+            }
+            if (EPI == EPI_QKV_ROPE && n + 16 <= g.N) epilogue_row16_qkv(g, mr, n, v, rc, rs);
+            else epilogue_row16<EPI>(g, mr, n, v);
+        }
+    } else if constexpr (CS > 0) {
         constexpr int kC4 = BN / 4;                                   // float4 pieces per row of the tile
         constexpr int kItems = C::RPC * kC4;
         static_assert(kItems <= 2 * kEpiWarps * 32, "two pieces per epilogue thread at most");
@@ -341,11 +369,11 @@ cudaError_t launch_skinny(const GemmArgs& g, cudaStream_t st) {
     return launch_k(kern, dim3((unsigned)total), dim3(kThreads), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
 }
 
-// cluster launch of the tail variant: grid = tiles_n x CS, cluster = the CS K slices of one N tile
-template <int BN, bool SPLIT, int KBMAX, int CS>
-cudaError_t launch_tail(const GemmArgs& g, cudaStream_t st) {
+// cluster launch (tail / cluster split-K variants): grid = tiles_n x CS, cluster = the CS K slices of one N tile
+template <int BN, int EPI, bool SPLIT, int KBMAX, int CS>
+cudaError_t launch_cluster(const GemmArgs& g, cudaStream_t st) {
     using C = SkinnyCfg<BN, SPLIT, KBMAX, CS>;
-    auto kern = gemm_skinny_kernel<BN, EPI_GENERIC, SPLIT, KBMAX, CS>;
+    auto kern = gemm_skinny_kernel<BN, EPI, SPLIT, KBMAX, CS>;
     static bool configured[kMaxDevices] = {};
     if (cudaError_t e = ensure_smem(kern, C::SMEM, configured); e != cudaSuccess) return e;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -401,9 +429,22 @@ cudaError_t launch_gemm_tail(const GemmArgs& g, int cs, cudaStream_t st) {
     if (g.M > BM || !g.out_f32 || (g.N & 3) || (g.ldo & 3) || (g.residual && (g.ldr & 3)) || (g.out_hi && (g.ldp & 3)))
         return cudaErrorInvalidValue;
     if (cs == 4 && g.N % 32 == 0 && (kb_all + 3) / 4 <= 3)
-        return g.passes == 3 ? launch_tail<32, true, 3, 4>(g, st) : launch_tail<32, false, 3, 4>(g, st);
+        return g.passes == 3 ? launch_cluster<32, EPI_GENERIC, true, 3, 4>(g, st) : launch_cluster<32, EPI_GENERIC, false, 3, 4>(g, st);
     if (cs == 8 && g.N % 48 == 0 && (kb_all + 7) / 8 <= 3)
-        return g.passes == 3 ? launch_tail<48, true, 3, 8>(g, st) : launch_tail<48, false, 3, 8>(g, st);
+        return g.passes == 3 ? launch_cluster<48, EPI_GENERIC, true, 3, 8>(g, st) : launch_cluster<48, EPI_GENERIC, false, 3, 8>(g, st);
+    return cudaErrorNotSupported;
+}
+
+// gate/up (+SwiGLU) and QKV (+RoPE + KV write) of a decode layer as cluster split-K GEMMs: K = 576 in 3 slices of 3
+// k-blocks (24 MMAs per CTA instead of 72, a third of the activation bytes per CTA), 64- / 32-column tiles, the fused
+// epilogue on the rows each CTA of the cluster owns after the distributed-shared-memory reduce-scatter.
+cudaError_t launch_gemm_cluster3(const GemmArgs& g, int epi, cudaStream_t st) {
+    const int kb_all = (g.K + BK - 1) / BK;
+    if (g.M > BM || (kb_all + 2) / 3 > 3) return cudaErrorNotSupported;
+    if (epi == EPI_SWIGLU && g.N % 64 == 0)
+        return g.passes == 3 ? launch_cluster<64, EPI_SWIGLU, true, 3, 3>(g, st) : launch_cluster<64, EPI_SWIGLU, false, 3, 3>(g, st);
+    if (epi == EPI_QKV_ROPE && g.N % 32 == 0)
+        return g.passes == 3 ? launch_cluster<32, EPI_QKV_ROPE, true, 3, 3>(g, st) : launch_cluster<32, EPI_QKV_ROPE, false, 3, 3>(g, st);
     return cudaErrorNotSupported;
 }
 

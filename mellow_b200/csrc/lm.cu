@@ -63,7 +63,7 @@ struct DecodeSmem {
 // slower in round 1: 23.4 vs 18.7 us.
 template <typename T>
 __global__ void __launch_bounds__(128, 3) decode_attention_kernel(const DecodeAttnArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     DecodeSmem<T>& sm = *reinterpret_cast<DecodeSmem<T>*>(smem_raw);
     constexpr bool F24 = sizeof(T) == 3;          // kKvF24 rows: 64 x u16 upper halves, then 64 x u8 mantissa bytes
     constexpr int ROWB = DecodeSmem<T>::ROWB;
@@ -280,27 +280,50 @@ __global__ void __launch_bounds__(128, 3) decode_attention_kernel(const DecodeAt
 // (m, l, acc) states are merged once at the end.  About half the instructions per key of the tile kernel and no
 // block-wide barrier until the merge.
 constexpr int kAttnChunk = 16;                                    // keys per warp-private chunk
-template <typename T, int ST>
+// BULK = false: 16-byte cp.async pieces into padded key rows.  BULK = true (variant 2): a chunk is ONE bulk copy per
+// operand (cp.async.bulk: 16 keys x ROWB contiguous bytes, completion on a per-(warp, slot) mbarrier), which removes the
+// per-piece address arithmetic (a fifth of the kernel's instructions); the rows are then unpadded, and the score role
+// stays free of bank conflicts by walking the 16-byte pieces of its key row in an order rotated by the key index (the
+// query registers are loaded in the matching order once).
+template <typename T, int ST, bool BULK>
 struct DecodeSmemW {
     static constexpr int ROWB = KvRowBytes<T>::value;
-    static constexpr int KROWB = ROWB + 16;                       // +16 B: conflict-free 16 B reads with lane = key
-    __align__(16) unsigned char k[4][ST][kAttnChunk][KROWB];
-    __align__(16) unsigned char v[4][ST][kAttnChunk][ROWB];
+    static constexpr int KROWB = BULK ? ROWB : ROWB + 16;         // +16 B: conflict-free 16 B reads with lane = key
+    __align__(128) unsigned char k[4][ST][kAttnChunk][KROWB];
+    __align__(128) unsigned char v[4][ST][kAttnChunk][ROWB];
     __align__(16) float p[4][3][kAttnChunk];
     __align__(16) float red[4][3][kHeadDim];
     float ml[4][3][2];
+    __align__(8) unsigned long long full[4][ST];                  // BULK: "chunk landed" barriers
 };
 
-template <typename T, int ST>
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bar_wait_parity(unsigned long long* bar, uint32_t parity) {
+    const uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar);
+    uint32_t done = 0;
+    const long long t0 = clock64();
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (!done && clock64() - t0 > 4000000000LL) __trap();    // a broken pipeline must fail, not hang the GPU
+    }
+}
+
+template <typename T, int ST, bool BULK>
 __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const DecodeAttnArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    using SM = DecodeSmemW<T, ST>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using SM = DecodeSmemW<T, ST, BULK>;
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     constexpr bool F24 = sizeof(T) == 3;
     constexpr int ROWB = SM::ROWB;
     constexpr int NCHB = ROWB / 16;               // 16-byte pieces per cached row
     constexpr int E = F24 ? 8 : 16 / sizeof(T);   // values per 16 B piece of the part the score role walks
     constexpr int NCH = kHeadDim / E;
+    constexpr int NST = NCH / 2;                  // pieces each half of a lane pair walks
     const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned char* kb = reinterpret_cast<const unsigned char*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
@@ -310,33 +333,61 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
     // chunk i of this warp = keys [k_begin + 16 * (warp + 4 i), +16), staged in ring slot i % ST
     auto load_chunk = [&](int i, int ctx_limit) {
         const int key0 = k_begin + kAttnChunk * (warp + 4 * i);
-        unsigned char (*kd)[SM::KROWB] = sm.k[warp][i % ST];
-        unsigned char (*vd)[ROWB] = sm.v[warp][i % ST];
-        for (int c = lane; c < kAttnChunk * NCHB; c += 32) {
-            const int j = c / NCHB, ch = c - j * NCHB;
-            const bool ok = key0 + j < ctx_limit;
-            const size_t off = (size_t)(ok ? key0 + j : 0) * ROWB + ch * 16;
-            cp_async16(&kd[j][ch * 16], kb + off, ok);
-            cp_async16(&vd[j][ch * 16], vb + off, ok);
+        if constexpr (BULK) {
+            if (lane == 0) {
+                // rows at and beyond ctx_limit are not copied: their slots keep zeros / older finite rows and are masked
+                const uint32_t bytes = (uint32_t)(min(kAttnChunk, ctx_limit - key0) * ROWB);
+                unsigned long long* bar = &sm.full[warp][i % ST];
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads of the slot -> async writes
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(2u * bytes) : "memory");
+                bulk_load(&sm.k[warp][i % ST][0][0], kb + (size_t)key0 * ROWB, bytes, bar);
+                bulk_load(&sm.v[warp][i % ST][0][0], vb + (size_t)key0 * ROWB, bytes, bar);
+            }
+        } else {
+            unsigned char (*kd)[SM::KROWB] = sm.k[warp][i % ST];
+            unsigned char (*vd)[ROWB] = sm.v[warp][i % ST];
+            for (int c = lane; c < kAttnChunk * NCHB; c += 32) {
+                const int j = c / NCHB, ch = c - j * NCHB;
+                const bool ok = key0 + j < ctx_limit;
+                const size_t off = (size_t)(ok ? key0 + j : 0) * ROWB + ch * 16;
+                cp_async16(&kd[j][ch * 16], kb + off, ok);
+                cp_async16(&vd[j][ch * 16], vb + off, ok);
+            }
         }
     };
     pdl_trigger();
     unsigned trec = kTraceNone;
     if (tid == 0) trec = trace_open(a.trace, a.trace_id);
+    if constexpr (BULK) {
+        if (lane < ST) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&sm.full[warp][lane])) : "memory");
+        }
+        // value slots start as zeros: a partially filled last chunk leaves rows the copy did not touch, and 0 * NaN would
+        // poison the accumulators (their probabilities are exactly zero)
+        for (int c = lane; c < ST * kAttnChunk * ROWB / 16; c += 32)
+            reinterpret_cast<uint4*>(&sm.v[warp][0][0][0])[c] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
     // PDL: chunks that lie inside the prefill prefix are immutable history and are requested before the wait
     int n_early = 0;
 #pragma unroll
     for (int i = 0; i < ST; ++i) {
         if (n_early == i && k_begin + kAttnChunk * (warp + 4 * i + 1) <= a.ctx_base && warp + 4 * i < a.tps * 4) {
             load_chunk(i, a.ctx_base);
-            cp_async_commit();
+            if (!BULK) cp_async_commit();
             n_early = i + 1;
         }
     }
     pdl_wait();
     if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, TR_WAITED);
     const int step_now = a.d_step ? *a.d_step : 0;
-    if (a.done && a.done[b]) { cp_async_wait<0>(); return; }      // finished row: no K/V stream
+    if (a.done && a.done[b]) {                                    // finished row: no K/V stream
+        if constexpr (BULK) { for (int i = 0; i < n_early; ++i) bar_wait_parity(&sm.full[warp][i], 0); }
+        else cp_async_wait<0>();
+        return;
+    }
     const int ctx = a.ctx_base + step_now;
     const int k_end = min(ctx, k_begin + a.tps * 64);
     const int n_chunks = k_end > k_begin ? (k_end - k_begin + kAttnChunk - 1) / kAttnChunk : 0;
@@ -345,41 +396,50 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
     for (int i = 0; i < ST; ++i) {                                // fill the ring: one commit group per slot, empty or not
         if (i >= n_early) {
             if (i < n_mine) load_chunk(i, ctx);
-            cp_async_commit();
+            if (!BULK) cp_async_commit();
         }
     }
-    // score role: lane = (key j, half); each half owns every other 16 B piece of the key row
+    // score role: lane = (key j, half); each half owns every other 16 B piece of the key row.  BULK: the pieces are
+    // walked in an order rotated by the key index so that unpadded rows are read without bank conflicts.
     const int sj = lane >> 1, shalf = lane & 1;
+    const int rot = !BULK ? 0 : (F24 ? (sj >> 1) & (NST - 1) : sj & (NST - 1));
     float qreg[3][kHeadDim / 2];
     {
         const float* qb = a.q + (size_t)b * kHidden + (kvh * 3) * kHeadDim;
 #pragma unroll
         for (int h = 0; h < 3; ++h)
 #pragma unroll
-            for (int i = 0; i < NCH / 2; ++i)
+            for (int i = 0; i < NST; ++i) {
+                const int piece = 2 * ((i + rot) & (NST - 1)) + shalf;
 #pragma unroll
                 for (int e = 0; e < E; e += 4) {
-                    const float4 t4 = *reinterpret_cast<const float4*>(qb + h * kHeadDim + (2 * i + shalf) * E + e);
+                    const float4 t4 = *reinterpret_cast<const float4*>(qb + h * kHeadDim + piece * E + e);
                     qreg[h][i * E + e] = t4.x * 0.125f; qreg[h][i * E + e + 1] = t4.y * 0.125f;      // head_dim^-0.5, exact
                     qreg[h][i * E + e + 2] = t4.z * 0.125f; qreg[h][i * E + e + 3] = t4.w * 0.125f;
                 }
+            }
     }
     float m_run[3] = {-INFINITY, -INFINITY, -INFINITY}, l_run[3] = {0.f, 0.f, 0.f};
     float acc[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     const int dp = lane * 2;                                      // PV role: this lane's pair of head dims
     for (int i = 0; i < n_mine; ++i) {
-        cp_async_wait<ST - 1>();                                  // chunk i has landed (this thread's pieces) ...
-        __syncwarp();                                             // ... and everybody else's
         const int slot = i % ST;
+        if constexpr (BULK) {
+            bar_wait_parity(&sm.full[warp][slot], (uint32_t)(i / ST) & 1u);
+        } else {
+            cp_async_wait<ST - 1>();                              // chunk i has landed (this thread's pieces) ...
+            __syncwarp();                                         // ... and everybody else's
+        }
         const int key0 = k_begin + kAttnChunk * (warp + 4 * i);
         float s0 = 0.f, s1 = 0.f, s2 = 0.f;
         {
             const unsigned char* rowp = sm.k[warp][slot][sj];
 #pragma unroll
-            for (int c = 0; c < NCH / 2; ++c) {
+            for (int c = 0; c < NST; ++c) {
+                const int piece = 2 * ((c + rot) & (NST - 1)) + shalf;
                 if constexpr (F24) {
-                    const uint4 hv = *reinterpret_cast<const uint4*>(rowp + (2 * c + shalf) * 16);
-                    const uint2 lv = *reinterpret_cast<const uint2*>(rowp + 128 + (2 * c + shalf) * 8);
+                    const uint4 hv = *reinterpret_cast<const uint4*>(rowp + piece * 16);
+                    const uint2 lv = *reinterpret_cast<const uint2*>(rowp + 128 + piece * 8);
                     const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
                     for (int p = 0; p < 4; ++p) {
@@ -389,7 +449,7 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
                         s0 += qreg[0][c * E + 2 * p + 1] * k1; s1 += qreg[1][c * E + 2 * p + 1] * k1; s2 += qreg[2][c * E + 2 * p + 1] * k1;
                     }
                 } else {
-                    const T* kp = reinterpret_cast<const T*>(rowp) + (2 * c + shalf) * E;
+                    const T* kp = reinterpret_cast<const T*>(rowp) + piece * E;
 #pragma unroll
                     for (int e = 0; e < E; ++e) {
                         const float kvv = kv_load(kp + e);
@@ -454,9 +514,9 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
         }
         __syncwarp();                                             // the slot and sm.p are reused
         if (i + ST < n_mine) load_chunk(i + ST, ctx);
-        cp_async_commit();
+        if (!BULK) cp_async_commit();
     }
-    cp_async_wait<0>();
+    if (!BULK) cp_async_wait<0>();
     if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, 5);           // this warp's keys consumed
 #pragma unroll
     for (int h = 0; h < 3; ++h) {
@@ -656,22 +716,25 @@ cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embe
     return launch_k(prefix_kernel, grid, dim3(144), 0, st, rows33, ids, embed, B, prefix);
 }
 
-template <typename T, int ST>
+template <typename T, int ST, bool BULK>
 cudaError_t launch_decode_attention_warp(const DecodeAttnArgs& a, dim3 grid, cudaStream_t st) {
     static bool configured[kMaxDevices] = {};
-    auto kern = decode_attention_warp_kernel<T, ST>;
-    if (cudaError_t e = ensure_smem(kern, sizeof(DecodeSmemW<T, ST>), configured); e != cudaSuccess) return e;
-    return launch_k(kern, grid, dim3(128), sizeof(DecodeSmemW<T, ST>), st, a);
+    auto kern = decode_attention_warp_kernel<T, ST, BULK>;
+    if (cudaError_t e = ensure_smem(kern, sizeof(DecodeSmemW<T, ST, BULK>), configured); e != cudaSuccess) return e;
+    return launch_k(kern, grid, dim3(128), sizeof(DecodeSmemW<T, ST, BULK>), st, a);
 }
 
 cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
     dim3 grid(a.nsplit, kKvHeads, a.B);
     cudaError_t e;
-    if (a.variant == 1) {
-        // ring depth 2: 3 CTAs (12 warps) per SM for every row format
-        e = a.kv_fmt == kKvBf16 ? launch_decode_attention_warp<bf16, 3>(a, grid, st)
-          : a.kv_fmt == kKvF24 ? launch_decode_attention_warp<kv24, 2>(a, grid, st)
-                               : launch_decode_attention_warp<float, 2>(a, grid, st);
+    if (a.variant == 2) {                                 // warp-autonomous, bulk copies; ring depth 2 = 3 CTAs per SM
+        e = a.kv_fmt == kKvBf16 ? launch_decode_attention_warp<bf16, 3, true>(a, grid, st)
+          : a.kv_fmt == kKvF24 ? launch_decode_attention_warp<kv24, 2, true>(a, grid, st)
+                               : launch_decode_attention_warp<float, 2, true>(a, grid, st);
+    } else if (a.variant == 1) {                          // warp-autonomous, cp.async pieces
+        e = a.kv_fmt == kKvBf16 ? launch_decode_attention_warp<bf16, 3, false>(a, grid, st)
+          : a.kv_fmt == kKvF24 ? launch_decode_attention_warp<kv24, 2, false>(a, grid, st)
+                               : launch_decode_attention_warp<float, 2, false>(a, grid, st);
     } else {
         static bool c0[kMaxDevices] = {}, c1[kMaxDevices] = {}, c2[kMaxDevices] = {};
         if (cudaError_t e0 = ensure_smem(decode_attention_kernel<float>, sizeof(DecodeSmem<float>), c0); e0 != cudaSuccess) return e0;

@@ -335,12 +335,13 @@ def test_kv24_policy_keeps_token_identity_and_logit_tolerance(engine24, engine, 
 
 @pytest.mark.parametrize("which", ["engine", "engine24", "engine_fast"])
 def test_decode_attention_variants_agree(which, request, inputs, golden):
-    """Decode attention exists as the warp-autonomous kernel (default) and the 64-key tile kernel of round 1 (with an
-    optional L2 prefetch of the K/V history): same greedy ids from all of them (fp32 summation order differs)."""
+    """Decode attention exists as the warp-autonomous kernel (1: cp.async pieces, 2: one bulk copy per chunk) and as the
+    64-key tile kernel of round 1 (0, with an optional L2 prefetch of the K/V history): same greedy ids from all of them
+    (fp32 summation order differs)."""
     eng = request.getfixturevalue(which)
     ref = None
     try:
-        for variant, pf in ((1, 0), (0, 0), (0, -1), (0, 389)):
+        for variant, pf in ((1, 0), (2, 0), (0, 0), (0, -1), (0, 389)):
             eng.set_option("attn_variant", variant)
             eng.set_option("kv_prefetch", pf)
             toks = eng.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 12).cpu()
@@ -398,6 +399,13 @@ def test_decode_tails_keep_ids_and_logits(which, request, inputs, oracle_taps, g
         eng.set_option("decode_tails", 1)
         toks = eng.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 12).cpu()
         assert toks.tolist() == golden["tokens"].tolist()
+        # ... and with gate/up / QKV as cluster split-K GEMMs on top (3 kernels of the layer use thread-block clusters)
+        for tails in (1, 0):
+            eng.set_option("decode_tails", tails)
+            eng.set_option("decode_cluster", 1)
+            toks = eng.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 12).cpu()
+            assert toks.tolist() == golden["tokens"].tolist(), f"decode_cluster=1 decode_tails={tails}"
+        eng.set_option("decode_tails", 1)
         eng.set_prefix(oracle_taps["prefix"])
         eng.prefill(2, want_logits=False)
         forced = torch.from_numpy(golden["tokens"]).to(torch.int32)
@@ -411,6 +419,7 @@ def test_decode_tails_keep_ids_and_logits(which, request, inputs, oracle_taps, g
         assert eng.generate(w1, w2, ids, 12).cpu().tolist() == [want[0], want[1], want[0]]
     finally:
         eng.set_option("decode_tails", 0)
+        eng.set_option("decode_cluster", 0)
 
 
 def test_in_kernel_timeline_records_every_decode_kernel(engine, inputs, golden):

@@ -314,13 +314,13 @@ def run_ours(args):
     alg_bytes = 2 * Bp * KV_HEADS * ctx * HEAD_DIM * kv_bytes + 2 * Bp * HIDDEN * 4
     achieved = alg_bytes / (ms_attn * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tname = {4: "r1_decode_attention_b128_ctx539_ncu_full.json", 3: "r2_decode_attention_kv24_b128_ctx539_ncu_full.json"}.get(kv_bytes)
+    tname = {3: "r2_decode_attention_warp_kv24_b128_ctx539_ncu_full.json"}.get(kv_bytes)
     tpath = os.path.join(ROOT, "profiles", tname) if tname else ""
     if tpath and os.path.isfile(tpath) and Bp == 128 and ctx == 539:
         with open(tpath) as f:                       # dram__bytes_read+write per launch from the committed ncu --set full capture
             traffic = json.load(f)["traffic_bytes_per_launch"]
         traffic_src = f"cited from profiles/{tname} (ncu --set full of this kernel at this operating point), not measured in this run"
-    roofline = {"kernel": "decode_attention_kernel", "bound": "hbm", "achieved": achieved,
+    roofline = {"kernel": "decode_attention_warp_kernel<kv24>" if kv_bytes == 3 else "decode_attention_warp_kernel", "bound": "hbm", "achieved": achieved,
                 "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms_attn * 1e3, "ctx": ctx,
                 "timing": "CUDA events over 120 back-to-back launches cycling the 30 layer caches (successive launches "

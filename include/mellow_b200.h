@@ -54,15 +54,15 @@ long long mb_workspace_bytes(void* h);
  *                        0 = every row keeps decoding until all rows have stopped, like the reference loop
  *   "prefill_attn"   (1) causal prefill attention: 1 = tcgen05 kernel (TMA-fed bf16 operand planes, S / O in TMEM),
  *                        0 = the mma.sync kernel of round 1
- *   "attn_variant"   (1) decode attention kernel: 1 = warp-autonomous (each warp streams its own 16-key chunks, no block
- *                        barrier in the loop), 2 = the same with one bulk copy (cp.async.bulk) per chunk and operand,
- *                        0 = the 64-key tile kernel of round 1
+ *   "attn_variant"   (2) decode attention kernel: 2 = warp-autonomous (each warp streams its own 16-key chunks with one bulk
+ *                        copy per chunk and operand, no block barrier in the loop), 1 = the same with 16-byte cp.async
+ *                        pieces, 0 = the 64-key tile kernel of round 1
  *   "kv_prefetch"    (0) tile kernel only: keys per (row, kv head) stream prefetched into L2 while the kernel waits for
  *                        its predecessor (-1 = the whole immutable history); measured slower, off
- *   "decode_tails"   (0) 1 = o_proj / down_proj of a decode layer as cluster split-K GEMMs that finish the residual add
+ *   "decode_tails"   (1) 1 = o_proj / down_proj of a decode layer as cluster split-K GEMMs that finish the residual add
  *                        and the (deferred) RMSNorm themselves: 5 kernels per layer instead of 7
- *   "decode_cluster" (0) 1 = gate/up (+SwiGLU) and QKV (+RoPE, KV write) of a decode layer as cluster split-K GEMMs (3 K
- *                        slices per cluster, reduce-scatter through distributed shared memory, fused epilogue)
+ *   "decode_cluster" (0) lab builds only: gate/up (+SwiGLU) and QKV (+RoPE, KV write) of a decode layer as cluster split-K
+ *                        GEMMs (3 K slices per cluster); measured slower (two waves of clusters), ignored otherwise
  *   "wide_tiles"     (-1) decode split-K GEMM tiling: 1 = 32-column tiles x 3 / 8 K slices, 0 = 16-column tiles x 3 / 4,
  *                        -1 = by policy (wide except MB_POLICY_FAST)
  *   "gemm_engine"    (1) 0 = mma.sync cross-check engine (lab builds only, MB_BUILD_LAB=1) */

@@ -20,7 +20,7 @@ namespace mb {
 //   MB_NO_GRAPH=1      replay the decode step as individual launches instead of one CUDA graph
 //   MB_DECODE_UNFUSED=1 use the generic per-layer path (the one batches > 128 rows take) for every batch size
 //   MB_EPI_SLEEP=<ns>  back-off of the epilogue warps that wait for the accumulator (decode GEMMs)
-//   MB_DECODE_TAILS=0/1 decode: o_proj / down as cluster split-K tails with the deferred RMSNorm (option "decode_tails")
+//   MB_DECODE_TAILS=0/1 decode: o_proj / down as cluster split-K tails with the deferred RMSNorm (option "decode_tails", default 1)
 //   MB_KV_PREFETCH=<keys> decode (tile attention kernel): keys per (row, kv head) stream prefetched into L2 before the
 //                      dependency wait (default 0 = off: measured 4-5 % SLOWER per step, profiles/r2_decode_ab.jsonl)
 struct Tunables {
@@ -35,7 +35,7 @@ const Tunables& tunables() {
         v.decode_unfused = getenv("MB_DECODE_UNFUSED") != nullptr;
         v.epi_sleep = getenv("MB_EPI_SLEEP") ? atoi(getenv("MB_EPI_SLEEP")) : 128;
         v.kv_prefetch = getenv("MB_KV_PREFETCH") ? atoi(getenv("MB_KV_PREFETCH")) : 0;
-        v.decode_tails = getenv("MB_DECODE_TAILS") ? atoi(getenv("MB_DECODE_TAILS")) : 0;
+        v.decode_tails = getenv("MB_DECODE_TAILS") ? atoi(getenv("MB_DECODE_TAILS")) : 1;
         return v;
     }();
     return t;
@@ -221,8 +221,8 @@ struct Handle {
     int kv_prefetch = 0;                 // (tile kernel) keys per stream prefetched into L2 before the dependency wait; -1 = all
     int decode_cluster = 0;              // decode gate/up and QKV as cluster split-K GEMMs with the fused epilogue (gemm_skinny.cu)
     int prefill_attn = 1;                // causal prefill attention: 1 = tcgen05 kernel (attn_umma.cu), 0 = mma.sync kernel
-    int attn_variant = 1;                // decode attention kernel: 1 = warp-autonomous, 0 = 64-key tiles (lm.cu)
-    int decode_tails = 0;                // o_proj / down as cluster split-K tails with the norm deferred (gemm_skinny.cu)
+    int attn_variant = 2;                // decode attention kernel: 2 = warp-autonomous + bulk copies, 1 = cp.async pieces, 0 = 64-key tiles (lm.cu)
+    int decode_tails = 1;                // o_proj / down as cluster split-K tails with the norm deferred (gemm_skinny.cu)
     int wide_tiles = -1;                 // decode split-K tiling: -1 = by policy, 0 = 16-column tiles, 1 = 32-column tiles
     TraceBuf* trace = nullptr;           // mb_set_trace: optional in-kernel timeline of the decode kernels
 };

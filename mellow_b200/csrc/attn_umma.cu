@@ -3,7 +3,7 @@
 // cache-less from mellow/wrapper.py:217 (pure causal mask, pads attended).
 //
 // Operands.  The QKV GEMM epilogue (gemm.cuh, EPI_QKV_ROPE) leaves, next to the KV cache, bf16 hi/lo PLANES of the roped
-// queries (scaled by 64^-0.5), the roped keys and the TRANSPOSED values, so this kernel converts nothing: every tile is
+// queries (scaled by 64^-0.5 * log2 e: the softmax runs on exp2), the roped keys and the TRANSPOSED values, so this kernel converts nothing: every tile is
 // one cp.async.bulk.tensor into 128B-swizzled shared memory, consumed by UMMA descriptors.
 //   * the M = 128 rows of a tile are 42 consecutive queries x the 3 query heads that share a kv head (row = 3*s + hh:
 //     a 4-D tensor map over [M][kv head][hh][64] walks them), so K / V are streamed once for the three heads and only
@@ -200,7 +200,7 @@ prefill_attention_umma_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const
                 for (int j = 0; j < 16; ++j) mt = fmaxf(mt, key0 + c0 + j <= s_eff ? v[j] : -INFINITY);
             }
             const float m_new = fmaxf(m_run, mt);                // finite from the first tile on (key 0 <= every query)
-            const float alpha = expf(m_run - m_new);
+            const float alpha = exp2f(m_run - m_new);            // scores are in log2 units (the q planes carry log2(e) / 8)
             // pass 2: P = exp(S - m), as bf16 hi/lo in the K-major 128B-swizzle layout of the PV A operand
             float lsum = 0.f;
 #pragma unroll 1
@@ -210,7 +210,7 @@ prefill_attention_umma_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const
                     tmem_ld16(tmem_s + lane_addr + (uint32_t)c0, v);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
-                        v[j] = key0 + c0 + j <= s_eff ? expf(v[j] - m_new) : 0.f;
+                        v[j] = key0 + c0 + j <= s_eff ? exp2f(v[j] - m_new) : 0.f;
                         lsum += v[j];
                     }
                 } else {

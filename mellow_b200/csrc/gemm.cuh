@@ -5,6 +5,8 @@
 
 namespace mb {
 
+constexpr float kQScaleLog2 = 0.125f * 1.4426950408889634f;   // head_dim^-0.5 * log2(e): attn_umma.cu evaluates exp2(s - m)
+
 enum { EPI_GENERIC = 0, EPI_SWIGLU = 1, EPI_QKV_ROPE = 2, EPI_ARGMAX = 3 };
 enum { ACT_NONE = 0, ACT_GELU = 1, ACT_SIGMOID = 2 };
 
@@ -38,7 +40,7 @@ struct GemmArgs {
     // the weight rows are permuted at pack time), so rotate-half pairs sit in adjacent accumulator columns.
     float* q_out;                                     // [M,576] roped queries (may be null when the planes below are written)
     // prefill with the tcgen05 attention kernel (attn_umma.cu): the operands it streams with TMA, as bf16 hi/lo planes
-    bf16* qp_hi; bf16* qp_lo;                         // [M,576] roped queries * head_dim^-0.5 (exact power of two)
+    bf16* qp_hi; bf16* qp_lo;                         // [M,576] roped queries * head_dim^-0.5 * log2(e)
     bf16* kp_hi; bf16* kp_lo;                         // [B][3][rows_per_seq][64] roped keys
     bf16* vt_hi; bf16* vt_lo; int vt_ld;              // [B][3][64][vt_ld] values, TRANSPOSED (keys contiguous)
     void* k_cache; void* v_cache;                     // this layer: [B][3][t_max][64], float or bf16
@@ -199,7 +201,7 @@ __device__ __forceinline__ void epilogue_row16_qkv(const GemmArgs& g, int m, int
         if (g.qp_hi) {
             float qs[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) qs[j] = v[j] * 0.125f;
+            for (int j = 0; j < 16; ++j) qs[j] = v[j] * kQScaleLog2;   // scores come out in log2 units (softmax uses exp2)
             store_planes8(g.qp_hi, g.qp_lo, (size_t)m * kHidden + n, qs);
             store_planes8(g.qp_hi, g.qp_lo, (size_t)m * kHidden + n + 8, qs + 8);
         }

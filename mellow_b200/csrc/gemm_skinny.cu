@@ -438,7 +438,14 @@ cudaError_t launch_gemm_tail(const GemmArgs& g, int cs, cudaStream_t st) {
 // gate/up (+SwiGLU) and QKV (+RoPE + KV write) of a decode layer as cluster split-K GEMMs: K = 576 in 3 slices of 3
 // k-blocks (24 MMAs per CTA instead of 72, a third of the activation bytes per CTA), 64- / 32-column tiles, the fused
 // epilogue on the rows each CTA of the cluster owns after the distributed-shared-memory reduce-scatter.
+// MEASURED SLOWER (profiles/r2_decode_ab_option_matrix.jsonl: 1.30 vs 1.18 ms per step): the 48 clusters of 3 CTAs of
+// gate/up do not become resident together (GPCs of 16-20 SMs hold 5-6 such clusters each), so the grid runs in two
+// waves (body 11.3 us instead of 5.2).  Compiled into lab builds only (MB_BUILD_LAB=1).
 cudaError_t launch_gemm_cluster3(const GemmArgs& g, int epi, cudaStream_t st) {
+#ifndef MB_LAB
+    (void)g; (void)epi; (void)st;
+    return cudaErrorNotSupported;
+#else
     const int kb_all = (g.K + BK - 1) / BK;
     if (g.M > BM || (kb_all + 2) / 3 > 3) return cudaErrorNotSupported;
     if (epi == EPI_SWIGLU && g.N % 64 == 0)
@@ -446,6 +453,7 @@ cudaError_t launch_gemm_cluster3(const GemmArgs& g, int epi, cudaStream_t st) {
     if (epi == EPI_QKV_ROPE && g.N % 32 == 0)
         return g.passes == 3 ? launch_cluster<32, EPI_QKV_ROPE, true, 3, 3>(g, st) : launch_cluster<32, EPI_QKV_ROPE, false, 3, 3>(g, st);
     return cudaErrorNotSupported;
+#endif
 }
 
 // Decode-sized GEMM with resident weights.  Returns cudaErrorNotSupported (nothing launched) when the shape does not

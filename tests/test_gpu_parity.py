@@ -351,7 +351,7 @@ def test_decode_attention_variants_agree(which, request, inputs, golden):
             else:
                 assert toks.tolist() == golden["tokens"].tolist(), f"attn_variant={variant} kv_prefetch={pf}"
     finally:
-        eng.set_option("attn_variant", 1)
+        eng.set_option("attn_variant", 2)
         eng.set_option("kv_prefetch", 0)
 
 
@@ -396,6 +396,9 @@ def test_decode_tails_keep_ids_and_logits(which, request, inputs, oracle_taps, g
     for a ragged 3-row batch too."""
     eng = request.getfixturevalue(which)
     try:
+        eng.set_option("decode_tails", 0)                          # 7 kernels per layer: partial sums + add / RMSNorm kernels
+        toks = eng.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 12).cpu()
+        assert toks.tolist() == golden["tokens"].tolist()
         eng.set_option("decode_tails", 1)
         toks = eng.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 12).cpu()
         assert toks.tolist() == golden["tokens"].tolist()
@@ -418,7 +421,7 @@ def test_decode_tails_keep_ids_and_logits(which, request, inputs, oracle_taps, g
         want = golden["tokens"].tolist()
         assert eng.generate(w1, w2, ids, 12).cpu().tolist() == [want[0], want[1], want[0]]
     finally:
-        eng.set_option("decode_tails", 0)
+        eng.set_option("decode_tails", 1)
         eng.set_option("decode_cluster", 0)
 
 
@@ -449,8 +452,11 @@ def test_in_kernel_timeline_records_every_decode_kernel(engine, inputs, golden):
         kinds[kind] = kinds.get(kind, 0) + 1
         t_entry, t_wait, t_exit = int(ev["t"][r][0]), int(ev["t"][r][1]), int(ev["t"][r][2])
         assert t_entry <= t_wait <= t_exit, (kind, t_entry, t_wait, t_exit)
-    # 3 decode steps x 30 layers for the per-layer kinds; lm_head once after the prefill and once per decode step
-    assert all(kinds.get(k) == 90 for k in range(1, 8)), kinds
+    # 3 decode steps x 30 layers for the per-layer kinds.  With the cluster tails (default) o_proj / down finish the
+    # residual add and the norm themselves: no add+norm kernel after o_proj (kind 4), one after the LAST layer's down
+    # per step (kind 7, lm_head consumes normalised planes); lm_head once after the prefill and once per decode step
+    assert all(kinds.get(k) == 90 for k in (1, 2, 3, 5, 6)), kinds
+    assert kinds.get(4) is None and kinds.get(7) == 3, kinds
     assert kinds.get(8) == 4, kinds
 
 

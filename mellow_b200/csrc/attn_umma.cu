@@ -50,17 +50,28 @@ struct AttnCfg {
     static constexpr size_t SMEM = OFF_BAR + 128 + 1024;
 };
 
+// The softmax warps are the kernel's critical resource (ncu: 44 % issue-active, tensor pipe 19 %), so the per-element
+// work is kept to a handful of instructions: one MUFU for exp2 (arguments <= 0, results in [0,1]: the approximate
+// instruction's 2^-22 relative error is far inside the bf16x2 operand precision), packed bf16x2 conversions for the
+// hi / lo split.
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t cvt_bf16x2(float lo_elem, float hi_elem) {      // {hi_elem, lo_elem} -> one register
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
 __device__ __forceinline__ void pack8(const float* v, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        bf16 ah, al, bh, bl;
-        split_bf16(v[2 * j], ah, al);
-        split_bf16(v[2 * j + 1], bh, bl);
-        __nv_bfloat162 h2, l2;
-        h2.x = ah; h2.y = bh; l2.x = al; l2.y = bl;
-        h[j] = *reinterpret_cast<uint32_t*>(&h2);
-        l[j] = *reinterpret_cast<uint32_t*>(&l2);
+        const float a = v[2 * j], b = v[2 * j + 1];
+        h[j] = cvt_bf16x2(a, b);
+        const float ra = a - __uint_as_float(h[j] << 16), rb = b - __uint_as_float(h[j] & 0xFFFF0000u);
+        l[j] = cvt_bf16x2(ra, rb);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
     lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -182,6 +193,7 @@ prefill_attention_umma_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const
         const int s_eff = row_ok ? sq : s0;                      // padding rows follow the tile's first query (finite values)
         // tcgen05.ld is warp-collective: loop bounds follow the warp's LAST row, the per-lane causal mask is applied inside
         const int s_hi = min(s_last, s0 + (quad * 32 + 31) / 3);
+        const int s_lo = s0 + (quad * 32) / 3;                   // the warp's FIRST query: chunks up to it need no causal mask
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         pdl_wait();                                              // the output planes are an operand of the preceding GEMM
         float m_run = -INFINITY, l_run = 0.f;
@@ -196,22 +208,32 @@ prefill_attention_umma_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const
                 if (key0 + c0 > s_hi) break;                     // warp-uniform
                 float v[16];
                 tmem_ld16(tmem_s + lane_addr + (uint32_t)c0, v);
+                if (key0 + c0 + 15 <= s_lo) {                    // warp-uniform: the whole chunk is visible to every row
 #pragma unroll
-                for (int j = 0; j < 16; ++j) mt = fmaxf(mt, key0 + c0 + j <= s_eff ? v[j] : -INFINITY);
+                    for (int j = 0; j < 16; ++j) mt = fmaxf(mt, v[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) mt = fmaxf(mt, key0 + c0 + j <= s_eff ? v[j] : -INFINITY);
+                }
             }
             const float m_new = fmaxf(m_run, mt);                // finite from the first tile on (key 0 <= every query)
-            const float alpha = exp2f(m_run - m_new);            // scores are in log2 units (the q planes carry log2(e) / 8)
-            // pass 2: P = exp(S - m), as bf16 hi/lo in the K-major 128B-swizzle layout of the PV A operand
+            const float alpha = ex2_fast(m_run - m_new);         // scores are in log2 units (the q planes carry log2(e) / 8)
+            // pass 2: P = exp2(S - m), as bf16 hi/lo in the K-major 128B-swizzle layout of the PV A operand
             float lsum = 0.f;
 #pragma unroll 1
             for (int c0 = 0; c0 < kKT; c0 += 16) {
                 float v[16];
                 if (key0 + c0 <= s_hi) {                         // warp-uniform
                     tmem_ld16(tmem_s + lane_addr + (uint32_t)c0, v);
+                    if (key0 + c0 + 15 <= s_lo) {                // warp-uniform: no mask
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        v[j] = key0 + c0 + j <= s_eff ? exp2f(v[j] - m_new) : 0.f;
-                        lsum += v[j];
+                        for (int j = 0; j < 16; ++j) { v[j] = ex2_fast(v[j] - m_new); lsum += v[j]; }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            v[j] = key0 + c0 + j <= s_eff ? ex2_fast(v[j] - m_new) : 0.f;
+                            lsum += v[j];
+                        }
                     }
                 } else {
 #pragma unroll
@@ -229,7 +251,7 @@ prefill_attention_umma_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const
             }
             l_run = l_run * alpha + lsum;
             m_run = m_new;
-            if (it > 0) {                                        // rescale the running output (PV of the previous tile has retired:
+            if (it > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {   // rescale the running output when some row's maximum moved (PV of the previous tile has retired:
 #pragma unroll 1                                                 // S of this tile was issued after it)
                 for (int c0 = 0; c0 < kHeadDim; c0 += 16) {
                     float o[16];

@@ -11,7 +11,7 @@ ap.add_argument("--lib", default=os.path.join(ROOT, "mellow_b200", "csrc", "libm
 ap.add_argument("--out", default="")
 args = ap.parse_args()
 sass = subprocess.run(["cuobjdump", "-sass", args.lib], capture_output=True, text=True, check=True).stdout
-WATCH = ["UTCHMMA", "UTCQMMA", "UTMALDG", "UTMASTG", "UBLKPF", "UTMAPF", "LDTM", "STTM", "HMMA", "LDGSTS", "PRMT", "FFMA"]
+WATCH = ["UTCHMMA", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKPF", "UTMAPF", "UTMACCTL", "LDTM", "STTM", "HMMA", "LDGSTS", "PRMT", "FFMA"]
 fam = collections.OrderedDict()
 cur = None
 for line in sass.splitlines():

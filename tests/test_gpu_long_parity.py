@@ -171,3 +171,88 @@ def test_reference_inner_seams(engine, sd):
         want0 = R.last_logits(sd, R.llama_hidden(sd, prefix.cpu()))
     got0 = lm(inputs_embeds=prefix).logits[:, -1, :].cpu()
     assert (got0 - want0).abs().max() < LOGIT_TOL
+
+
+def _write_wavs(tmp_path, n, seed=321):
+    """n mono 16-bit wav files from the seeded synthetic waveforms, mixed rates / lengths (tile and crop branches)."""
+    import wave as wavmod
+    from mellow_b200 import synth
+    w = synth.synthetic_waveforms(n, seed=seed)
+    paths = []
+    for i in range(n):
+        sr = [32000, 44100, 22050][i % 3]
+        seconds = [10.0, 10.7, 4.2][i % 3]
+        x = torch.nn.functional.interpolate(w[i][None, None, :], size=int(sr * seconds), mode="linear")[0, 0]
+        p = str(tmp_path / f"clip{i}.wav")
+        with wavmod.open(p, "wb") as f:
+            f.setnchannels(1); f.setsampwidth(2); f.setframerate(sr)
+            f.writeframes((x.numpy() * 32767.0).round().astype("<i2").tobytes())
+        paths.append(p)
+    return paths
+
+
+def test_wrapper_passes_and_custom_stop_token(tmp_path):
+    """MellowWrapper.generate() over more examples than one engine pass holds (capacity 2 -> three passes for 5 examples)
+    returns what a single pass returns, also with a stop token other than '<|endoftext|>' -- the reference then returns
+    every row up to the GLOBAL stop step (wrapper.py:247-254), which the wrapper applies across passes."""
+    from mellow_b200 import MellowWrapper
+    paths = _write_wavs(tmp_path, 10)
+    examples = [[paths[i], paths[5 + i], f"what differs? ({i})"] for i in range(5)]
+    one = MellowWrapper(config="v0", model="v0", device=0, use_cuda=True, checkpoint="synthetic")
+    many = MellowWrapper(config="v0", model="v0", device=0, use_cuda=True, checkpoint="synthetic", max_batch=2)
+    try:
+        for stop in ("<|endoftext|>", "!"):
+            random.seed(11)
+            a = one.generate(examples=examples, max_len=10, top_p=0.8, temperature=1.0, stop_token=stop)
+            random.seed(11)
+            b = many.generate(examples=examples, max_len=10, top_p=0.8, temperature=1.0, stop_token=stop)
+            assert a == b and len(a) == 5 and len(set(a)) > 1, stop
+        assert many.model.max_batch == 2 and one.model.max_batch >= 5
+        # a longer request than the handle was sized for re-creates it (the reference accepts any max_len)
+        random.seed(11)
+        c = one.generate(examples=examples[:1], max_len=320, top_p=0.8, temperature=1.0)
+        assert one.model.max_new_tokens >= 320 and len(c) == 1
+    finally:
+        one.model.close()
+        many.model.close()
+
+
+def test_checkpoint_file_and_local_hf_tokenizer_end_to_end(tmp_path, sd):
+    """SURVEY section 8 row f2 as far as it goes offline: a checkpoint FILE in the reference's format (torch.save of the
+    flat state_dict, with the DataParallel 'module.' prefix the reference strips at wrapper.py:77-82) and a local Hugging
+    Face fast tokenizer directory; the text must be what the CPU oracle's ids decode to with that tokenizer."""
+    tokenizers = pytest.importorskip("tokenizers")
+    from tokenizers import Tokenizer, decoders, models, pre_tokenizers, trainers
+    from mellow_b200 import MellowWrapper
+    from mellow_b200.audio_io import load_audio_into_tensor
+    from oracle import restated as R
+    tokdir = tmp_path / "tok"
+    tokdir.mkdir()
+    tk = Tokenizer(models.BPE())
+    tk.pre_tokenizer = pre_tokenizers.ByteLevel(add_prefix_space=False)
+    tk.decoder = decoders.ByteLevel()
+    trainer = trainers.BpeTrainer(vocab_size=400, special_tokens=["<|endoftext|>"],
+                                  initial_alphabet=pre_tokenizers.ByteLevel.alphabet())
+    tk.train_from_iterator(["what is the difference between the two audios?", "describe the audio in detail!"] * 4, trainer)
+    tk.save(str(tokdir / "tokenizer.json"))
+    (tokdir / "tokenizer_config.json").write_text(
+        '{"tokenizer_class": "PreTrainedTokenizerFast", "eos_token": "<|endoftext|>", "bos_token": "<|endoftext|>", '
+        '"unk_token": "<|endoftext|>", "model_max_length": 8192}')
+    ckpt = str(tmp_path / "v0.ckpt")
+    torch.save({"module." + k: v for k, v in sd.items()}, ckpt)
+    paths = _write_wavs(tmp_path, 2, seed=77)
+    prompt = "what is the difference between the two audios?"
+    mw = MellowWrapper(config="v0", model="v0", device=0, use_cuda=True, checkpoint=ckpt, tokenizer=str(tokdir))
+    try:
+        random.seed(3)
+        out = mw.generate(examples=[[paths[0], paths[1], prompt]], max_len=8, top_p=0.8, temperature=1.0)
+        ids = mw.preprocess_text([prompt])["input_ids"]
+        assert ids.shape == (1, 129) and ids[0, -1] == mw.tokenizer.pad_token_id
+        random.seed(3)
+        a1 = load_audio_into_tensor(paths[0], 10, 32000, True, random)[None]
+        a2 = load_audio_into_tensor(paths[1], 10, 32000, True, random)[None]
+        with torch.no_grad():
+            want = R.generate_from_wave(sd, a1, a2, ids, 8)
+        assert out == [mw.tokenizer.decode(want[0].tolist()).split("<|endoftext|>")[0]]
+    finally:
+        mw.model.close()

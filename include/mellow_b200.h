@@ -52,13 +52,13 @@ long long mb_workspace_bytes(void* h);
  *   "decode_unfused" (0) 1 = use the generic per-layer decode path (the one batches > 128 rows take) for every batch
  *   "skip_finished"  (1) rows that emitted eos_id stop streaming their KV cache (their later tokens are not meaningful);
  *                        0 = every row keeps decoding until all rows have stopped, like the reference loop
- *   "prefill_attn"   (1) causal prefill attention: 1 = tcgen05 kernel (TMA-fed bf16 operand planes, S / O in TMEM),
- *                        0 = the mma.sync kernel of round 1
+ *   "prefill_attn"   (1) causal prefill attention: 1 = tcgen05 kernel (TMA-fed bf16 operand planes, S / O in TMEM);
+ *                        0 = the mma.sync kernel of round 1, lab builds only (MB_BUILD_LAB=1; an error otherwise)
  *   "attn_variant"   (2) decode attention kernel: 2 = warp-autonomous (each warp streams its own 16-key chunks with one bulk
- *                        copy per chunk and operand, no block barrier in the loop), 1 = the same with 16-byte cp.async
- *                        pieces, 0 = the 64-key tile kernel of round 1
- *   "kv_prefetch"    (0) tile kernel only: keys per (row, kv head) stream prefetched into L2 while the kernel waits for
- *                        its predecessor (-1 = the whole immutable history); measured slower, off
+ *                        copy per chunk and operand, no block barrier in the loop); lab builds only: 1 = the same with
+ *                        16-byte cp.async pieces, 0 = the 64-key tile kernel of round 1 (an error otherwise)
+ *   "kv_prefetch"    (0) lab tile kernel only: keys per (row, kv head) stream prefetched into L2 while the kernel waits
+ *                        for its predecessor (-1 = the whole immutable history); measured slower, off
  *   "decode_tails"   (1) 1 = o_proj / down_proj of a decode layer as cluster split-K GEMMs that finish the residual add
  *                        and the (deferred) RMSNorm themselves: 5 kernels per layer instead of 7
  *   "decode_cluster" (0) lab builds only: gate/up (+SwiGLU) and QKV (+RoPE, KV write) of a decode layer as cluster split-K

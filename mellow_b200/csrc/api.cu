@@ -923,8 +923,13 @@ int mb_set_option(void* hv, const char* name, int value) {
     else if (n == "kv_prefetch") h->kv_prefetch = value;
     else if (n == "wide_tiles") h->wide_tiles = value;
     else if (n == "decode_tails") h->decode_tails = value;
-    else if (n == "attn_variant") h->attn_variant = value;
-    else if (n == "prefill_attn") h->prefill_attn = value;
+    else if (n == "attn_variant" || n == "prefill_attn") {
+#ifndef MB_LAB
+        if ((n == "attn_variant" && value != 2) || (n == "prefill_attn" && value != 1))
+            return fail(h, "the alternative attention kernels are only in lab builds (MB_BUILD_LAB=1)");
+#endif
+        (n == "attn_variant" ? h->attn_variant : h->prefill_attn) = value;
+    }
     else if (n == "decode_cluster") h->decode_cluster = value;
     else if (n == "gemm_engine") {
 #ifdef MB_LAB

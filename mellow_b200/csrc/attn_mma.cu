@@ -11,7 +11,8 @@ namespace mb {
 
 namespace {
 
-constexpr int TQ = 64, TK = 64, LDS = kHeadDim + 8;      // 144-byte rows: conflict-free ldmatrix
+[[maybe_unused]] constexpr int TQ = 64;
+constexpr int TK = 64, LDS = kHeadDim + 8;               // 144-byte rows: conflict-free ldmatrix
 
 __device__ __forceinline__ void ldsm_x4(uint32_t* r, const bf16* p) {
     uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
@@ -101,6 +102,7 @@ __device__ __forceinline__ void stage_tile(const kv24* src_, int key0, int S, bf
     }
 }
 
+#ifdef MB_LAB   // mma.sync causal prefill attention of round 1 (prefill_attn 0): lab builds only, cross-check of attn_umma.cu
 template <typename T, bool SPLIT>
 __global__ void __launch_bounds__(128) prefill_attention_mma_kernel(const float* __restrict__ q, const T* __restrict__ kc,
                                                                     const T* __restrict__ vc, int S, int t_max,
@@ -240,6 +242,8 @@ __global__ void __launch_bounds__(128) prefill_attention_mma_kernel(const float*
         if (row1 < S) store_planes2(out_hi, out_lo, ((size_t)b * S + row1) * kHidden + col, o[jd][2] * i1, o[jd][3] * i1);
     }
 }
+
+#endif  // MB_LAB
 
 // ---------------------------------------------------------------------------------------------------------------
 // (Shifted-)window attention of the Swin blocks on the tensor cores (reference mellow/model/htsat.py:301-332,
@@ -419,6 +423,10 @@ cudaError_t launch_window_attention_mma(const float* qkv, const float* relbias, 
 
 cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_fmt, int B, int S,
                                          int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st) {
+#ifndef MB_LAB
+    (void)q; (void)kc; (void)vc; (void)kv_fmt; (void)B; (void)S; (void)t_max; (void)out_hi; (void)out_lo; (void)st;
+    return cudaErrorNotSupported;                       // lab builds only (MB_BUILD_LAB=1)
+#else
     dim3 grid((S + TQ - 1) / TQ, kHeads, B);
     if (kv_fmt == kKvBf16)
         return launch_k(prefill_attention_mma_kernel<bf16, false>, grid, dim3(128), 0, st, q, (const bf16*)kc,
@@ -428,6 +436,7 @@ cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const v
                         (const kv24*)vc, S, t_max, out_hi, out_lo);
     return launch_k(prefill_attention_mma_kernel<float, true>, grid, dim3(128), 0, st, q, (const float*)kc,
                     (const float*)vc, S, t_max, out_hi, out_lo);
+#endif
 }
 
 }  // namespace mb

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(144) prefix_kernel(const float* __restrict__ r
     reinterpret_cast<float4*>(prefix + ((size_t)b * kPrefix + p) * kHidden)[c4] = v;
 }
 
+#ifdef MB_LAB   // round 1's 64-key tile kernel (attn_variant 0): lab builds only, kept as a cross-check
 // ---------------------------------------------------------------------------------------------------------------
 // Decode attention: one new query per row, ctx keys.  CTA = (split, kv head, row): the 3 query heads that share the
 // kv head (GQA, modeling_llama.py:187-196) are processed together so K/V are read once.  128 threads, 64-key tiles,
@@ -269,9 +270,11 @@ __global__ void __launch_bounds__(128, 3) decode_attention_kernel(const DecodeAt
 }
 
 
+#endif  // MB_LAB
+
 // ---------------------------------------------------------------------------------------------------------------
-// Decode attention, warp-autonomous version (DecodeAttnArgs::variant = 1, the default).  What ncu showed on the tile
-// kernel above at B = 128 with 24-bit rows (profiles/r2_decode_attention_kv24_*): 38 % of the DRAM peak, 0.42 issued
+// Decode attention, warp-autonomous version (the product kernel).  What ncu showed on round 1's tile kernel (lab
+// builds) at B = 128 with 24-bit rows (profiles/r2_decode_attention_kv24_*): 38 % of the DRAM peak, 0.42 issued
 // instructions per scheduler cycle, 12 warps per SM, and stalls spread over the block barriers (four per 64-key tile),
 // the cp.async scoreboard and shared-memory latency -- a latency problem, not a bandwidth one.  Here the four warps of
 // the CTA never synchronise inside the loop: warp w streams the 16-key chunks w, w+4, w+8, ... of the CTA's key range
@@ -731,18 +734,24 @@ cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
         e = a.kv_fmt == kKvBf16 ? launch_decode_attention_warp<bf16, 3, true>(a, grid, st)
           : a.kv_fmt == kKvF24 ? launch_decode_attention_warp<kv24, 2, true>(a, grid, st)
                                : launch_decode_attention_warp<float, 2, true>(a, grid, st);
-    } else if (a.variant == 1) {                          // warp-autonomous, cp.async pieces
-        e = a.kv_fmt == kKvBf16 ? launch_decode_attention_warp<bf16, 3, false>(a, grid, st)
-          : a.kv_fmt == kKvF24 ? launch_decode_attention_warp<kv24, 2, false>(a, grid, st)
-                               : launch_decode_attention_warp<float, 2, false>(a, grid, st);
     } else {
-        static bool c0[kMaxDevices] = {}, c1[kMaxDevices] = {}, c2[kMaxDevices] = {};
-        if (cudaError_t e0 = ensure_smem(decode_attention_kernel<float>, sizeof(DecodeSmem<float>), c0); e0 != cudaSuccess) return e0;
-        if (cudaError_t e0 = ensure_smem(decode_attention_kernel<bf16>, sizeof(DecodeSmem<bf16>), c1); e0 != cudaSuccess) return e0;
-        if (cudaError_t e0 = ensure_smem(decode_attention_kernel<kv24>, sizeof(DecodeSmem<kv24>), c2); e0 != cudaSuccess) return e0;
-        e = a.kv_fmt == kKvBf16 ? launch_k(decode_attention_kernel<bf16>, grid, dim3(128), sizeof(DecodeSmem<bf16>), st, a)
-          : a.kv_fmt == kKvF24 ? launch_k(decode_attention_kernel<kv24>, grid, dim3(128), sizeof(DecodeSmem<kv24>), st, a)
-                               : launch_k(decode_attention_kernel<float>, grid, dim3(128), sizeof(DecodeSmem<float>), st, a);
+#ifdef MB_LAB
+        if (a.variant == 1) {                             // warp-autonomous, cp.async pieces
+            e = a.kv_fmt == kKvBf16 ? launch_decode_attention_warp<bf16, 3, false>(a, grid, st)
+              : a.kv_fmt == kKvF24 ? launch_decode_attention_warp<kv24, 2, false>(a, grid, st)
+                                   : launch_decode_attention_warp<float, 2, false>(a, grid, st);
+        } else {
+            static bool c0[kMaxDevices] = {}, c1[kMaxDevices] = {}, c2[kMaxDevices] = {};
+            if (cudaError_t e0 = ensure_smem(decode_attention_kernel<float>, sizeof(DecodeSmem<float>), c0); e0 != cudaSuccess) return e0;
+            if (cudaError_t e0 = ensure_smem(decode_attention_kernel<bf16>, sizeof(DecodeSmem<bf16>), c1); e0 != cudaSuccess) return e0;
+            if (cudaError_t e0 = ensure_smem(decode_attention_kernel<kv24>, sizeof(DecodeSmem<kv24>), c2); e0 != cudaSuccess) return e0;
+            e = a.kv_fmt == kKvBf16 ? launch_k(decode_attention_kernel<bf16>, grid, dim3(128), sizeof(DecodeSmem<bf16>), st, a)
+              : a.kv_fmt == kKvF24 ? launch_k(decode_attention_kernel<kv24>, grid, dim3(128), sizeof(DecodeSmem<kv24>), st, a)
+                                   : launch_k(decode_attention_kernel<float>, grid, dim3(128), sizeof(DecodeSmem<float>), st, a);
+        }
+#else
+        return cudaErrorNotSupported;                     // variants 0 / 1 exist in lab builds only (MB_BUILD_LAB=1)
+#endif
     }
     if (e != cudaSuccess || a.nsplit == 1) return e;
     return launch_k(decode_combine_kernel, dim3(kHeads, a.B), dim3(64), 0, st, a);

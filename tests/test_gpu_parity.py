@@ -24,6 +24,16 @@ LOGIT_TOL = 1e-2
 FAST_LOGIT_TOL = 1.5
 
 
+def option_available(eng, name, value):
+    """Alternative kernel variants are compiled into lab builds only (MB_BUILD_LAB=1); the product library refuses them."""
+    from mellow_b200.engine import MellowNativeError
+    try:
+        eng.set_option(name, value)
+        return True
+    except MellowNativeError:
+        return False
+
+
 def maxerr(a, b):
     a = torch.as_tensor(np.asarray(a.detach().cpu() if torch.is_tensor(a) else a)).double()
     b = torch.as_tensor(np.asarray(b.detach().cpu() if torch.is_tensor(b) else b)).double()
@@ -335,14 +345,15 @@ def test_kv24_policy_keeps_token_identity_and_logit_tolerance(engine24, engine, 
 
 @pytest.mark.parametrize("which", ["engine", "engine24", "engine_fast"])
 def test_decode_attention_variants_agree(which, request, inputs, golden):
-    """Decode attention exists as the warp-autonomous kernel (1: cp.async pieces, 2: one bulk copy per chunk) and as the
-    64-key tile kernel of round 1 (0, with an optional L2 prefetch of the K/V history): same greedy ids from all of them
-    (fp32 summation order differs)."""
+    """Decode attention: the warp-autonomous kernel with one bulk copy per chunk (2, the product kernel) and, in lab
+    builds, its cp.async form (1) and the 64-key tile kernel of round 1 (0, with an optional L2 prefetch of the K/V
+    history): same greedy ids from all of them (fp32 summation order differs)."""
     eng = request.getfixturevalue(which)
     ref = None
     try:
-        for variant, pf in ((1, 0), (2, 0), (0, 0), (0, -1), (0, 389)):
-            eng.set_option("attn_variant", variant)
+        for variant, pf in ((2, 0), (1, 0), (0, 0), (0, -1), (0, 389)):
+            if not option_available(eng, "attn_variant", variant):
+                continue                                        # product build: only the default kernel exists
             eng.set_option("kv_prefetch", pf)
             toks = eng.generate(inputs["wave1"], inputs["wave2"], inputs["ids"], 12).cpu()
             if which == "engine_fast":                          # no identity claim against the fp32 golden for policy fast
@@ -357,9 +368,9 @@ def test_decode_attention_variants_agree(which, request, inputs, golden):
 
 @pytest.mark.parametrize("which", ["engine", "engine24", "engine_fast"])
 def test_prefill_attention_kernels_agree(which, request, sd, oracle_taps):
-    """Causal prefill attention exists on tcgen05 (default: TMA-fed operand planes, S / O in TMEM) and on the legacy
-    mma.sync path; both must reproduce the oracle's prefill logits, also for a 3-row batch (deferred-norm GEMM path)
-    and for a longer sequence through the cache-less forward (S = 400: seven 64-key tiles)."""
+    """Causal prefill attention on tcgen05 (TMA-fed operand planes, S / O in TMEM) -- and, in lab builds, on the legacy
+    mma.sync path -- must reproduce the oracle's prefill logits, also for a 3-row batch (deferred-norm GEMM path) and
+    for a longer sequence through the cache-less forward (S = 400: seven 64-key tiles)."""
     eng = request.getfixturevalue(which)
     tol = FAST_LOGIT_TOL if which == "engine_fast" else LOGIT_TOL
     prefix = oracle_taps["prefix"]
@@ -368,12 +379,14 @@ def test_prefill_attention_kernels_agree(which, request, sd, oracle_taps):
     got = {}
     try:
         for kern in (1, 0):
-            eng.set_option("prefill_attn", kern)
+            if not option_available(eng, "prefill_attn", kern):
+                continue                                        # product build: the mma.sync kernel is not compiled in
             eng.set_prefix(prefix)
             got[kern] = eng.prefill(2).cpu()
             assert maxerr(got[kern], want) < tol, f"prefill_attn={kern}"
         if which != "engine_fast":
-            assert maxerr(got[0], got[1]) < 2e-3
+            if 0 in got:
+                assert maxerr(got[0], got[1]) < 2e-3
             eng.set_option("prefill_attn", 1)
             p3 = torch.cat([prefix, prefix[:1]])
             if eng.max_batch >= 3:

@@ -224,6 +224,7 @@ struct Handle {
     int attn_variant = 2;                // decode attention kernel: 2 = warp-autonomous + bulk copies, 1 = cp.async pieces, 0 = 64-key tiles (lm.cu)
     int decode_tails = 1;                // o_proj / down as cluster split-K tails with the norm deferred (gemm_skinny.cu)
     int wide_tiles = -1;                 // decode split-K tiling: -1 = by policy, 0 = 16-column tiles, 1 = 32-column tiles
+    int epilogue_rows = 0;               // persistent GEMM, plain epilogue: 1 = row-per-thread global accesses (round 1), 0 = staged 128-byte rows
     TraceBuf* trace = nullptr;           // mb_set_trace: optional in-kernel timeline of the decode kernels
 };
 inline void drop_graph(Handle* h) {
@@ -275,6 +276,7 @@ GemmArgs gemm_base(const Handle* h, const bf16* a_hi, const bf16* a_lo, int lda,
     g.M = M; g.N = N; g.K = K;
     g.passes = h->policy == kPolicySplit ? 3 : 1;
     g.epi_sleep = tunables().epi_sleep;
+    g.epi_rows = h->epilogue_rows;
     return g;
 }
 
@@ -923,6 +925,7 @@ int mb_set_option(void* hv, const char* name, int value) {
     else if (n == "kv_prefetch") h->kv_prefetch = value;
     else if (n == "wide_tiles") h->wide_tiles = value;
     else if (n == "decode_tails") h->decode_tails = value;
+    else if (n == "epilogue_rows") h->epilogue_rows = value != 0;
     else if (n == "attn_variant" || n == "prefill_attn") {
 #ifndef MB_LAB
         if ((n == "attn_variant" && value != 2) || (n == "prefill_attn" && value != 1))

@@ -23,12 +23,16 @@ struct Cfg {
     static constexpr uint32_t A_TILE = BM * BK * 2;
     static constexpr uint32_t B_BYTES = BN * BK * 2;
     static constexpr uint32_t STAGE_BYTES = (SPLIT ? 2 : 1) * (A_TILE + B_BYTES);
-    static constexpr uint32_t BUDGET = 227u * 1024u - 1024u - 256u;
+    // epilogue staging: one 32-row x 32-column fp32 block (4 KB, 128-byte rows, 16-byte pieces XOR-swizzled by row) per
+    // epilogue warp, through which accumulator rows (one per thread after tcgen05.ld) turn into whole 128-byte row
+    // segments per 8 lanes for the global loads / stores
+    static constexpr uint32_t STG_BYTES = BN >= 32 ? (uint32_t)kEpiWarps * 4096u : 0u;
+    static constexpr uint32_t BUDGET = 227u * 1024u - 1024u - 256u - STG_BYTES;
     static constexpr int STAGES_FIT = (int)(BUDGET / STAGE_BYTES);
     static constexpr int STAGES = STAGES_FIT > 8 ? 8 : STAGES_FIT;
     static constexpr uint32_t ACC_COLS = BN <= 32 ? 32 : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
     static constexpr uint32_t TMEM_COLS = 2 * ACC_COLS;                             // two accumulators: MMA of tile i+1
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;       // overlaps epilogue of tile i
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + STG_BYTES;   // overlaps epilogue of tile i
     static_assert(STAGES >= 2, "tile does not fit");
 };
 
@@ -46,6 +50,60 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile, int
     t.kb_begin = (int)(((long long)kb_all * t.z) / nsplit);
     t.KB = (int)(((long long)kb_all * (t.z + 1)) / nsplit) - t.kb_begin;
     return t;
+}
+
+
+// EPI_GENERIC on one 32-row x 32-column block of the accumulator, coalesced.  `v` holds this thread's row (lane = row,
+// already scaled by the deferred rstd).  The block goes through the warp's swizzled staging buffer once; afterwards 8
+// lanes own one 128-byte row segment (lane -> row 4i + lane/8, columns 4*(lane%8)..+3), so the residual loads and the
+// fp32 / plane stores are whole lines instead of 16-byte pieces of 32 different rows, and bias / gain are one 16-byte
+// load per lane and block.  sq[i] accumulates this lane's share of sum(x^2) of row 4i + lane/8.
+__device__ __forceinline__ void epilogue_block32_coalesced(const GemmArgs& g, int m_base, int n0, const float* v, float* stg,
+                                                           int lane, float* sq) {
+    const int cc = lane & 7, rsub = lane >> 3;
+    const int n = n0 + cc * 4;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (g.bias) b4 = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+    if (g.norm_w) g4 = __ldg(reinterpret_cast<const float4*>(g.norm_w + n));
+    float4 res[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m_base + 4 * i + rsub;
+        res[i] = (g.residual && m < g.M) ? *reinterpret_cast<const float4*>(g.residual + (size_t)m * g.ldr + n)
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + rsub;
+        const int m = m_base + r;
+        float4 x = *reinterpret_cast<const float4*>(stg + r * 32 + ((cc ^ (r & 7)) << 2));
+        x.x += b4.x; x.y += b4.y; x.z += b4.z; x.w += b4.w;
+        if (g.act == ACT_GELU) { x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w); }
+        else if (g.act == ACT_SIGMOID) { x.x = sigmoidf_(x.x); x.y = sigmoidf_(x.y); x.z = sigmoidf_(x.z); x.w = sigmoidf_(x.w); }
+        x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
+        if (m < g.M) {
+            if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + (size_t)m * g.ldo + n) = x;
+            if (g.out_hi) {
+                bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+                split_bf16(x.x * g4.x, h0, l0); split_bf16(x.y * g4.y, h1, l1);
+                split_bf16(x.z * g4.z, h2, l2); split_bf16(x.w * g4.w, h3, l3);
+                __nv_bfloat162 a, b;
+                a.x = h0; a.y = h1; b.x = h2; b.y = h3;
+                const size_t idx = (size_t)m * g.ldp + n;
+                *reinterpret_cast<uint2*>(g.out_hi + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+                if (g.out_lo) {
+                    a.x = l0; a.y = l1; b.x = l2; b.y = l3;
+                    *reinterpret_cast<uint2*>(g.out_lo + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+                }
+            }
+            sq[i] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        }
+    }
+    __syncwarp();                                                    // the next block overwrites the staging buffer
 }
 
 // Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence (n fastest, so the CTAs that run
@@ -190,6 +248,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             // deferred RMSNorm (gemm.cuh): consumer scale of this row, producer partial of this warp's chunks
             const float rs = (g.ssq_in != nullptr && m < g.M) ? deferred_rstd(g, m) : 1.0f;
             float sq = 0.f;
+            // whole 32-column blocks of a plain epilogue leave through the staging buffer as 128-byte row segments
+            // (warp-uniform choice); ragged tiles, odd leading dimensions and the other epilogues keep the row path
+            bool coalesced = false;
+            float sqc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (EPI == EPI_GENERIC && (BN % 32) == 0 && C::STG_BYTES != 0)
+                coalesced = !g.epi_rows && nsplit == 1 && t.n0 + BN <= g.N && (!g.out_f32 || (g.ldo & 3) == 0) &&
+                            (!g.residual || (g.ldr & 3) == 0) && (!g.out_hi || (g.ldp & 3) == 0);
+            float* stg = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256) + (warp - 2) * 1024;
 #pragma unroll 1
             for (int ci = half; ci < kChunks; ci += kSub) {
                 const int c0 = ci * 32;
@@ -201,7 +267,13 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&tempty[buf]);
                 }
-                if (m < g.M) {
+                if (EPI == EPI_GENERIC && (BN % 32) == 0 && coalesced) {
+                    if (g.ssq_in != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= rs;
+                    }
+                    epilogue_block32_coalesced(g, t.m0 + q * 32, t.n0 + c0, v, stg, lane, sqc);
+                } else if (m < g.M) {
 #pragma unroll
                     for (int h = 0; h < 32; h += 16) {
                         const int n = t.n0 + c0 + h;
@@ -226,8 +298,21 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     }
                 }
             }
-            if (EPI == EPI_GENERIC && g.ssq_out != nullptr && m < g.M)
-                g.ssq_out[(size_t)((t.n0 / BN) * kSub + half) * g.ssq_ld + m] = sq;
+            if (EPI == EPI_GENERIC && g.ssq_out != nullptr) {
+                if (coalesced) {                                     // 8 lanes share a row: fixed-order butterfly, lane % 8 == 0 writes
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float s = sqc[i];
+                        s += __shfl_xor_sync(0xffffffffu, s, 1);
+                        s += __shfl_xor_sync(0xffffffffu, s, 2);
+                        s += __shfl_xor_sync(0xffffffffu, s, 4);
+                        const int mr = t.m0 + q * 32 + 4 * i + (lane >> 3);
+                        if ((lane & 7) == 0 && mr < g.M) g.ssq_out[(size_t)((t.n0 / BN) * kSub + half) * g.ssq_ld + mr] = s;
+                    }
+                } else if (m < g.M) {
+                    g.ssq_out[(size_t)((t.n0 / BN) * kSub + half) * g.ssq_ld + m] = sq;
+                }
+            }
         }
     }
     tc_fence_before();

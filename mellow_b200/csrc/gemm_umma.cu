@@ -53,6 +53,19 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile, int
 }
 
 
+// 4 floats -> 4 bf16 hi (+ 4 bf16 lo) as one 8-byte store per plane
+__device__ __forceinline__ void store_planes4(bf16* hi, bf16* lo, size_t idx, float4 x) {
+    bf16 h0, l0, h1, l1, h2, l2, h3, l3;
+    split_bf16(x.x, h0, l0); split_bf16(x.y, h1, l1); split_bf16(x.z, h2, l2); split_bf16(x.w, h3, l3);
+    __nv_bfloat162 a, b;
+    a.x = h0; a.y = h1; b.x = h2; b.y = h3;
+    *reinterpret_cast<uint2*>(hi + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    if (lo) {
+        a.x = l0; a.y = l1; b.x = l2; b.y = l3;
+        *reinterpret_cast<uint2*>(lo + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    }
+}
+
 // EPI_GENERIC on one 32-row x 32-column block of the accumulator, coalesced.  `v` holds this thread's row (lane = row,
 // already scaled by the deferred rstd).  The block goes through the warp's swizzled staging buffer once; afterwards 8
 // lanes own one 128-byte row segment (lane -> row 4i + lane/8, columns 4*(lane%8)..+3), so the residual loads and the
@@ -87,20 +100,86 @@ __device__ __forceinline__ void epilogue_block32_coalesced(const GemmArgs& g, in
         x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
         if (m < g.M) {
             if (g.out_f32) *reinterpret_cast<float4*>(g.out_f32 + (size_t)m * g.ldo + n) = x;
-            if (g.out_hi) {
-                bf16 h0, l0, h1, l1, h2, l2, h3, l3;
-                split_bf16(x.x * g4.x, h0, l0); split_bf16(x.y * g4.y, h1, l1);
-                split_bf16(x.z * g4.z, h2, l2); split_bf16(x.w * g4.w, h3, l3);
-                __nv_bfloat162 a, b;
-                a.x = h0; a.y = h1; b.x = h2; b.y = h3;
-                const size_t idx = (size_t)m * g.ldp + n;
-                *reinterpret_cast<uint2*>(g.out_hi + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
-                if (g.out_lo) {
-                    a.x = l0; a.y = l1; b.x = l2; b.y = l3;
-                    *reinterpret_cast<uint2*>(g.out_lo + idx) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
-                }
-            }
+            if (g.out_hi) store_planes4(g.out_hi, g.out_lo, (size_t)m * g.ldp + n, make_float4(x.x * g4.x, x.y * g4.y, x.z * g4.z, x.w * g4.w));
             sq[i] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        }
+    }
+    __syncwarp();                                                    // the next block overwrites the staging buffer
+}
+
+// EPI_QKV_ROPE on one 32-row x 32-column block (n0 % 32 == 0, so the block lies inside one head of q, k or v), same
+// staging as epilogue_block32_coalesced: RoPE, the fp32 queries or their attention-operand planes, the key planes and
+// the K / V cache rows are written as whole row segments.  The TRANSPOSED value planes are the exception: there the
+// accumulator layout (lane = row = key) already is the contiguous one, so they are stored from `v` directly.
+__device__ __forceinline__ void epilogue_block32_qkv_coalesced(const GemmArgs& g, int m_base, int n0, const float* v, float* stg,
+                                                               int lane) {
+    const int cc = lane & 7, rsub = lane >> 3;
+    const int n = n0 + cc * 4;
+    const bool is_q = n0 < kHidden;
+    const bool is_v = n0 >= kHidden + kKvHeads * kHeadDim;
+    const int dpos = g.pos_base + (g.d_pos ? *g.d_pos : 0);
+    if (is_v && g.kp_hi) {
+        const int m = m_base + lane;
+        if (m < g.M) {
+            const int b = m / g.rows_per_seq, s = m - b * g.rows_per_seq;
+            const int c2 = n0 - kHidden - kKvHeads * kHeadDim;
+            const size_t o = (((size_t)b * kKvHeads + (c2 >> 6)) * kHeadDim + (c2 & 63)) * g.vt_ld + s;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) store_planes1(g.vt_hi, g.vt_lo, o + (size_t)j * g.vt_ld, v[j]);
+        }
+    }
+    float2 cs[8], sn[8];
+    int bb[8], ss[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int m = m_base + 4 * i + rsub;
+        m = m < g.M ? m : g.M - 1;
+        bb[i] = m / g.rows_per_seq;
+        ss[i] = m - bb[i] * g.rows_per_seq;
+        if (!is_v) {
+            const int t = (dpos + ss[i]) * 32 + ((n & (kHeadDim - 1)) >> 1);
+            cs[i] = __ldg(reinterpret_cast<const float2*>(g.rope_cos + t));
+            sn[i] = __ldg(reinterpret_cast<const float2*>(g.rope_sin + t));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(stg + lane * 32 + ((c ^ (lane & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + rsub;
+        const int m = m_base + r;
+        float4 x = *reinterpret_cast<const float4*>(stg + r * 32 + ((cc ^ (r & 7)) << 2));
+        if (m >= g.M) continue;
+        if (!is_v) {                                                 // two rotate-half pairs (pair-interleaved head dims)
+            const float a0 = x.x * cs[i].x - x.y * sn[i].x, a1 = x.y * cs[i].x + x.x * sn[i].x;
+            const float a2 = x.z * cs[i].y - x.w * sn[i].y, a3 = x.w * cs[i].y + x.z * sn[i].y;
+            x = make_float4(a0, a1, a2, a3);
+        }
+        if (is_q) {
+            if (g.q_out) *reinterpret_cast<float4*>(g.q_out + (size_t)m * kHidden + n) = x;
+            if (g.qp_hi)
+                store_planes4(g.qp_hi, g.qp_lo, (size_t)m * kHidden + n,
+                              make_float4(x.x * kQScaleLog2, x.y * kQScaleLog2, x.z * kQScaleLog2, x.w * kQScaleLog2));
+            continue;
+        }
+        const int c2 = n - kHidden - (is_v ? kKvHeads * kHeadDim : 0);
+        const int kvh = c2 >> 6, dd = c2 & 63;
+        if (!is_v && g.kp_hi)
+            store_planes4(g.kp_hi, g.kp_lo, (((size_t)bb[i] * kKvHeads + kvh) * g.rows_per_seq + ss[i]) * kHeadDim + dd, x);
+        const size_t row = ((size_t)bb[i] * kKvHeads + kvh) * g.t_max + dpos + ss[i];
+        void* base = is_v ? g.v_cache : g.k_cache;
+        if (g.kv_fmt == kKvF24) {                                    // 4 values: 8 B of upper halves + 4 mantissa bytes
+            unsigned char* rp = reinterpret_cast<unsigned char*>(base) + row * 192;
+            const uint32_t u0 = f24_bits(x.x), u1 = f24_bits(x.y), u2 = f24_bits(x.z), u3 = f24_bits(x.w);
+            *reinterpret_cast<uint2*>(rp + dd * 2) = make_uint2((u0 >> 16) | (u1 & 0xFFFF0000u), (u2 >> 16) | (u3 & 0xFFFF0000u));
+            *reinterpret_cast<uint32_t*>(rp + 128 + dd) =
+                ((u0 >> 8) & 0xFFu) | (u1 & 0xFF00u) | ((((u2 >> 8) & 0xFFu) | (u3 & 0xFF00u)) << 16);
+        } else if (g.kv_fmt == kKvBf16) {
+            store_planes4(reinterpret_cast<bf16*>(base) + row * kHeadDim + dd, nullptr, 0, x);
+        } else {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + row * kHeadDim + dd) = x;
         }
     }
     __syncwarp();                                                    // the next block overwrites the staging buffer
@@ -255,6 +334,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             if (EPI == EPI_GENERIC && (BN % 32) == 0 && C::STG_BYTES != 0)
                 coalesced = !g.epi_rows && nsplit == 1 && t.n0 + BN <= g.N && (!g.out_f32 || (g.ldo & 3) == 0) &&
                             (!g.residual || (g.ldr & 3) == 0) && (!g.out_hi || (g.ldp & 3) == 0);
+            if (EPI == EPI_QKV_ROPE && (BN % 32) == 0 && C::STG_BYTES != 0)
+                coalesced = !g.epi_rows && nsplit == 1 && t.n0 + BN <= g.N;
             float* stg = reinterpret_cast<float*>(smem + (size_t)C::STAGES * C::STAGE_BYTES + 256) + (warp - 2) * 1024;
 #pragma unroll 1
             for (int ci = half; ci < kChunks; ci += kSub) {
@@ -273,6 +354,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                         for (int j = 0; j < 32; ++j) v[j] *= rs;
                     }
                     epilogue_block32_coalesced(g, t.m0 + q * 32, t.n0 + c0, v, stg, lane, sqc);
+                } else if (EPI == EPI_QKV_ROPE && (BN % 32) == 0 && coalesced) {
+                    if (g.ssq_in != nullptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] *= rs;
+                    }
+                    epilogue_block32_qkv_coalesced(g, t.m0 + q * 32, t.n0 + c0, v, stg, lane);
                 } else if (m < g.M) {
 #pragma unroll
                     for (int h = 0; h < 32; h += 16) {

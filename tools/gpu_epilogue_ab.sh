@@ -4,7 +4,7 @@
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q --timeout 180 2>&1 | tail -30 > gpurun_out/epi_tests.log; tail -5 gpurun_out/epi_tests.log
 rm -f gpurun_out/prefill_ab_ref_*.pt
-for v in 1 0 1 0; do
+for v in 1 0 0; do
   timeout 200 python tools/prefill_ab.py --opt epilogue_rows=$v --tag epilogue_rows_$v 2>&1 | tail -1 | tee -a gpurun_out/prefill_ab_epilogue.jsonl
 done
 timeout 300 python bench.py --steps 3 --warmup 3 > gpurun_out/epi_bench.json 2> gpurun_out/epi_bench.err

@@ -63,6 +63,11 @@ long long mb_workspace_bytes(void* h);
  *                        and the (deferred) RMSNorm themselves: 5 kernels per layer instead of 7
  *   "decode_cluster" (0) lab builds only: gate/up (+SwiGLU) and QKV (+RoPE, KV write) of a decode layer as cluster split-K
  *                        GEMMs (3 K slices per cluster); measured slower (two waves of clusters), ignored otherwise
+ *   "cta_pairs"      (1) persistent GEMM (prefill / encoder, M >= 1024): 192- / 256-column tiles as cta_group::2 pairs (two
+ *                        CTAs of a cluster on one TPC share a 256-row tile, each loading half of the weight tile);
+ *                        0 = single CTAs (bit-identical results, ~9 % slower LM prefill)
+ *   "epilogue_rows"  (0) persistent GEMM: 1 = the row-per-thread global accesses of round 1 in the plain / QKV epilogue
+ *                        instead of the staged 128-byte row segments (A/B switch)
  *   "wide_tiles"     (-1) decode split-K GEMM tiling: 1 = 32-column tiles x 3 / 8 K slices, 0 = 16-column tiles x 3 / 4,
  *                        -1 = by policy (wide except MB_POLICY_FAST)
  *   "gemm_engine"    (1) 0 = mma.sync cross-check engine (lab builds only, MB_BUILD_LAB=1) */

@@ -224,6 +224,7 @@ struct Handle {
     int attn_variant = 2;                // decode attention kernel: 2 = warp-autonomous + bulk copies, 1 = cp.async pieces, 0 = 64-key tiles (lm.cu)
     int decode_tails = 1;                // o_proj / down as cluster split-K tails with the norm deferred (gemm_skinny.cu)
     int wide_tiles = -1;                 // decode split-K tiling: -1 = by policy, 0 = 16-column tiles, 1 = 32-column tiles
+    int cta_pairs = 1;                   // persistent GEMM: 1 = cta_group::2 pairs on the wide tiles of the large GEMMs
     int epilogue_rows = 0;               // persistent GEMM, plain epilogue: 1 = row-per-thread global accesses (round 1), 0 = staged 128-byte rows
     TraceBuf* trace = nullptr;           // mb_set_trace: optional in-kernel timeline of the decode kernels
 };
@@ -277,6 +278,7 @@ GemmArgs gemm_base(const Handle* h, const bf16* a_hi, const bf16* a_lo, int lda,
     g.passes = h->policy == kPolicySplit ? 3 : 1;
     g.epi_sleep = tunables().epi_sleep;
     g.epi_rows = h->epilogue_rows;
+    g.cta_pairs = h->cta_pairs;
     return g;
 }
 
@@ -926,6 +928,7 @@ int mb_set_option(void* hv, const char* name, int value) {
     else if (n == "wide_tiles") h->wide_tiles = value;
     else if (n == "decode_tails") h->decode_tails = value;
     else if (n == "epilogue_rows") h->epilogue_rows = value != 0;
+    else if (n == "cta_pairs") h->cta_pairs = value != 0;
     else if (n == "attn_variant" || n == "prefill_attn") {
 #ifndef MB_LAB
         if ((n == "attn_variant" && value != 2) || (n == "prefill_attn" && value != 1))

@@ -20,6 +20,7 @@ struct GemmArgs {
     int epi_sleep;                                    // weight-resident kernel: ns the epilogue warps sleep between polls of the accumulator barrier
     int resident;                                     // decode chain: use the weight-resident kernel (gemm_skinny.cu) when the shape fits
     int bn_hint;                                      // decode-sized GEMMs: N-tile width 16 / 32 (0 = default rule)
+    int cta_pairs;                                    // gemm_umma.cu: 1 = cta_group::2 pairs for the 192 / 256-column tiles of large GEMMs
     int epi_rows;                                     // gemm_umma.cu: 1 = keep the row-per-thread global accesses in the plain epilogue (A/B switch)
     // Deferred RMSNorm (LlamaRMSNorm, modeling_llama.py:62-67) across a producer / consumer pair of GEMMs.  RMSNorm(x) * W^T =
     // rstd(x) * ((x * gain) * W^T), and rstd is one scalar per row, so the PRODUCER of x (o_proj / down_proj, EPI_GENERIC

@@ -18,10 +18,14 @@ namespace {
 
 using namespace umma;
 
-template <int BN, bool SPLIT>
+// CG = 2: CTA pairs (cta_group::2, umma.cuh).  A 128 x BN tile needs (128 + BN) x 128 B x planes per k-block for
+// 3 x 4 x BN/2 tensor cycles: 62.5 B/clk/SM at BN = 256 and 71 at BN = 192, which is the per-SM L2 -> SM rate (ncu: tensor
+// pipe 55-70 % active, profiles/r2_lm_prefill_gemms_b128_ncu_full.json).  A pair works on 256 x BN, each CTA loading its
+// 128 rows of A and HALF of B: 41.7 / 46.7 B/clk/SM, and the ring gets a third stage.
+template <int BN, bool SPLIT, int CG = 1>
 struct Cfg {
     static constexpr uint32_t A_TILE = BM * BK * 2;
-    static constexpr uint32_t B_BYTES = BN * BK * 2;
+    static constexpr uint32_t B_BYTES = (BN / CG) * BK * 2;
     static constexpr uint32_t STAGE_BYTES = (SPLIT ? 2 : 1) * (A_TILE + B_BYTES);
     // epilogue staging: one 32-row x 32-column fp32 block (4 KB, 128-byte rows, 16-byte pieces XOR-swizzled by row) per
     // epilogue warp, through which accumulator rows (one per thread after tcgen05.ld) turn into whole 128-byte row
@@ -38,13 +42,13 @@ struct Cfg {
 
 struct TileCoord { int m0, n0, z, kb_begin, KB; };
 
-template <int BN>
+template <int BN, int CG = 1>
 __device__ __forceinline__ TileCoord tile_coord(const GemmArgs& g, int tile, int tiles_n, int per_split, int nsplit) {
     TileCoord t;
     t.z = tile / per_split;
     const int rem = tile - t.z * per_split;
     const int mt = rem / tiles_n;
-    t.m0 = mt * BM;
+    t.m0 = mt * BM * CG;                                              // CG = 2: first row of the pair's 256-row tile
     t.n0 = (rem - mt * tiles_n) * BN;
     const int kb_all = (g.K + BK - 1) / BK;
     t.kb_begin = (int)(((long long)kb_all * t.z) / nsplit);
@@ -188,12 +192,12 @@ __device__ __forceinline__ void epilogue_block32_qkv_coalesced(const GemmArgs& g
 // Persistent: grid = min(#tiles, #SMs); every role walks the same static tile sequence (n fastest, so the CTAs that run
 // concurrently share A rows and the whole W in L2).  The smem ring runs continuously across tiles; the accumulator
 // is double-buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1.
-template <int BN, int EPI, bool SPLIT>
+template <int BN, int EPI, bool SPLIT, int CG = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                  const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                  const GemmArgs g) {
-    using C = Cfg<BN, SPLIT>;
+    using C = Cfg<BN, SPLIT, CG>;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)C::STAGES * C::STAGE_BYTES);
@@ -205,8 +209,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nsplit = g.split_k > 1 ? g.split_k : 1;
     const int tiles_n = (g.N + BN - 1) / BN;
-    const int per_split = tiles_n * ((g.M + BM - 1) / BM);
+    const int per_split = tiles_n * ((g.M + BM * CG - 1) / (BM * CG));
     const int total = per_split * nsplit;
+    // CG = 2: the two CTAs of a cluster walk the same tile sequence; `rank` picks the CTA's 128 rows of A / of the
+    // accumulator and its half of the B tile.  Barriers: full[] lives in the LEADER (rank 0: one arrival, the bytes of both
+    // CTAs); empty[] and tfull[] exist in both CTAs and are signalled by the multicast commit; tempty[] lives in the leader
+    // and counts the epilogue warps of both CTAs.
+    const uint32_t rank = CG == 2 ? cluster_rank() : 0u;
+    const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     pdl_trigger();
     unsigned trec = kTraceNone;                                      // thread 0 only
@@ -214,15 +225,21 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         trec = trace_open(g.trace, g.trace_id);
         for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(&tfull[0], 1); mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], kEpiWarps); mbar_init(&tempty[1], kEpiWarps);
+        mbar_init(&tempty[0], kEpiWarps * CG); mbar_init(&tempty[1], kEpiWarps * CG);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(C::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();                                 // the peer must see initialised barriers before it signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -230,8 +247,34 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         if (elect_one()) {
             int it = 0;
             bool first = true;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const TileCoord t = tile_coord<BN>(g, tile, tiles_n, per_split, nsplit);
+            // one stage = this CTA's A rows and its share of the B rows; CG = 2: bytes are counted on the leader's barrier
+            auto expect = [&](int s) { if (rank == 0) mbar_expect_tx(&full[s], C::STAGE_BYTES * CG); };
+            auto load_b = [&](int s, int kb, int n0) {
+                unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
+                const int nb = n0 + (int)rank * (BN / CG);
+                if (CG == 2) {
+                    const uint32_t bar = cluster_addr(&full[s], 0);
+                    tma_load_2d_2sm(st + C::A_TILE, &tm_b_hi, bar, kb * BK, nb);
+                    if (SPLIT) tma_load_2d_2sm(st + 2 * C::A_TILE + C::B_BYTES, &tm_b_lo, bar, kb * BK, nb);
+                } else {
+                    tma_load_2d(st + C::A_TILE, &tm_b_hi, &full[s], kb * BK, nb);
+                    if (SPLIT) tma_load_2d(st + 2 * C::A_TILE + C::B_BYTES, &tm_b_lo, &full[s], kb * BK, nb);
+                }
+            };
+            auto load_a = [&](int s, int kb, int m0) {
+                unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
+                const int ma = m0 + (int)rank * BM;
+                if (CG == 2) {
+                    const uint32_t bar = cluster_addr(&full[s], 0);
+                    tma_load_2d_2sm(st, &tm_a_hi, bar, kb * BK, ma);
+                    if (SPLIT) tma_load_2d_2sm(st + C::A_TILE + C::B_BYTES, &tm_a_lo, bar, kb * BK, ma);
+                } else {
+                    tma_load_2d(st, &tm_a_hi, &full[s], kb * BK, ma);
+                    if (SPLIT) tma_load_2d(st + C::A_TILE + C::B_BYTES, &tm_a_lo, &full[s], kb * BK, ma);
+                }
+            };
+            for (int tile = tile0; tile < total; tile += tile_step) {
+                const TileCoord t = tile_coord<BN, CG>(g, tile, tiles_n, per_split, nsplit);
                 int kb = 0;
                 if (first) {
                     // PDL: the weight (B) tiles of the first ring slots never depend on the preceding kernel, so they
@@ -239,18 +282,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     first = false;
                     const int npre = t.KB < C::STAGES ? t.KB : C::STAGES;
                     for (int i = 0; i < npre; ++i) {
-                        unsigned char* st = smem + (size_t)i * C::STAGE_BYTES;
-                        mbar_expect_tx(&full[i], C::STAGE_BYTES);
-                        tma_load_2d(st + C::A_TILE, &tm_b_hi, &full[i], (t.kb_begin + i) * BK, t.n0);
-                        if (SPLIT) tma_load_2d(st + 2 * C::A_TILE + C::B_BYTES, &tm_b_lo, &full[i], (t.kb_begin + i) * BK, t.n0);
+                        expect(i);
+                        load_b(i, t.kb_begin + i, t.n0);
                     }
                     pdl_wait();
                     if (first_cta()) trace_put(g.trace, trec, g.trace_id, TR_WAITED);
-                    for (int i = 0; i < npre; ++i) {
-                        unsigned char* st = smem + (size_t)i * C::STAGE_BYTES;
-                        tma_load_2d(st, &tm_a_hi, &full[i], (t.kb_begin + i) * BK, t.m0);
-                        if (SPLIT) tma_load_2d(st + C::A_TILE + C::B_BYTES, &tm_a_lo, &full[i], (t.kb_begin + i) * BK, t.m0);
-                    }
+                    for (int i = 0; i < npre; ++i) load_a(i, t.kb_begin + i, t.m0);
                     kb = npre;
                     it = npre;
                 }
@@ -258,24 +295,21 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                     const int s = it % C::STAGES;
                     const uint32_t ph = (it / C::STAGES) & 1;
                     mbar_wait_fast(&empty[s], ph ^ 1);
-                    unsigned char* st = smem + (size_t)s * C::STAGE_BYTES;
-                    mbar_expect_tx(&full[s], C::STAGE_BYTES);
-                    tma_load_2d(st + C::A_TILE, &tm_b_hi, &full[s], (t.kb_begin + kb) * BK, t.n0);
-                    if (SPLIT) tma_load_2d(st + 2 * C::A_TILE + C::B_BYTES, &tm_b_lo, &full[s], (t.kb_begin + kb) * BK, t.n0);
-                    tma_load_2d(st, &tm_a_hi, &full[s], (t.kb_begin + kb) * BK, t.m0);
-                    if (SPLIT) tma_load_2d(st + C::A_TILE + C::B_BYTES, &tm_a_lo, &full[s], (t.kb_begin + kb) * BK, t.m0);
+                    expect(s);
+                    load_b(s, t.kb_begin + kb, t.n0);
+                    load_a(s, t.kb_begin + kb, t.m0);
                 }
             }
         }
     } else if (warp == 1) {
-        if (elect_one()) {
-            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3, M>>4
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        if (rank == 0 && elect_one()) {                              // CG = 2: the leader issues for the pair
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, both K-major, N>>3, M>>4 (M = 256 for a pair)
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
             int it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
-                const TileCoord t = tile_coord<BN>(g, tile, tiles_n, per_split, nsplit);
+            for (int tile = tile0; tile < total; tile += tile_step, ++lt) {
+                const TileCoord t = tile_coord<BN, CG>(g, tile, tiles_n, per_split, nsplit);
                 const int buf = lt & 1;
-                mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator
+                mbar_wait(&tempty[buf], ((lt >> 1) & 1) ^ 1);        // epilogue has drained this accumulator (both CTAs of a pair)
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)buf * C::ACC_COLS;
                 for (int kb = 0; kb < t.KB; ++kb, ++it) {
@@ -291,16 +325,26 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         const uint64_t dah = umma_desc_join(a_hi + 2 * k), dbh = umma_desc_join(b_hi + 2 * k);
-                        if (k == 0 && kb == 0) umma_bf16_c<false>(tacc, dah, dbh, idesc);
-                        else umma_bf16_c<true>(tacc, dah, dbh, idesc);
-                        if (SPLIT) {
-                            umma_bf16_c<true>(tacc, dah, umma_desc_join(b_lo + 2 * k), idesc);
-                            umma_bf16_c<true>(tacc, umma_desc_join(a_lo + 2 * k), dbh, idesc);
+                        if (CG == 2) {
+                            if (k == 0 && kb == 0) umma2_bf16_c<false>(tacc, dah, dbh, idesc);
+                            else umma2_bf16_c<true>(tacc, dah, dbh, idesc);
+                            if (SPLIT) {
+                                umma2_bf16_c<true>(tacc, dah, umma_desc_join(b_lo + 2 * k), idesc);
+                                umma2_bf16_c<true>(tacc, umma_desc_join(a_lo + 2 * k), dbh, idesc);
+                            }
+                        } else {
+                            if (k == 0 && kb == 0) umma_bf16_c<false>(tacc, dah, dbh, idesc);
+                            else umma_bf16_c<true>(tacc, dah, dbh, idesc);
+                            if (SPLIT) {
+                                umma_bf16_c<true>(tacc, dah, umma_desc_join(b_lo + 2 * k), idesc);
+                                umma_bf16_c<true>(tacc, umma_desc_join(a_lo + 2 * k), dbh, idesc);
+                            }
                         }
                     }
-                    umma_commit(&empty[s]);                          // frees the smem stage once these MMAs retire
+                    // frees the smem stage (in both CTAs of a pair) once these MMAs retire
+                    if (CG == 2) umma2_commit(&empty[s]); else umma_commit(&empty[s]);
                 }
-                umma_commit(&tfull[buf]);                            // accumulator complete
+                if (CG == 2) umma2_commit(&tfull[buf]); else umma_commit(&tfull[buf]);   // accumulator complete
             }
         }
     } else {
@@ -311,9 +355,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         const int half = (warp - 2) >> 2;                            // the warps of a quadrant take 32-column chunks round-robin
         constexpr int kSub = kEpiWarps / 4;
         pdl_wait();                                                  // residual reads / output writes depend on the predecessor
+        // the accumulator goes back to the MMA issuer: a local arrive, or (CG = 2) an arrive on the leader's barrier
+        auto release_acc = [&](int buf) {
+            if (CG == 2) mbar_arrive_cluster(cluster_addr(&tempty[buf], 0));
+            else mbar_arrive(&tempty[buf]);
+        };
         int lt = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
-            const TileCoord t = tile_coord<BN>(g, tile, tiles_n, per_split, nsplit);
+        for (int tile = tile0; tile < total; tile += tile_step, ++lt) {
+            TileCoord t = tile_coord<BN, CG>(g, tile, tiles_n, per_split, nsplit);
+            t.m0 += (int)rank * BM;                                  // this CTA's 128 rows of the pair's tile
             const int buf = lt & 1;
             const int m = t.m0 + q * 32 + lane;
             mbar_wait(&tfull[buf], (lt >> 1) & 1);
@@ -321,7 +371,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
             const uint32_t tacc = tmem_base + (uint32_t)buf * C::ACC_COLS + ((uint32_t)(q * 32) << 16);
             constexpr int kChunks = (BN + 31) / 32;
             if (half * 32 >= BN) {                                   // narrow tile: nothing for the second warp to drain
-                if (lane == 0) mbar_arrive(&tempty[buf]);
+                if (lane == 0) release_acc(buf);
                 continue;
             }
             // deferred RMSNorm (gemm.cuh): consumer scale of this row, producer partial of this warp's chunks
@@ -346,7 +396,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
                 if (ci + kSub >= kChunks) {                          // this warp has read its share: hand the accumulator back
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tempty[buf]);
+                    if (lane == 0) release_acc(buf);
                 }
                 if (EPI == EPI_GENERIC && (BN % 32) == 0 && coalesced) {
                     if (g.ssq_in != nullptr) {
@@ -403,39 +453,61 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_const
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();                                 // no CTA of a pair may leave while its peer still uses its smem / TMEM
+    else __syncthreads();
     if (threadIdx.x == 0) trace_close(g.trace, trec, g.trace_id);
     if (warp == 1) {
         __syncwarp();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(C::TMEM_COLS) : "memory");
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int BN, int EPI, bool SPLIT>
+template <int BN, int EPI, bool SPLIT, int CG = 1>
 cudaError_t launch_one(const GemmArgs& g, cudaStream_t st) {
-    using C = Cfg<BN, SPLIT>;
-    auto kern = gemm_umma_kernel<BN, EPI, SPLIT>;
+    using C = Cfg<BN, SPLIT, CG>;
+    auto kern = gemm_umma_kernel<BN, EPI, SPLIT, CG>;
     static bool configured[kMaxDevices] = {};
     if (cudaError_t e = ensure_smem(kern, C::SMEM, configured); e != cudaSuccess) return e;
     CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-    if (!make_map(&ta_hi, g.A_hi, g.M, g.K, g.lda, BM) || !make_map(&tb_hi, g.W_hi, g.N, g.K, g.ldw, BN))
+    if (!make_map(&ta_hi, g.A_hi, g.M, g.K, g.lda, BM) || !make_map(&tb_hi, g.W_hi, g.N, g.K, g.ldw, BN / CG))
         return cudaErrorInvalidValue;
     if (SPLIT) {
-        if (!make_map(&ta_lo, g.A_lo, g.M, g.K, g.lda, BM) || !make_map(&tb_lo, g.W_lo, g.N, g.K, g.ldw, BN))
+        if (!make_map(&ta_lo, g.A_lo, g.M, g.K, g.lda, BM) || !make_map(&tb_lo, g.W_lo, g.N, g.K, g.ldw, BN / CG))
             return cudaErrorInvalidValue;
     } else {
         ta_lo = ta_hi;
         tb_lo = tb_hi;
     }
     const int num_sms = sm_count();
-    const long long total = (long long)((g.N + BN - 1) / BN) * ((g.M + BM - 1) / BM) * (g.split_k > 1 ? g.split_k : 1);
-    dim3 grid((unsigned)(total < num_sms ? total : num_sms));
-    return launch_k(kern, grid, dim3(kThreads), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
+    const long long total = (long long)((g.N + BN - 1) / BN) * ((g.M + BM * CG - 1) / (BM * CG)) * (g.split_k > 1 ? g.split_k : 1);
+    if (CG == 1) {
+        dim3 grid((unsigned)(total < num_sms ? total : num_sms));
+        return launch_k(kern, grid, dim3(kThreads), C::SMEM, st, ta_hi, ta_lo, tb_hi, tb_lo, g);
+    }
+    // pairs: one cluster of 2 per TPC
+    const long long pairs = num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * (total < pairs ? total : pairs))); cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::SMEM; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kern, ta_hi, ta_lo, tb_hi, tb_lo, g);
 }
 
 template <int BN, int EPI>
 cudaError_t launch_p(const GemmArgs& g, cudaStream_t st) {
+    // CTA pairs for the wide tiles of the large (prefill / encoder) GEMMs; GemmArgs::cta_pairs = 0 keeps single CTAs
+    if constexpr (BN == 192 || BN == 256) {
+        if (g.cta_pairs && g.M >= 1024 && g.split_k <= 1)
+            return g.passes == 3 ? launch_one<BN, EPI, true, 2>(g, st) : launch_one<BN, EPI, false, 2>(g, st);
+    }
     return g.passes == 3 ? launch_one<BN, EPI, true>(g, st) : launch_one<BN, EPI, false>(g, st);
 }
 

@@ -110,6 +110,41 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the two SMs of a TPC run one MMA of M = 256.  Each CTA stages
+// its own 128 rows of A and HALF of the B tile; the leader (cluster rank 0) issues the MMA, whose B operand is read from
+// both CTAs' shared memory (same offset), and each CTA's TMEM receives its 128 accumulator rows.
+template <bool ACC>
+__device__ __forceinline__ void umma2_bf16_c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\t"
+                     "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+}
+// completion of the pair's MMAs arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+// TMA load into this CTA's shared memory whose transaction bytes are counted on a barrier given as a shared::cluster
+// address (the leader's barrier, also when the peer CTA issues the load)
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// shared::cluster address of `p` (an address in this CTA's shared memory) in the CTA of cluster rank `rank`
+__device__ __forceinline__ uint32_t cluster_addr(const void* p, uint32_t rank) {
+    uint32_t ra;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(p)), "r"(rank));
+    return ra;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ uint32_t cluster_rank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));

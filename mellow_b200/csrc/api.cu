@@ -205,6 +205,7 @@ struct Handle {
     int* cand_idx = nullptr;
     bool logits_fused = false;           // the last lm_head wrote argmax candidates instead of logits
     int *d_tokens = nullptr, *d_done = nullptr, *d_step = nullptr, *d_stop = nullptr, *d_ids = nullptr;
+    int *d_assign = nullptr, *d_merge = nullptr;   // decode attention work list / merge counters (kernels.cuh: DecodeAttnArgs::assign)
     float *wave_stage = nullptr;
     int prefix_B = 0;
     int enc_clips = 0;                   // clips of the last full encoder pass (its tail buffers feed mb_encode_heads)
@@ -218,12 +219,14 @@ struct Handle {
     int kv_fmt = kKvF32;                 // KV-cache row format (common.cuh)
     // mb_set_option (defaults from the environment switches above)
     bool use_graph = true, decode_unfused = false, skip_finished = true;
+    bool share_keys = true;              // finished rows' attention CTAs take a share of the unfinished rows' keys (B <= 128)
     int kv_prefetch = 0;                 // (tile kernel) keys per stream prefetched into L2 before the dependency wait; -1 = all
     int decode_cluster = 0;              // decode gate/up and QKV as cluster split-K GEMMs with the fused epilogue (gemm_skinny.cu)
     int prefill_attn = 1;                // causal prefill attention: 1 = tcgen05 kernel (attn_umma.cu), 0 = mma.sync kernel
     int attn_variant = 2;                // decode attention kernel: 2 = warp-autonomous + bulk copies, 1 = cp.async pieces, 0 = 64-key tiles (lm.cu)
     int decode_tails = 1;                // o_proj / down as cluster split-K tails with the norm deferred (gemm_skinny.cu)
     int wide_tiles = -1;                 // decode split-K tiling: -1 = by policy, 0 = 16-column tiles, 1 = 32-column tiles
+    int o_tail = 432, down_tail = 848;   // decode tails: cluster size * 100 + tile columns (gemm_skinny.cu: launch_gemm_tail)
     int cta_pairs = 1;                   // persistent GEMM: 1 = cta_group::2 pairs on the wide tiles of the large GEMMs
     int epilogue_rows = 0;               // persistent GEMM, plain epilogue: 1 = row-per-thread global accesses (round 1), 0 = staged 128-byte rows
     TraceBuf* trace = nullptr;           // mb_set_trace: optional in-kernel timeline of the decode kernels
@@ -476,6 +479,8 @@ int run_decode_attention(Handle* h, int l, int B, cudaStream_t st, bool skip_don
     a.tps = ((h->t_max + 63) / 64 + a.nsplit - 1) / a.nsplit;
     a.ctx_base = kPrefix; a.d_step = h->d_step;
     a.done = (skip_done && h->skip_finished) ? h->d_done : nullptr;
+    const bool share = a.done != nullptr && h->share_keys && a.nsplit == 1 && B <= 128;   // same rule as sample_and_advance
+    a.assign = share ? h->d_assign : nullptr; a.merge_count = h->d_merge;
     a.part_acc = h->part_acc; a.part_ml = h->part_ml;
     a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
     a.pf_keys = h->kv_prefetch; a.variant = h->attn_variant;
@@ -503,7 +508,7 @@ int lm_layer_decode_fused(Handle* h, int l, int n, const float* next_norm, cudaS
         GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.qkv, kHidden, n, kQkvDim, kHidden);
         g.resident = 1;
         g.trace = h->trace; g.trace_id = 1000 + l;
-        if (tails && l > 0) { g.ssq_in = h->ssq_b; g.ssq_parts = kHidden / 48; g.ssq_ld = ssq_ld; }
+        if (tails && l > 0) { g.ssq_in = h->ssq_b; g.ssq_parts = kHidden / (h->down_tail % 100); g.ssq_ld = ssq_ld; }
         g.q_out = h->q;
         g.k_cache = kv_layer(h, h->kcache, l); g.v_cache = kv_layer(h, h->vcache, l);
         g.rope_cos = h->w.rope_cos; g.rope_sin = h->w.rope_sin;
@@ -518,7 +523,7 @@ int lm_layer_decode_fused(Handle* h, int l, int n, const float* next_norm, cudaS
         g.residual = h->x; g.ldr = kHidden; g.out_f32 = h->x; g.ldo = kHidden;
         g.out_hi = h->lb_hi; g.out_lo = lo_of(h, h->lb_lo); g.ldp = kHidden; g.norm_w = k.ln2;
         g.ssq_out = h->ssq_a; g.ssq_ld = ssq_ld;
-        MB_CK(h, launch_gemm_tail(g, 4, st));
+        MB_CK(h, launch_gemm_tail(g, h->o_tail, st));
         h->launches++;
     } else {
         GemmArgs g = gemm_base(h, h->la_hi, h->la_lo, kHidden, k.o, kHidden, n, kHidden, kHidden);
@@ -534,7 +539,7 @@ int lm_layer_decode_fused(Handle* h, int l, int n, const float* next_norm, cudaS
                            : gemm_base(h, h->la_hi, h->la_lo, kHidden, k.gu, kHidden, n, 2 * kInter, kHidden);
         g.resident = 1;
         g.trace = h->trace; g.trace_id = 5000 + l;
-        if (tails) { g.ssq_in = h->ssq_a; g.ssq_parts = kHidden / 32; g.ssq_ld = ssq_ld; }
+        if (tails) { g.ssq_in = h->ssq_a; g.ssq_parts = kHidden / (h->o_tail % 100); g.ssq_ld = ssq_ld; }
         g.out_hi = h->lh_hi; g.out_lo = lo_of(h, h->lh_lo); g.ldp = kInter;
         MB_TRY(run_gemm(h, g, EPI_SWIGLU, st));
     }
@@ -544,7 +549,7 @@ int lm_layer_decode_fused(Handle* h, int l, int n, const float* next_norm, cudaS
         g.residual = h->x; g.ldr = kHidden; g.out_f32 = h->x; g.ldo = kHidden;
         g.out_hi = h->la_hi; g.out_lo = lo_of(h, h->la_lo); g.ldp = kHidden; g.norm_w = next_norm;
         g.ssq_out = h->ssq_b; g.ssq_ld = ssq_ld;
-        MB_CK(h, launch_gemm_tail(g, 8, st));
+        MB_CK(h, launch_gemm_tail(g, h->down_tail, st));
         h->launches++;
     } else {
         GemmArgs g = gemm_base(h, h->lh_hi, h->lh_lo, kInter, k.down, kInter, n, kHidden, kInter);
@@ -684,7 +689,7 @@ int sample_and_advance(Handle* h, int B, int max_len, float temperature, float t
     a.temperature = temperature; a.top_p = top_p; a.d_step = h->d_step; a.tokens_out = h->d_tokens;
     a.forced = forced; a.x_next = h->x; a.done = h->d_done; a.logits_dump = logits_dump;
     MB_CK(h, launch_sample(a, st));
-    MB_CK(h, launch_step_advance(h->d_step, h->d_done, B, h->d_stop, st));
+    MB_CK(h, launch_step_advance(h->d_step, h->d_done, B, h->d_stop, (h->share_keys && B <= 128) ? h->d_assign : nullptr, st));
     h->launches += 2;
     return 0;
 }
@@ -711,6 +716,7 @@ int do_decode(Handle* h, int B, int max_len, float temperature, float top_p, int
     MB_CK(h, cudaMemsetAsync(h->d_step, 0, sizeof(int), st));
     MB_CK(h, cudaMemsetAsync(h->d_done, 0, sizeof(int) * B, st));
     MB_CK(h, cudaMemsetAsync(h->d_stop, 0xff, sizeof(int), st));
+    MB_CK(h, cudaMemsetAsync(h->d_merge, 0, sizeof(int) * 128 * kKvHeads, st));
     MB_CK(h, cudaMemsetAsync(h->d_tokens, 0, sizeof(int) * (size_t)B * max_len, st));
     // step 0: logits come from the prefill
     MB_TRY(sample_and_advance(h, B, max_len, temperature, top_p, eos_id, logits_dump, forced, st));
@@ -861,6 +867,9 @@ static int create_body(Handle* h) {
     MB_TRY(dev_alloc(h, &h->gemm_partial, (size_t)kMaxSplitK * 128 * kHidden));
     MB_TRY(dev_alloc(h, &h->d_tokens, B * h->max_new));
     MB_TRY(dev_alloc(h, &h->d_done, B));
+    MB_TRY(dev_alloc(h, &h->d_assign, 128));
+    MB_CK(h, cudaMemset(h->d_assign, 0, 128 * sizeof(int)));
+    MB_TRY(dev_alloc(h, &h->d_merge, 128 * kKvHeads));
     MB_TRY(dev_alloc(h, &h->d_step, 4));
     MB_TRY(dev_alloc(h, &h->d_stop, 4));
     MB_TRY(dev_alloc(h, &h->d_ids, B * kTextLen));
@@ -924,9 +933,12 @@ int mb_set_option(void* hv, const char* name, int value) {
     if (n == "graph") h->use_graph = value != 0;
     else if (n == "decode_unfused") h->decode_unfused = value != 0;
     else if (n == "skip_finished") h->skip_finished = value != 0;
+    else if (n == "share_keys") h->share_keys = value != 0;
     else if (n == "kv_prefetch") h->kv_prefetch = value;
     else if (n == "wide_tiles") h->wide_tiles = value;
     else if (n == "decode_tails") h->decode_tails = value;
+    else if (n == "o_tail") h->o_tail = value;
+    else if (n == "down_tail") h->down_tail = value;
     else if (n == "epilogue_rows") h->epilogue_rows = value != 0;
     else if (n == "cta_pairs") h->cta_pairs = value != 0;
     else if (n == "attn_variant" || n == "prefill_attn") {

@@ -423,16 +423,30 @@ cudaError_t launch_skinny_epi(const GemmArgs& g, int bn, cudaStream_t st) {
 
 // Tail of a decode layer (o_proj / down_proj): cluster split-K with the residual add, the planes of x * gain and the
 // deferred-RMSNorm partials in the kernel (SkinnyCfg).  cs = 4: 32-column tiles (o_proj, K = 576 in 3+2+2+2 k-blocks);
-// cs = 8: 48-column tiles (down_proj, K = 1536 in 8 x 3 k-blocks).  g.partial / g.split_k are not used.
-cudaError_t launch_gemm_tail(const GemmArgs& g, int cs, cudaStream_t st) {
+// cs = 8: 48-column tiles (down_proj, K = 1536 in 8 x 3 k-blocks).  g.partial / g.split_k are not used.  `shape` = cluster
+// size * 100 + tile columns; the other shapes (experiments on the CTA counts, profiles/r2_decode_ab_tail_shapes.jsonl) are
+// compiled into lab builds only (MB_BUILD_LAB=1).
+template <int BN, int KBMAX, int CS>
+cudaError_t launch_tail_p(const GemmArgs& g, cudaStream_t st) {
     const int kb_all = (g.K + BK - 1) / BK;
+    if (g.N % BN != 0 || (kb_all + CS - 1) / CS > KBMAX) return cudaErrorNotSupported;
+    return g.passes == 3 ? launch_cluster<BN, EPI_GENERIC, true, KBMAX, CS>(g, st) : launch_cluster<BN, EPI_GENERIC, false, KBMAX, CS>(g, st);
+}
+
+cudaError_t launch_gemm_tail(const GemmArgs& g, int shape, cudaStream_t st) {
     if (g.M > BM || !g.out_f32 || (g.N & 3) || (g.ldo & 3) || (g.residual && (g.ldr & 3)) || (g.out_hi && (g.ldp & 3)))
         return cudaErrorInvalidValue;
-    if (cs == 4 && g.N % 32 == 0 && (kb_all + 3) / 4 <= 3)
-        return g.passes == 3 ? launch_cluster<32, EPI_GENERIC, true, 3, 4>(g, st) : launch_cluster<32, EPI_GENERIC, false, 3, 4>(g, st);
-    if (cs == 8 && g.N % 48 == 0 && (kb_all + 7) / 8 <= 3)
-        return g.passes == 3 ? launch_cluster<48, EPI_GENERIC, true, 3, 8>(g, st) : launch_cluster<48, EPI_GENERIC, false, 3, 8>(g, st);
-    return cudaErrorNotSupported;
+    switch (shape) {                                                  // cluster size * 100 + tile columns
+        case 432: return launch_tail_p<32, 3, 4>(g, st);
+        case 848: return launch_tail_p<48, 3, 8>(g, st);
+#ifdef MB_LAB
+        case 332: return launch_tail_p<32, 3, 3>(g, st);
+        case 232: return launch_tail_p<32, 5, 2>(g, st);
+        case 448: return launch_tail_p<48, 3, 4>(g, st);
+        case 648: return launch_tail_p<48, 4, 6>(g, st);
+#endif
+        default: return cudaErrorNotSupported;
+    }
 }
 
 // gate/up (+SwiGLU) and QKV (+RoPE + KV write) of a decode layer as cluster split-K GEMMs: K = 576 in 3 slices of 3

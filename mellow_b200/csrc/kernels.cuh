@@ -60,6 +60,7 @@ cudaError_t launch_prefill_attention_umma(const PrefillAttnPlanes& p, int B, int
 // causal prefill attention on the legacy tensor path (mma.sync, attn_mma.cu)
 cudaError_t launch_prefill_attention_mma(const float* q, const void* kc, const void* vc, int kv_fmt, int B, int S,
                                          int t_max, bf16* out_hi, bf16* out_lo, cudaStream_t st);
+constexpr int kAttnDynParts = 4;       // most CTAs that share the keys of one (row, kv head) under DecodeAttnArgs::assign
 struct DecodeAttnArgs {
     const float* q;                 // [B,576]
     const void* kc; const void* vc; // layer caches [B][3][t_max][64]
@@ -67,6 +68,11 @@ struct DecodeAttnArgs {
     int tps;                           // key tiles (64 keys) owned by each split: ceil(ceil(t_max/64)/nsplit)
     int ctx_base; const int* d_step;   // ctx = ctx_base + *d_step  (keys 0..ctx-1)
     const int* done;                   // optional [B]: rows that already emitted the stop token skip their K/V stream
+    // optional (nsplit == 1, B <= 128): work list written by step_advance_kernel.  assign[slot] = row |
+    // part << 8 | nparts << 16 (nparts = 0: idle slot): the CTAs of finished rows take a share of the keys of the rows
+    // that are still decoding; the nparts partial states of a (row, kv head) are merged by whichever CTA finishes last
+    // (merge_count [B][3], self-resetting), in a fixed order, through part_acc / part_ml (stride kAttnDynParts)
+    const int* assign; int* merge_count;
     float* part_acc; float* part_ml;   // [B][9][nsplit][64], [B][9][nsplit][2]
     bf16* out_hi; bf16* out_lo;        // [B,576]
     int variant;                       // 1 = warp-autonomous kernel (default), 0 = 64-key tile kernel
@@ -91,7 +97,7 @@ struct SampleArgs {
 cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, int M, const float* w, bf16* hi, bf16* lo,
                                cudaStream_t st, TraceBuf* trace = nullptr, unsigned trace_id = 0);
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st);
-cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st);
+cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, int* assign, cudaStream_t st);
 // out[i] = embed[ids[i]] (fp32 rows of 576): lm.model.embed_tokens of the reference (wrapper.py:237)
 cudaError_t launch_embed_rows(const int* ids, int n, const float* embed, float* out, cudaStream_t st);
 

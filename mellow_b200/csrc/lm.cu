@@ -327,29 +327,41 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
     constexpr int E = F24 ? 8 : 16 / sizeof(T);   // values per 16 B piece of the part the score role walks
     constexpr int NCH = kHeadDim / E;
     constexpr int NST = NCH / 2;                  // pieces each half of a lane pair walks
-    const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+    const int split = blockIdx.x, kvh = blockIdx.y, slot_b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned char* kb = reinterpret_cast<const unsigned char*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
-    const unsigned char* vb = reinterpret_cast<const unsigned char*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
-    const int k_begin = split * a.tps * 64;       // static ownership of the key range, like the tile kernel
+    // What this CTA works on: row b, share `part` of `nparts` of its keys (nparts = 0: nothing).  Without a work list:
+    // its own row, the static split.  With one (DecodeAttnArgs::assign) the entry of this slot.
+    int b, part, nparts, tps, k_begin;
+    const unsigned char *kb, *vb;
+    auto take = [&](int v, int ctx_now) {
+        b = v & 0xff; part = (v >> 8) & 0xff; nparts = (v >> 16) & 0xff;
+        if (b >= a.B || nparts > kAttnDynParts || part >= nparts) nparts = 0;   // only a stale speculative read can look like this
+        const bool shared = nparts > 1;
+        tps = shared ? ((ctx_now + 63) / 64 + nparts - 1) / nparts : a.tps;
+        k_begin = (shared ? part : split) * tps * 64;     // static ownership of the key range, like the tile kernel
+        kb = reinterpret_cast<const unsigned char*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
+        vb = reinterpret_cast<const unsigned char*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
+    };
+    int ring0 = 0;                                // ring position of chunk 0 (> 0 once early loads were discarded)
 
-    // chunk i of this warp = keys [k_begin + 16 * (warp + 4 i), +16), staged in ring slot i % ST
+    // chunk i of this warp = keys [k_begin + 16 * (warp + 4 i), +16), staged in ring slot (ring0 + i) % ST
     auto load_chunk = [&](int i, int ctx_limit) {
         const int key0 = k_begin + kAttnChunk * (warp + 4 * i);
+        const int slot = (ring0 + i) % ST;
         if constexpr (BULK) {
             if (lane == 0) {
                 // rows at and beyond ctx_limit are not copied: their slots keep zeros / older finite rows and are masked
                 const uint32_t bytes = (uint32_t)(min(kAttnChunk, ctx_limit - key0) * ROWB);
-                unsigned long long* bar = &sm.full[warp][i % ST];
+                unsigned long long* bar = &sm.full[warp][slot];
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads of the slot -> async writes
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                              ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(2u * bytes) : "memory");
-                bulk_load(&sm.k[warp][i % ST][0][0], kb + (size_t)key0 * ROWB, bytes, bar);
-                bulk_load(&sm.v[warp][i % ST][0][0], vb + (size_t)key0 * ROWB, bytes, bar);
+                bulk_load(&sm.k[warp][slot][0][0], kb + (size_t)key0 * ROWB, bytes, bar);
+                bulk_load(&sm.v[warp][slot][0][0], vb + (size_t)key0 * ROWB, bytes, bar);
             }
         } else {
-            unsigned char (*kd)[SM::KROWB] = sm.k[warp][i % ST];
-            unsigned char (*vd)[ROWB] = sm.v[warp][i % ST];
+            unsigned char (*kd)[SM::KROWB] = sm.k[warp][slot];
+            unsigned char (*vd)[ROWB] = sm.v[warp][slot];
             for (int c = lane; c < kAttnChunk * NCHB; c += 32) {
                 const int j = c / NCHB, ch = c - j * NCHB;
                 const bool ok = key0 + j < ctx_limit;
@@ -373,11 +385,18 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
     }
-    // PDL: chunks that lie inside the prefill prefix are immutable history and are requested before the wait
+    // PDL: chunks that lie inside the prefill prefix are immutable history and are requested before the wait.  The work
+    // list entry and the step counter are read SPECULATIVELY here (their producers are several kernels back, but the
+    // chain of early launches gives no guarantee) and checked after the wait; a stale guess only costs the early loads.
+    const int own = slot_b | (1 << 16);
+    const int v_spec = a.assign ? (int)__ldcg(a.assign + slot_b) : own;
+    const int ctx_spec = a.ctx_base + (a.d_step ? (int)__ldcg(a.d_step) : 0);
+    take(v_spec, ctx_spec);
+    const int tps_spec = tps;
     int n_early = 0;
 #pragma unroll
     for (int i = 0; i < ST; ++i) {
-        if (n_early == i && k_begin + kAttnChunk * (warp + 4 * i + 1) <= a.ctx_base && warp + 4 * i < a.tps * 4) {
+        if (n_early == i && nparts > 0 && k_begin + kAttnChunk * (warp + 4 * i + 1) <= a.ctx_base && warp + 4 * i < tps * 4) {
             load_chunk(i, a.ctx_base);
             if (!BULK) cp_async_commit();
             n_early = i + 1;
@@ -386,13 +405,24 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
     pdl_wait();
     if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, TR_WAITED);
     const int step_now = a.d_step ? *a.d_step : 0;
-    if (a.done && a.done[b]) {                                    // finished row: no K/V stream
+    const int ctx = a.ctx_base + step_now;
+    // SURVEY 8 row f3.  Without a work list a finished row just drops its K/V stream.  With one (written by
+    // step_advance_kernel) the slots of finished rows are handed a share of the keys of the rows still decoding.
+    const int v_now = a.assign ? a.assign[slot_b] : ((a.done && a.done[slot_b]) ? 0 : own);
+    take(v_now, ctx);
+    if (nparts > 0 && n_early > 0 && (v_now != v_spec || tps != tps_spec)) {
+        // the guess was stale: what was requested before the wait is not this CTA's key range
+        if constexpr (BULK) { for (int i = 0; i < n_early; ++i) bar_wait_parity(&sm.full[warp][i], 0); }
+        else cp_async_wait<0>();
+        __syncwarp();
+        ring0 = n_early; n_early = 0;
+    }
+    if (nparts == 0) {                                            // nothing to do: finished row / idle slot
         if constexpr (BULK) { for (int i = 0; i < n_early; ++i) bar_wait_parity(&sm.full[warp][i], 0); }
         else cp_async_wait<0>();
         return;
     }
-    const int ctx = a.ctx_base + step_now;
-    const int k_end = min(ctx, k_begin + a.tps * 64);
+    const int k_end = min(ctx, k_begin + tps * 64);
     const int n_chunks = k_end > k_begin ? (k_end - k_begin + kAttnChunk - 1) / kAttnChunk : 0;
     const int n_mine = n_chunks > warp ? (n_chunks - warp + 3) / 4 : 0;
 #pragma unroll
@@ -426,9 +456,9 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
     float acc[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     const int dp = lane * 2;                                      // PV role: this lane's pair of head dims
     for (int i = 0; i < n_mine; ++i) {
-        const int slot = i % ST;
+        const int slot = (ring0 + i) % ST;
         if constexpr (BULK) {
-            bar_wait_parity(&sm.full[warp][slot], (uint32_t)(i / ST) & 1u);
+            bar_wait_parity(&sm.full[warp][slot], (uint32_t)((ring0 + i) / ST) & 1u);
         } else {
             cp_async_wait<ST - 1>();                              // chunk i has landed (this thread's pieces) ...
             __syncwarp();                                         // ... and everybody else's
@@ -540,12 +570,47 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
             num += sc_w * sm.red[w][h][d];
             den += sc_w * sm.ml[w][h][1];
         }
-        if (a.nsplit == 1) {
+        if (nparts > 1) {                                         // key share of a work list: partial state of this part
+            const size_t o = ((size_t)b * kHeads + kvh * 3 + h) * kAttnDynParts + part;
+            a.part_acc[o * kHeadDim + d] = num;
+            if (d == 0) { a.part_ml[o * 2] = m; a.part_ml[o * 2 + 1] = den; }
+        } else if (a.nsplit == 1) {
             store_planes1(a.out_hi, a.out_lo, (size_t)b * kHidden + (kvh * 3 + h) * kHeadDim + d, num / den);
         } else {
             const size_t o = (((size_t)b * kHeads + kvh * 3 + h) * a.nsplit + split);
             a.part_acc[o * kHeadDim + d] = num;
             if (d == 0) { a.part_ml[o * 2] = m; a.part_ml[o * 2 + 1] = den; }
+        }
+    }
+    if (nparts > 1) {
+        // whichever of the nparts CTAs of this (row, kv head) finishes last merges their states, always in part order
+        __shared__ int s_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            int* cnt = a.merge_count + b * kKvHeads + kvh;
+            const int old = atomicAdd(cnt, 1);
+            s_last = old == nparts - 1;
+            if (s_last) *cnt = 0;                                  // ready for the next layer's launch
+        }
+        __syncthreads();
+        if (s_last) {
+            __threadfence();
+            for (int e = tid; e < 3 * kHeadDim; e += 128) {
+                const int h = e >> 6, d = e & 63;
+                const size_t base = ((size_t)b * kHeads + kvh * 3 + h) * kAttnDynParts;
+                float m = -INFINITY;
+                for (int s = 0; s < nparts; ++s) m = fmaxf(m, __ldcg(a.part_ml + (base + s) * 2));
+                float num = 0.f, den = 0.f;
+                for (int s = 0; s < nparts; ++s) {
+                    const float ms = __ldcg(a.part_ml + (base + s) * 2);
+                    if (ms == -INFINITY) continue;                 // a share without keys
+                    const float w = expf(ms - m);
+                    num += w * __ldcg(a.part_acc + (base + s) * kHeadDim + d);
+                    den += w * __ldcg(a.part_ml + (base + s) * 2 + 1);
+                }
+                store_planes1(a.out_hi, a.out_lo, (size_t)b * kHidden + (kvh * 3 + h) * kHeadDim + d, num / den);
+            }
         }
     }
     if (tid == 0) trace_close(a.trace, trec, a.trace_id);
@@ -679,15 +744,41 @@ __global__ void __launch_bounds__(160) add_rmsnorm_row_kernel(float* __restrict_
     if (t == 0) trace_close(trace, trec, trace_id);
 }
 
-// step += 1; records the first step count at which every row has emitted eos (wrapper.py:247-249)
-__global__ void step_advance_kernel(int* d_step, const int* done, int B, int* d_stop_step) {
+// step += 1; records the first step count at which every row has emitted eos (wrapper.py:247-249).  assign != nullptr
+// (B <= 128 = blockDim): also the work list of the next step's decode attention (DecodeAttnArgs::assign).  With n rows
+// still decoding and m = B - n finished, every live row is cut into P = min(kAttnDynParts, B / n) key shares: the row's
+// own slot keeps share 0 (its keys from 0 on: what it requests before its dependency wait stays valid), the j-th
+// finished slot takes share 1 + j / n of the (j % n)-th live row, the remaining finished slots idle.
+__global__ void __launch_bounds__(128) step_advance_kernel(int* d_step, const int* done, int B, int* d_stop_step, int* assign) {
     __shared__ int all;
+    __shared__ int wcnt[4];
+    __shared__ int act[128];
     pdl_trigger();
     pdl_wait();
     if (threadIdx.x == 0) all = 1;
     __syncthreads();
     for (int b = threadIdx.x; b < B; b += blockDim.x)
         if (!done[b]) all = 0;
+    if (assign != nullptr) {
+        const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+        const bool live = t < B && !done[t];
+        const unsigned bal = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) wcnt[warp] = __popc(bal);
+        __syncthreads();
+        int pos = __popc(bal & ((1u << lane) - 1u)), n = 0;     // live rows before this one; live rows in all
+        for (int w = 0; w < 4; ++w) { if (w < warp) pos += wcnt[w]; n += wcnt[w]; }
+        if (live) act[pos] = t;
+        __syncthreads();
+        if (t < B) {
+            int P = n > 0 ? B / n : 0;
+            if (P > kAttnDynParts) P = kAttnDynParts;
+            const int j = t - pos;                               // finished rows before this one
+            int v = 0;
+            if (live) v = t | (P << 16);
+            else if (n > 0 && 1 + j / n < P) v = act[j % n] | ((1 + j / n) << 8) | (P << 16);
+            assign[t] = v;
+        }
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         const int s = *d_step + 1;
@@ -774,8 +865,9 @@ cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st) {
     return launch_k(sample_kernel, dim3(a.B), dim3(1024), 0, st, a);
 }
 
-cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, cudaStream_t st) {
-    return launch_k(step_advance_kernel, dim3(1), dim3(128), 0, st, d_step, done, B, d_stop_step);
+cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, int* assign, cudaStream_t st) {
+    if (assign != nullptr && B > 128) return cudaErrorInvalidValue;
+    return launch_k(step_advance_kernel, dim3(1), dim3(128), 0, st, d_step, done, B, d_stop_step, assign);
 }
 
 }  // namespace mb

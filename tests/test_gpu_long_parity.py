@@ -126,6 +126,54 @@ def test_batch_128_runs_300_steps_like_the_reference(engine):
         eng.close()
 
 
+def test_finished_rows_hand_their_attention_ctas_to_the_live_rows(engine):
+    """SURVEY 8 row f3 (option share_keys): rows that emitted the stop token leave the batch on the device; their
+    decode-attention CTAs then take a share of the keys of the rows still decoding (2, then 4 CTAs per row and kv head, then
+    idle slots).  The live rows must keep producing the reference's logits / ids while 64, 96 and 112 of the 128 rows
+    finish (teacher forcing: the forced stop token sets the row's done flag)."""
+    from mellow_b200.engine import Engine
+    g = _golden("long1234")
+    _, w1, w2, ids, steps = _maker().set_inputs("long1234")
+    ref = torch.from_numpy(g["tokens"]).to(torch.int32)                      # (2, 300)
+    margins = (g["top8_vals"][..., 0] - g["top8_vals"][..., 1]).T            # (2, steps)
+    B, live = 128, 16
+    forced = ref.repeat(64, 1).contiguous()                                  # row r is a copy of pair r % 2
+    forced[64:, 2] = 0                                                       # 64 rows stop: 2 CTAs per live row and kv head
+    forced[32:64, 4] = 0                                                     # 96 stopped: 4 CTAs
+    forced[16:32, 8] = 0                                                     # 112 stopped: 4 CTAs, 64 idle slots
+    eng = Engine(None, device=0, max_batch=B, max_new_tokens=steps, policy="split24", arena=engine.arena)
+    try:
+        eng.encode(w1.repeat(64, 1), w2.repeat(64, 1))
+
+        def run(n, **kw):
+            eng.prefix(ids.repeat(64, 1))
+            eng.prefill(B, want_logits=False)
+            return eng.decode(B, n, forced_tokens=forced[:, :n].contiguous().cuda(), **kw)
+
+        # (i) logits of the live rows over the steps that cross the three hand-overs (individual launches)
+        n = 16
+        own, dump = run(n, dump_logits=True)
+        dump = dump[:, :live].cpu()                                          # (n, live, V)
+        assert torch.isfinite(dump).all()
+        top_ids = torch.from_numpy(g["top8_ids"][:n]).repeat(1, live // 2, 1)   # (n, live, 8): row r -> pair r % 2
+        top_vals = torch.from_numpy(g["top8_vals"][:n]).repeat(1, live // 2, 1)
+        err = (torch.gather(dump, 2, top_ids) - top_vals).abs().max().item()
+        assert err < LOGIT_TOL, f"live rows' top-8 logits off by {err:.2e} while finished rows hand over their CTAs"
+        # (ii) 300 steps under the CUDA graph: ids of the live rows, against the reference and against share_keys = 0
+        shared = run(steps).cpu()
+        eng.set_option("share_keys", 0)
+        plain = run(steps).cpu()
+        decided = torch.from_numpy(margins >= MARGIN_GATE)                   # (2, steps)
+        for r in range(live):
+            d = decided[r % 2]
+            assert torch.equal(shared[r][d], ref[r % 2][d]), f"row {r}: ids differ from the reference on a decided step"
+            assert torch.equal(shared[r][d], plain[r][d]), f"row {r}: share_keys changes a decided id"
+        print(f"share_keys: live-row top-8 logits within {err:.2e}; ids identical to share_keys=0 on "
+              f"{(shared[:live] == plain[:live]).float().mean().item():.4f} of the steps")
+    finally:
+        eng.close()
+
+
 def test_config0_reference_wavs_through_the_wrapper():
     """BASELINE.json configs[0]: resource/1.wav + 2.wav, random.seed(0), 30 greedy steps through MellowWrapper.generate()
     (GPU resampler, tile / crop, stand-in tokenizer) against ids produced by the reference classes from audio prepared

@@ -56,6 +56,10 @@ long long mb_workspace_bytes(void* h);
  *                        of the keys of the rows that are still decoding (up to 4 CTAs per row and kv head, work list kept
  *                        on the device by the step kernel, partial softmax states merged in a fixed order by the CTA that
  *                        finishes last); 0 = finished rows only drop their own K/V stream
+ *   "attn_self_merge" (0) decode attention of batches < 128 rows (keys of a row split statically over several CTAs): 0 = a
+ *                        separate combine kernel merges the partial softmax states, 1 = the CTA that finishes last does
+ *                        (the share_keys mechanism; measured 3 % slower per step here: fence + atomic + re-read cost more
+ *                        than a dependent launch)
  *   "o_tail", "down_tail" (432, 848) shape of the decode tail GEMMs, cluster size * 100 + tile columns; other shapes
  *                        exist in lab builds only (measured: profiles/r2_decode_ab_tail_shapes.jsonl)
  *   "prefill_attn"   (1) causal prefill attention: 1 = tcgen05 kernel (TMA-fed bf16 operand planes, S / O in TMEM);

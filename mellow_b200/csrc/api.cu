@@ -219,6 +219,7 @@ struct Handle {
     int kv_fmt = kKvF32;                 // KV-cache row format (common.cuh)
     // mb_set_option (defaults from the environment switches above)
     bool use_graph = true, decode_unfused = false, skip_finished = true;
+    int attn_self_merge = 0;             // decode attention with statically split keys (< 128 rows): 1 = the last CTA of a (row, kv head) merges, 0 = combine kernel (faster: profiles/r2_decode_ab_self_merge.jsonl)
     bool share_keys = true;              // finished rows' attention CTAs take a share of the unfinished rows' keys (B <= 128)
     int kv_prefetch = 0;                 // (tile kernel) keys per stream prefetched into L2 before the dependency wait; -1 = all
     int decode_cluster = 0;              // decode gate/up and QKV as cluster split-K GEMMs with the fused epilogue (gemm_skinny.cu)
@@ -481,12 +482,13 @@ int run_decode_attention(Handle* h, int l, int B, cudaStream_t st, bool skip_don
     a.done = (skip_done && h->skip_finished) ? h->d_done : nullptr;
     const bool share = a.done != nullptr && h->share_keys && a.nsplit == 1 && B <= 128;   // same rule as sample_and_advance
     a.assign = share ? h->d_assign : nullptr; a.merge_count = h->d_merge;
+    a.self_merge = h->attn_self_merge;
     a.part_acc = h->part_acc; a.part_ml = h->part_ml;
     a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
     a.pf_keys = h->kv_prefetch; a.variant = h->attn_variant;
     a.trace = h->trace; a.trace_id = 2000 + l;
     MB_CK(h, launch_decode_attention(a, st));
-    h->launches += a.nsplit == 1 ? 1 : 2;
+    h->launches += (a.nsplit == 1 || (a.variant != 0 && a.self_merge)) ? 1 : 2;
     return 0;
 }
 
@@ -870,6 +872,7 @@ static int create_body(Handle* h) {
     MB_TRY(dev_alloc(h, &h->d_assign, 128));
     MB_CK(h, cudaMemset(h->d_assign, 0, 128 * sizeof(int)));
     MB_TRY(dev_alloc(h, &h->d_merge, 128 * kKvHeads));
+    MB_CK(h, cudaMemset(h->d_merge, 0, 128 * kKvHeads * sizeof(int)));
     MB_TRY(dev_alloc(h, &h->d_step, 4));
     MB_TRY(dev_alloc(h, &h->d_stop, 4));
     MB_TRY(dev_alloc(h, &h->d_ids, B * kTextLen));
@@ -934,6 +937,7 @@ int mb_set_option(void* hv, const char* name, int value) {
     else if (n == "decode_unfused") h->decode_unfused = value != 0;
     else if (n == "skip_finished") h->skip_finished = value != 0;
     else if (n == "share_keys") h->share_keys = value != 0;
+    else if (n == "attn_self_merge") h->attn_self_merge = value != 0;
     else if (n == "kv_prefetch") h->kv_prefetch = value;
     else if (n == "wide_tiles") h->wide_tiles = value;
     else if (n == "decode_tails") h->decode_tails = value;

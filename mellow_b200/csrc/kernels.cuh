@@ -73,6 +73,7 @@ struct DecodeAttnArgs {
     // that are still decoding; the nparts partial states of a (row, kv head) are merged by whichever CTA finishes last
     // (merge_count [B][3], self-resetting), in a fixed order, through part_acc / part_ml (stride kAttnDynParts)
     const int* assign; int* merge_count;
+    int self_merge;                    // nsplit > 1: 1 = the same in-kernel merge for the static splits, 0 = decode_combine_kernel
     float* part_acc; float* part_ml;   // [B][9][nsplit][64], [B][9][nsplit][2]
     bf16* out_hi; bf16* out_lo;        // [B,576]
     int variant;                       // 1 = warp-autonomous kernel (default), 0 = 64-key tile kernel

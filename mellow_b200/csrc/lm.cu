@@ -557,6 +557,9 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
         if (lane == 0) { sm.ml[warp][h][0] = m_run[h]; sm.ml[warp][h][1] = l_run[h]; }
     }
     __syncthreads();
+    // CTAs that share the keys of this (row, kv head): the shares of a work list, else the static split
+    const int mparts = nparts > 1 ? nparts : a.nsplit, mpart = nparts > 1 ? part : split;
+    const int mstride = nparts > 1 ? kAttnDynParts : a.nsplit;
     for (int e = tid; e < 3 * kHeadDim; e += 128) {               // merge the four warp states (fixed order)
         const int h = e >> 6, d = e & 63;
         float m = sm.ml[0][h][0];
@@ -570,27 +573,24 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
             num += sc_w * sm.red[w][h][d];
             den += sc_w * sm.ml[w][h][1];
         }
-        if (nparts > 1) {                                         // key share of a work list: partial state of this part
-            const size_t o = ((size_t)b * kHeads + kvh * 3 + h) * kAttnDynParts + part;
-            a.part_acc[o * kHeadDim + d] = num;
-            if (d == 0) { a.part_ml[o * 2] = m; a.part_ml[o * 2 + 1] = den; }
-        } else if (a.nsplit == 1) {
+        if (mparts == 1) {
             store_planes1(a.out_hi, a.out_lo, (size_t)b * kHidden + (kvh * 3 + h) * kHeadDim + d, num / den);
-        } else {
-            const size_t o = (((size_t)b * kHeads + kvh * 3 + h) * a.nsplit + split);
+        } else {                                                  // partial state of this share of the keys
+            const size_t o = ((size_t)b * kHeads + kvh * 3 + h) * mstride + mpart;
             a.part_acc[o * kHeadDim + d] = num;
             if (d == 0) { a.part_ml[o * 2] = m; a.part_ml[o * 2 + 1] = den; }
         }
     }
-    if (nparts > 1) {
-        // whichever of the nparts CTAs of this (row, kv head) finishes last merges their states, always in part order
+    if (mparts > 1 && (nparts > 1 || a.self_merge)) {
+        // whichever of the mparts CTAs of this (row, kv head) finishes last merges their states, always in share order
+        // (no combine kernel: one dependent launch less per layer for the batches whose keys are split statically)
         __shared__ int s_last;
         __threadfence();
         __syncthreads();
         if (tid == 0) {
             int* cnt = a.merge_count + b * kKvHeads + kvh;
             const int old = atomicAdd(cnt, 1);
-            s_last = old == nparts - 1;
+            s_last = old == mparts - 1;
             if (s_last) *cnt = 0;                                  // ready for the next layer's launch
         }
         __syncthreads();
@@ -598,11 +598,11 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
             __threadfence();
             for (int e = tid; e < 3 * kHeadDim; e += 128) {
                 const int h = e >> 6, d = e & 63;
-                const size_t base = ((size_t)b * kHeads + kvh * 3 + h) * kAttnDynParts;
+                const size_t base = ((size_t)b * kHeads + kvh * 3 + h) * mstride;
                 float m = -INFINITY;
-                for (int s = 0; s < nparts; ++s) m = fmaxf(m, __ldcg(a.part_ml + (base + s) * 2));
+                for (int s = 0; s < mparts; ++s) m = fmaxf(m, __ldcg(a.part_ml + (base + s) * 2));
                 float num = 0.f, den = 0.f;
-                for (int s = 0; s < nparts; ++s) {
+                for (int s = 0; s < mparts; ++s) {
                     const float ms = __ldcg(a.part_ml + (base + s) * 2);
                     if (ms == -INFINITY) continue;                 // a share without keys
                     const float w = expf(ms - m);
@@ -844,7 +844,7 @@ cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
         return cudaErrorNotSupported;                     // variants 0 / 1 exist in lab builds only (MB_BUILD_LAB=1)
 #endif
     }
-    if (e != cudaSuccess || a.nsplit == 1) return e;
+    if (e != cudaSuccess || a.nsplit == 1 || (a.variant != 0 && a.self_merge)) return e;   // the warp kernels can merge their splits themselves
     return launch_k(decode_combine_kernel, dim3(kHeads, a.B), dim3(64), 0, st, a);
 }
 

@@ -52,14 +52,11 @@ long long mb_workspace_bytes(void* h);
  *   "decode_unfused" (0) 1 = use the generic per-layer decode path (the one batches > 128 rows take) for every batch
  *   "skip_finished"  (1) rows that emitted eos_id stop streaming their KV cache (their later tokens are not meaningful);
  *                        0 = every row keeps decoding until all rows have stopped, like the reference loop
- *   "share_keys"     (1) with skip_finished, batches of <= 128 rows: the decode-attention CTAs of finished rows take a share
- *                        of the keys of the rows that are still decoding (up to 4 CTAs per row and kv head, work list kept
- *                        on the device by the step kernel, partial softmax states merged in a fixed order by the CTA that
- *                        finishes last); 0 = finished rows only drop their own K/V stream
- *   "attn_self_merge" (0) decode attention of batches < 128 rows (keys of a row split statically over several CTAs): 0 = a
- *                        separate combine kernel merges the partial softmax states, 1 = the CTA that finishes last does
- *                        (the share_keys mechanism; measured 3 % slower per step here: fence + atomic + re-read cost more
- *                        than a dependent launch)
+ *   "share_keys"     (1) with skip_finished, batches of 128 rows: once two thirds of the rows have finished (seen by the
+ *                        16-step stop poll), the decode-attention CTAs of finished rows take a share of the keys of the rows
+ *                        that are still decoding (3 or 4 CTAs per row and kv head, work list kept on the device by the step
+ *                        kernel, partial softmax states merged in a fixed order by the CTA that finishes last);
+ *                        0 = finished rows only drop their own K/V stream
  *   "o_tail", "down_tail" (432, 848) shape of the decode tail GEMMs, cluster size * 100 + tile columns; other shapes
  *                        exist in lab builds only (measured: profiles/r2_decode_ab_tail_shapes.jsonl)
  *   "prefill_attn"   (1) causal prefill attention: 1 = tcgen05 kernel (TMA-fed bf16 operand planes, S / O in TMEM);

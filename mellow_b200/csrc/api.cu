@@ -212,6 +212,8 @@ struct Handle {
     // decode graph cache
     cudaGraphExec_t graph = nullptr;
     int g_B = 0, g_max_len = 0, g_eos = 0, g_launches = 0;
+    cudaGraphExec_t graph_share = nullptr;   // the same step with the work-list decode attention (rows have finished)
+    bool share_now = false;              // decode attention launches follow the work list (set by the decode loop)
     float g_temp = 0.f;
     const int* g_forced = nullptr;
     cudaStream_t g_stream = nullptr;
@@ -219,7 +221,6 @@ struct Handle {
     int kv_fmt = kKvF32;                 // KV-cache row format (common.cuh)
     // mb_set_option (defaults from the environment switches above)
     bool use_graph = true, decode_unfused = false, skip_finished = true;
-    int attn_self_merge = 0;             // decode attention with statically split keys (< 128 rows): 1 = the last CTA of a (row, kv head) merges, 0 = combine kernel (faster: profiles/r2_decode_ab_self_merge.jsonl)
     bool share_keys = true;              // finished rows' attention CTAs take a share of the unfinished rows' keys (B <= 128)
     int kv_prefetch = 0;                 // (tile kernel) keys per stream prefetched into L2 before the dependency wait; -1 = all
     int decode_cluster = 0;              // decode gate/up and QKV as cluster split-K GEMMs with the fused epilogue (gemm_skinny.cu)
@@ -234,6 +235,7 @@ struct Handle {
 };
 inline void drop_graph(Handle* h) {
     if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }
+    if (h->graph_share) { cudaGraphExecDestroy(h->graph_share); h->graph_share = nullptr; }
 }
 
 inline cudaStream_t pick_stream(Handle* h, void* stream) { return stream ? (cudaStream_t)stream : h->own_stream; }
@@ -480,15 +482,14 @@ int run_decode_attention(Handle* h, int l, int B, cudaStream_t st, bool skip_don
     a.tps = ((h->t_max + 63) / 64 + a.nsplit - 1) / a.nsplit;
     a.ctx_base = kPrefix; a.d_step = h->d_step;
     a.done = (skip_done && h->skip_finished) ? h->d_done : nullptr;
-    const bool share = a.done != nullptr && h->share_keys && a.nsplit == 1 && B <= 128;   // same rule as sample_and_advance
+    const bool share = a.done != nullptr && h->share_now && a.nsplit == 1 && B <= 128;    // the list is kept by sample_and_advance
     a.assign = share ? h->d_assign : nullptr; a.merge_count = h->d_merge;
-    a.self_merge = h->attn_self_merge;
     a.part_acc = h->part_acc; a.part_ml = h->part_ml;
     a.out_hi = h->la_hi; a.out_lo = lo_of(h, h->la_lo);
     a.pf_keys = h->kv_prefetch; a.variant = h->attn_variant;
     a.trace = h->trace; a.trace_id = 2000 + l;
     MB_CK(h, launch_decode_attention(a, st));
-    h->launches += (a.nsplit == 1 || (a.variant != 0 && a.self_merge)) ? 1 : 2;
+    h->launches += a.nsplit == 1 ? 1 : 2;
     return 0;
 }
 
@@ -691,7 +692,8 @@ int sample_and_advance(Handle* h, int B, int max_len, float temperature, float t
     a.temperature = temperature; a.top_p = top_p; a.d_step = h->d_step; a.tokens_out = h->d_tokens;
     a.forced = forced; a.x_next = h->x; a.done = h->d_done; a.logits_dump = logits_dump;
     MB_CK(h, launch_sample(a, st));
-    MB_CK(h, launch_step_advance(h->d_step, h->d_done, B, h->d_stop, (h->share_keys && B <= 128) ? h->d_assign : nullptr, st));
+    // the work list of the decode attention is kept only while the loop runs the work-list kernel (do_decode)
+    MB_CK(h, launch_step_advance(h->d_step, h->d_done, B, h->d_stop, h->share_now ? h->d_assign : nullptr, 1, st));
     h->launches += 2;
     return 0;
 }
@@ -718,52 +720,71 @@ int do_decode(Handle* h, int B, int max_len, float temperature, float top_p, int
     MB_CK(h, cudaMemsetAsync(h->d_step, 0, sizeof(int), st));
     MB_CK(h, cudaMemsetAsync(h->d_done, 0, sizeof(int) * B, st));
     MB_CK(h, cudaMemsetAsync(h->d_stop, 0xff, sizeof(int), st));
+    MB_CK(h, cudaMemsetAsync(h->d_stop + 1, 0, sizeof(int), st));
     MB_CK(h, cudaMemsetAsync(h->d_merge, 0, sizeof(int) * 128 * kKvHeads, st));
     MB_CK(h, cudaMemsetAsync(h->d_tokens, 0, sizeof(int) * (size_t)B * max_len, st));
+    const bool use_graph = !logits_dump && h->use_graph;      // teacher forcing replays the graph too (the pointer is part of its key)
+    // SURVEY 8 row f3 (option share_keys): once the poll below has seen two thirds of the rows finished, the steps run
+    // with the work-list decode attention (finished rows' CTAs take key shares of the live rows, 3 or 4 per row).
+    // Until then the plain kernel runs (faster when nobody shares, and two shares per row do not pay for their
+    // merge).  Individual launches (parity dumps) use the work list from the first step.
+    const bool can_share = h->share_keys && h->skip_finished && B <= 128 && decode_nsplit(h, B) == 1 &&
+                           B <= 128 && h->engine == 1 && !h->decode_unfused;
+    h->share_now = can_share && !use_graph;
     // step 0: logits come from the prefill
     MB_TRY(sample_and_advance(h, B, max_len, temperature, top_p, eos_id, logits_dump, forced, st));
-    const bool use_graph = !logits_dump && h->use_graph;      // teacher forcing replays the graph too (the pointer is part of its key)
-    int stop = -1;
+    int stop[2] = {-1, 0};                                    // {first step at which every row had stopped, finished rows}
     if (use_graph && max_len > 1) {
         const bool hit = h->graph && h->g_B == B && h->g_max_len == max_len && h->g_eos == eos_id &&
                          h->g_temp == temperature && h->g_stream == st && h->g_forced == forced;
         if (!hit) {
             drop_graph(h);
-            cudaGraph_t graph = nullptr;
-            const long long before = h->launches;
-            MB_CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            int rc = decode_step(h, B, /*fused=*/true, st);
-            if (rc == 0) rc = sample_and_advance(h, B, max_len, temperature, top_p, eos_id, nullptr, forced, st);
-            cudaError_t ce = cudaStreamEndCapture(st, &graph);
-            if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
-            MB_CK(h, ce);
-            h->g_launches = (int)(h->launches - before);
-            h->launches = before;
-            MB_CK(h, cudaGraphInstantiate(&h->graph, graph, 0));
-            cudaGraphDestroy(graph);
             h->g_B = B; h->g_max_len = max_len; h->g_eos = eos_id; h->g_temp = temperature; h->g_stream = st; h->g_forced = forced;
         }
     }
+    auto capture = [&](cudaGraphExec_t* exec) -> int {
+        cudaGraph_t graph = nullptr;
+        const long long before = h->launches;
+        MB_CK(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        int rc = decode_step(h, B, /*fused=*/true, st);
+        if (rc == 0) rc = sample_and_advance(h, B, max_len, temperature, top_p, eos_id, nullptr, forced, st);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc != 0) { if (graph) cudaGraphDestroy(graph); return rc; }
+        MB_CK(h, ce);
+        h->g_launches = (int)(h->launches - before);
+        h->launches = before;
+        MB_CK(h, cudaGraphInstantiate(exec, graph, 0));
+        cudaGraphDestroy(graph);
+        return 0;
+    };
     for (int s = 1; s < max_len; ++s) {
         if (use_graph) {
-            MB_CK(h, cudaGraphLaunch(h->graph, st));
+            cudaGraphExec_t* exec = h->share_now ? &h->graph_share : &h->graph;
+            if (*exec == nullptr) MB_TRY(capture(exec));
+            MB_CK(h, cudaGraphLaunch(*exec, st));
             h->launches += h->g_launches;
         } else {
             MB_TRY(decode_step(h, B, /*fused=*/logits_dump == nullptr, st));
             MB_TRY(sample_and_advance(h, B, max_len, temperature, top_p, eos_id, logits_dump, forced, st));
         }
         if ((s & 15) == 0) {          // the reference syncs every step (wrapper.py:248); poll the stop flag sparsely
-            MB_CK(h, cudaMemcpyAsync(&stop, h->d_stop, sizeof(int), cudaMemcpyDeviceToHost, st));
+            MB_CK(h, cudaMemcpyAsync(stop, h->d_stop, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
             MB_CK(h, cudaStreamSynchronize(st));
-            if (stop >= 0) break;
+            if (stop[0] >= 0) break;
+            if (can_share && !h->share_now && stop[1] < B && B / (B - stop[1]) >= 3) {     // >= 3 key shares per live row
+                MB_CK(h, launch_step_advance(h->d_step, h->d_done, B, h->d_stop, h->d_assign, /*advance=*/0, st));   // build the list
+                h->launches++;
+                h->share_now = true;
+            }
         }
     }
-    MB_CK(h, cudaMemcpyAsync(&stop, h->d_stop, sizeof(int), cudaMemcpyDeviceToHost, st));
+    h->share_now = false;
+    MB_CK(h, cudaMemcpyAsync(stop, h->d_stop, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (tokens_out)
         MB_CK(h, cudaMemcpyAsync(tokens_out, h->d_tokens, sizeof(int) * (size_t)B * max_len,
                                  tokens_on_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, st));
     MB_CK(h, cudaStreamSynchronize(st));
-    if (steps_out_host) *steps_out_host = stop >= 0 ? stop : max_len;
+    if (steps_out_host) *steps_out_host = stop[0] >= 0 ? stop[0] : max_len;
     return 0;
 }
 
@@ -803,7 +824,7 @@ void mb_destroy(void* hv) {
     if (!hv) return;
     Handle* h = reinterpret_cast<Handle*>(hv);
     cudaSetDevice(h->device);
-    if (h->graph) cudaGraphExecDestroy(h->graph);
+    drop_graph(h);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     for (void* p : h->allocs) cudaFree(p);
     delete h;
@@ -937,7 +958,6 @@ int mb_set_option(void* hv, const char* name, int value) {
     else if (n == "decode_unfused") h->decode_unfused = value != 0;
     else if (n == "skip_finished") h->skip_finished = value != 0;
     else if (n == "share_keys") h->share_keys = value != 0;
-    else if (n == "attn_self_merge") h->attn_self_merge = value != 0;
     else if (n == "kv_prefetch") h->kv_prefetch = value;
     else if (n == "wide_tiles") h->wide_tiles = value;
     else if (n == "decode_tails") h->decode_tails = value;

@@ -73,7 +73,6 @@ struct DecodeAttnArgs {
     // that are still decoding; the nparts partial states of a (row, kv head) are merged by whichever CTA finishes last
     // (merge_count [B][3], self-resetting), in a fixed order, through part_acc / part_ml (stride kAttnDynParts)
     const int* assign; int* merge_count;
-    int self_merge;                    // nsplit > 1: 1 = the same in-kernel merge for the static splits, 0 = decode_combine_kernel
     float* part_acc; float* part_ml;   // [B][9][nsplit][64], [B][9][nsplit][2]
     bf16* out_hi; bf16* out_lo;        // [B,576]
     int variant;                       // 1 = warp-autonomous kernel (default), 0 = 64-key tile kernel
@@ -98,7 +97,7 @@ struct SampleArgs {
 cudaError_t launch_add_rmsnorm(float* x, const float* partial, int n_partial, int M, const float* w, bf16* hi, bf16* lo,
                                cudaStream_t st, TraceBuf* trace = nullptr, unsigned trace_id = 0);
 cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st);
-cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, int* assign, cudaStream_t st);
+cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, int* assign, int advance, cudaStream_t st);
 // out[i] = embed[ids[i]] (fp32 rows of 576): lm.model.embed_tokens of the reference (wrapper.py:237)
 cudaError_t launch_embed_rows(const int* ids, int n, const float* embed, float* out, cudaStream_t st);
 

@@ -327,41 +327,29 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
     constexpr int E = F24 ? 8 : 16 / sizeof(T);   // values per 16 B piece of the part the score role walks
     constexpr int NCH = kHeadDim / E;
     constexpr int NST = NCH / 2;                  // pieces each half of a lane pair walks
-    const int split = blockIdx.x, kvh = blockIdx.y, slot_b = blockIdx.z;
+    const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // What this CTA works on: row b, share `part` of `nparts` of its keys (nparts = 0: nothing).  Without a work list:
-    // its own row, the static split.  With one (DecodeAttnArgs::assign) the entry of this slot.
-    int b, part, nparts, tps, k_begin;
-    const unsigned char *kb, *vb;
-    auto take = [&](int v, int ctx_now) {
-        b = v & 0xff; part = (v >> 8) & 0xff; nparts = (v >> 16) & 0xff;
-        if (b >= a.B || nparts > kAttnDynParts || part >= nparts) nparts = 0;   // only a stale speculative read can look like this
-        const bool shared = nparts > 1;
-        tps = shared ? ((ctx_now + 63) / 64 + nparts - 1) / nparts : a.tps;
-        k_begin = (shared ? part : split) * tps * 64;     // static ownership of the key range, like the tile kernel
-        kb = reinterpret_cast<const unsigned char*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
-        vb = reinterpret_cast<const unsigned char*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
-    };
-    int ring0 = 0;                                // ring position of chunk 0 (> 0 once early loads were discarded)
+    const unsigned char* kb = reinterpret_cast<const unsigned char*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
+    const unsigned char* vb = reinterpret_cast<const unsigned char*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
+    const int k_begin = split * a.tps * 64;       // static ownership of the key range, like the tile kernel
 
-    // chunk i of this warp = keys [k_begin + 16 * (warp + 4 i), +16), staged in ring slot (ring0 + i) % ST
+    // chunk i of this warp = keys [k_begin + 16 * (warp + 4 i), +16), staged in ring slot i % ST
     auto load_chunk = [&](int i, int ctx_limit) {
         const int key0 = k_begin + kAttnChunk * (warp + 4 * i);
-        const int slot = (ring0 + i) % ST;
         if constexpr (BULK) {
             if (lane == 0) {
                 // rows at and beyond ctx_limit are not copied: their slots keep zeros / older finite rows and are masked
                 const uint32_t bytes = (uint32_t)(min(kAttnChunk, ctx_limit - key0) * ROWB);
-                unsigned long long* bar = &sm.full[warp][slot];
+                unsigned long long* bar = &sm.full[warp][i % ST];
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads of the slot -> async writes
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                              ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(2u * bytes) : "memory");
-                bulk_load(&sm.k[warp][slot][0][0], kb + (size_t)key0 * ROWB, bytes, bar);
-                bulk_load(&sm.v[warp][slot][0][0], vb + (size_t)key0 * ROWB, bytes, bar);
+                bulk_load(&sm.k[warp][i % ST][0][0], kb + (size_t)key0 * ROWB, bytes, bar);
+                bulk_load(&sm.v[warp][i % ST][0][0], vb + (size_t)key0 * ROWB, bytes, bar);
             }
         } else {
-            unsigned char (*kd)[SM::KROWB] = sm.k[warp][slot];
-            unsigned char (*vd)[ROWB] = sm.v[warp][slot];
+            unsigned char (*kd)[SM::KROWB] = sm.k[warp][i % ST];
+            unsigned char (*vd)[ROWB] = sm.v[warp][i % ST];
             for (int c = lane; c < kAttnChunk * NCHB; c += 32) {
                 const int j = c / NCHB, ch = c - j * NCHB;
                 const bool ok = key0 + j < ctx_limit;
@@ -385,18 +373,11 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
     }
-    // PDL: chunks that lie inside the prefill prefix are immutable history and are requested before the wait.  The work
-    // list entry and the step counter are read SPECULATIVELY here (their producers are several kernels back, but the
-    // chain of early launches gives no guarantee) and checked after the wait; a stale guess only costs the early loads.
-    const int own = slot_b | (1 << 16);
-    const int v_spec = a.assign ? (int)__ldcg(a.assign + slot_b) : own;
-    const int ctx_spec = a.ctx_base + (a.d_step ? (int)__ldcg(a.d_step) : 0);
-    take(v_spec, ctx_spec);
-    const int tps_spec = tps;
+    // PDL: chunks that lie inside the prefill prefix are immutable history and are requested before the wait
     int n_early = 0;
 #pragma unroll
     for (int i = 0; i < ST; ++i) {
-        if (n_early == i && nparts > 0 && k_begin + kAttnChunk * (warp + 4 * i + 1) <= a.ctx_base && warp + 4 * i < tps * 4) {
+        if (n_early == i && k_begin + kAttnChunk * (warp + 4 * i + 1) <= a.ctx_base && warp + 4 * i < a.tps * 4) {
             load_chunk(i, a.ctx_base);
             if (!BULK) cp_async_commit();
             n_early = i + 1;
@@ -405,24 +386,13 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
     pdl_wait();
     if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, TR_WAITED);
     const int step_now = a.d_step ? *a.d_step : 0;
-    const int ctx = a.ctx_base + step_now;
-    // SURVEY 8 row f3.  Without a work list a finished row just drops its K/V stream.  With one (written by
-    // step_advance_kernel) the slots of finished rows are handed a share of the keys of the rows still decoding.
-    const int v_now = a.assign ? a.assign[slot_b] : ((a.done && a.done[slot_b]) ? 0 : own);
-    take(v_now, ctx);
-    if (nparts > 0 && n_early > 0 && (v_now != v_spec || tps != tps_spec)) {
-        // the guess was stale: what was requested before the wait is not this CTA's key range
-        if constexpr (BULK) { for (int i = 0; i < n_early; ++i) bar_wait_parity(&sm.full[warp][i], 0); }
-        else cp_async_wait<0>();
-        __syncwarp();
-        ring0 = n_early; n_early = 0;
-    }
-    if (nparts == 0) {                                            // nothing to do: finished row / idle slot
+    if (a.done && a.done[b]) {                                    // finished row: no K/V stream
         if constexpr (BULK) { for (int i = 0; i < n_early; ++i) bar_wait_parity(&sm.full[warp][i], 0); }
         else cp_async_wait<0>();
         return;
     }
-    const int k_end = min(ctx, k_begin + tps * 64);
+    const int ctx = a.ctx_base + step_now;
+    const int k_end = min(ctx, k_begin + a.tps * 64);
     const int n_chunks = k_end > k_begin ? (k_end - k_begin + kAttnChunk - 1) / kAttnChunk : 0;
     const int n_mine = n_chunks > warp ? (n_chunks - warp + 3) / 4 : 0;
 #pragma unroll
@@ -456,9 +426,9 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
     float acc[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
     const int dp = lane * 2;                                      // PV role: this lane's pair of head dims
     for (int i = 0; i < n_mine; ++i) {
-        const int slot = (ring0 + i) % ST;
+        const int slot = i % ST;
         if constexpr (BULK) {
-            bar_wait_parity(&sm.full[warp][slot], (uint32_t)((ring0 + i) / ST) & 1u);
+            bar_wait_parity(&sm.full[warp][slot], (uint32_t)(i / ST) & 1u);
         } else {
             cp_async_wait<ST - 1>();                              // chunk i has landed (this thread's pieces) ...
             __syncwarp();                                         // ... and everybody else's
@@ -557,9 +527,6 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
         if (lane == 0) { sm.ml[warp][h][0] = m_run[h]; sm.ml[warp][h][1] = l_run[h]; }
     }
     __syncthreads();
-    // CTAs that share the keys of this (row, kv head): the shares of a work list, else the static split
-    const int mparts = nparts > 1 ? nparts : a.nsplit, mpart = nparts > 1 ? part : split;
-    const int mstride = nparts > 1 ? kAttnDynParts : a.nsplit;
     for (int e = tid; e < 3 * kHeadDim; e += 128) {               // merge the four warp states (fixed order)
         const int h = e >> 6, d = e & 63;
         float m = sm.ml[0][h][0];
@@ -573,43 +540,342 @@ __global__ void __launch_bounds__(128, 3) decode_attention_warp_kernel(const Dec
             num += sc_w * sm.red[w][h][d];
             den += sc_w * sm.ml[w][h][1];
         }
-        if (mparts == 1) {
+        if (a.nsplit == 1) {
             store_planes1(a.out_hi, a.out_lo, (size_t)b * kHidden + (kvh * 3 + h) * kHeadDim + d, num / den);
-        } else {                                                  // partial state of this share of the keys
-            const size_t o = ((size_t)b * kHeads + kvh * 3 + h) * mstride + mpart;
+        } else {
+            const size_t o = (((size_t)b * kHeads + kvh * 3 + h) * a.nsplit + split);
             a.part_acc[o * kHeadDim + d] = num;
             if (d == 0) { a.part_ml[o * 2] = m; a.part_ml[o * 2 + 1] = den; }
         }
     }
-    if (mparts > 1 && (nparts > 1 || a.self_merge)) {
-        // whichever of the mparts CTAs of this (row, kv head) finishes last merges their states, always in share order
-        // (no combine kernel: one dependent launch less per layer for the batches whose keys are split statically)
-        __shared__ int s_last;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-            int* cnt = a.merge_count + b * kKvHeads + kvh;
-            const int old = atomicAdd(cnt, 1);
-            s_last = old == mparts - 1;
-            if (s_last) *cnt = 0;                                  // ready for the next layer's launch
+    if (tid == 0) trace_close(a.trace, trec, a.trace_id);
+}
+
+// The same kernel following a WORK LIST (DecodeAttnArgs::assign): launched instead of the plain kernel
+// above once two thirds of the rows have finished, so that the CTAs of finished rows take key shares of the rows
+// still decoding and the last CTA of a (row, kv head) merges the shares.  A separate function on purpose: carrying the
+// work-list code in the plain kernel, even as a dead template branch, cost it 0.8 - 3 % (builds A/B'd against each
+// other inside one gpurun call, profiles/r2_lib_ab_*.jsonl).  Only instantiated with BULK = DYN = true.
+template <typename T, int ST, bool BULK, bool DYN>
+__global__ void __launch_bounds__(128, 3) decode_attention_share_kernel(const DecodeAttnArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    using SM = DecodeSmemW<T, ST, BULK>;
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);
+    constexpr bool F24 = sizeof(T) == 3;
+    constexpr int ROWB = SM::ROWB;
+    constexpr int NCHB = ROWB / 16;               // 16-byte pieces per cached row
+    constexpr int E = F24 ? 8 : 16 / sizeof(T);   // values per 16 B piece of the part the score role walks
+    constexpr int NCH = kHeadDim / E;
+    constexpr int NST = NCH / 2;                  // pieces each half of a lane pair walks
+    const int split = blockIdx.x, kvh = blockIdx.y, slot_b = blockIdx.z;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // What this CTA works on: row b, share `part` of `nparts` of its keys (nparts = 0: nothing).  Plain kernel: its own
+    // row, the static split.  DYN: the entry of this slot in the work list (DecodeAttnArgs::assign).
+    int b = slot_b, part = 0, nparts = 1, tps = a.tps;
+    int k_begin = split * a.tps * 64;             // static ownership of the key range, like the tile kernel
+    const unsigned char* kb = reinterpret_cast<const unsigned char*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
+    const unsigned char* vb = reinterpret_cast<const unsigned char*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
+    auto take = [&](int v, int ctx_now) {
+        b = v & 0xff; part = (v >> 8) & 0xff; nparts = (v >> 16) & 0xff;
+        if (b >= a.B || nparts > kAttnDynParts || part >= nparts) nparts = 0;   // only a stale speculative read can look like this
+        const bool shared = nparts > 1;
+        tps = shared ? ((ctx_now + 63) / 64 + nparts - 1) / nparts : a.tps;
+        k_begin = (shared ? part : split) * tps * 64;
+        kb = reinterpret_cast<const unsigned char*>(a.kc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
+        vb = reinterpret_cast<const unsigned char*>(a.vc) + ((size_t)b * kKvHeads + kvh) * a.t_max * ROWB;
+    };
+
+    // chunk i of this warp = keys [k_begin + 16 * (warp + 4 i), +16), staged in ring slot i % ST.  DYN: ring position
+    // ring0 + i, ring0 = number of early requests that were dropped (the plain kernel keeps the static arithmetic)
+    [[maybe_unused]] int ring0 = 0;
+    auto ring = [&](int i) { if constexpr (DYN) return ring0 + i; else return i; };
+    auto load_chunk = [&](int i, int ctx_limit) {
+        const int key0 = k_begin + kAttnChunk * (warp + 4 * i);
+        const int slot = ring(i) % ST;
+        if constexpr (BULK) {
+            if (lane == 0) {
+                // rows at and beyond ctx_limit are not copied: their slots keep zeros / older finite rows and are masked
+                const uint32_t bytes = (uint32_t)(min(kAttnChunk, ctx_limit - key0) * ROWB);
+                unsigned long long* bar = &sm.full[warp][slot];
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic reads of the slot -> async writes
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                             ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(2u * bytes) : "memory");
+                bulk_load(&sm.k[warp][slot][0][0], kb + (size_t)key0 * ROWB, bytes, bar);
+                bulk_load(&sm.v[warp][slot][0][0], vb + (size_t)key0 * ROWB, bytes, bar);
+            }
+        } else {
+            unsigned char (*kd)[SM::KROWB] = sm.k[warp][slot];
+            unsigned char (*vd)[ROWB] = sm.v[warp][slot];
+            for (int c = lane; c < kAttnChunk * NCHB; c += 32) {
+                const int j = c / NCHB, ch = c - j * NCHB;
+                const bool ok = key0 + j < ctx_limit;
+                const size_t off = (size_t)(ok ? key0 + j : 0) * ROWB + ch * 16;
+                cp_async16(&kd[j][ch * 16], kb + off, ok);
+                cp_async16(&vd[j][ch * 16], vb + off, ok);
+            }
         }
-        __syncthreads();
-        if (s_last) {
-            __threadfence();
-            for (int e = tid; e < 3 * kHeadDim; e += 128) {
-                const int h = e >> 6, d = e & 63;
-                const size_t base = ((size_t)b * kHeads + kvh * 3 + h) * mstride;
-                float m = -INFINITY;
-                for (int s = 0; s < mparts; ++s) m = fmaxf(m, __ldcg(a.part_ml + (base + s) * 2));
-                float num = 0.f, den = 0.f;
-                for (int s = 0; s < mparts; ++s) {
-                    const float ms = __ldcg(a.part_ml + (base + s) * 2);
-                    if (ms == -INFINITY) continue;                 // a share without keys
-                    const float w = expf(ms - m);
-                    num += w * __ldcg(a.part_acc + (base + s) * kHeadDim + d);
-                    den += w * __ldcg(a.part_ml + (base + s) * 2 + 1);
+    };
+    pdl_trigger();
+    unsigned trec = kTraceNone;
+    if (tid == 0) trec = trace_open(a.trace, a.trace_id);
+    if constexpr (BULK) {
+        if (lane < ST) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&sm.full[warp][lane])) : "memory");
+        }
+        // value slots start as zeros: a partially filled last chunk leaves rows the copy did not touch, and 0 * NaN would
+        // poison the accumulators (their probabilities are exactly zero)
+        for (int c = lane; c < ST * kAttnChunk * ROWB / 16; c += 32)
+            reinterpret_cast<uint4*>(&sm.v[warp][0][0][0])[c] = make_uint4(0u, 0u, 0u, 0u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncwarp();
+    }
+    // PDL: chunks that lie inside the prefill prefix are immutable history and are requested before the wait -- as if
+    // this slot worked on its own row from its first key, which is what every row that is still decoding does (a row's
+    // own slot keeps share 0 of a work list): nothing here waits for a load.
+    int n_early = 0;
+    auto request_early = [&]() {
+        n_early = 0;
+#pragma unroll
+        for (int i = 0; i < ST; ++i) {
+            if (n_early == i && k_begin + kAttnChunk * (warp + 4 * i + 1) <= a.ctx_base && warp + 4 * i < tps * 4) {
+                load_chunk(i, a.ctx_base);
+                if (!BULK) cp_async_commit();
+                n_early = i + 1;
+            }
+        }
+    };
+    auto drop_early = [&]() {                                     // the requested chunks are not this CTA's keys: let them land
+        if constexpr (BULK) {
+            for (int i = 0; i < n_early; ++i)
+                bar_wait_parity(&sm.full[warp][(ring0 + i) % ST], (uint32_t)((ring0 + i) / ST) & 1u);
+        } else cp_async_wait<0>();
+        __syncwarp();
+        ring0 += n_early; n_early = 0;                            // the ring goes on behind them
+    };
+    request_early();
+    [[maybe_unused]] int b_early = b, k_early = k_begin;
+    if constexpr (DYN) {
+        // The slot of a finished row works on a key share of another row.  Its work list entry and the step counter are
+        // read SPECULATIVELY here (their producers are several kernels back, but the chain of early launches gives no
+        // guarantee) and checked after the wait; a stale guess only costs the early requests.
+        const int v_spec = (int)__ldcg(a.assign + slot_b);
+        if (((v_spec >> 16) & 0xff) > 1 && ((v_spec & 0xff) != slot_b || ((v_spec >> 8) & 0xff) != 0)) {
+            const int ctx_spec = a.ctx_base + (a.d_step ? (int)__ldcg(a.d_step) : 0);
+            drop_early();
+            take(v_spec, ctx_spec);
+            if (nparts > 1) { request_early(); b_early = b; k_early = k_begin; }
+        }
+    }
+    pdl_wait();
+    if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, TR_WAITED);
+    const int step_now = a.d_step ? *a.d_step : 0;
+    const int ctx = a.ctx_base + step_now;
+    if constexpr (DYN) {
+        // the slots of finished rows are handed a share of the keys of the rows still decoding
+        take(a.assign[slot_b], ctx);
+        if (n_early > 0 && (nparts == 0 || b != b_early || k_begin != k_early)) drop_early();
+        if (nparts == 0) return;                                  // idle slot
+    } else if (a.done && a.done[b]) {                             // finished row: no K/V stream
+        if constexpr (BULK) { for (int i = 0; i < n_early; ++i) bar_wait_parity(&sm.full[warp][i], 0); }
+        else cp_async_wait<0>();
+        return;
+    }
+    const int k_end = min(ctx, k_begin + tps * 64);
+    const int n_chunks = k_end > k_begin ? (k_end - k_begin + kAttnChunk - 1) / kAttnChunk : 0;
+    const int n_mine = n_chunks > warp ? (n_chunks - warp + 3) / 4 : 0;
+#pragma unroll
+    for (int i = 0; i < ST; ++i) {                                // fill the ring: one commit group per slot, empty or not
+        if (i >= n_early) {
+            if (i < n_mine) load_chunk(i, ctx);
+            if (!BULK) cp_async_commit();
+        }
+    }
+    // score role: lane = (key j, half); each half owns every other 16 B piece of the key row.  BULK: the pieces are
+    // walked in an order rotated by the key index so that unpadded rows are read without bank conflicts.
+    const int sj = lane >> 1, shalf = lane & 1;
+    const int rot = !BULK ? 0 : (F24 ? (sj >> 1) & (NST - 1) : sj & (NST - 1));
+    float qreg[3][kHeadDim / 2];
+    {
+        const float* qb = a.q + (size_t)b * kHidden + (kvh * 3) * kHeadDim;
+#pragma unroll
+        for (int h = 0; h < 3; ++h)
+#pragma unroll
+            for (int i = 0; i < NST; ++i) {
+                const int piece = 2 * ((i + rot) & (NST - 1)) + shalf;
+#pragma unroll
+                for (int e = 0; e < E; e += 4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(qb + h * kHeadDim + piece * E + e);
+                    qreg[h][i * E + e] = t4.x * 0.125f; qreg[h][i * E + e + 1] = t4.y * 0.125f;      // head_dim^-0.5, exact
+                    qreg[h][i * E + e + 2] = t4.z * 0.125f; qreg[h][i * E + e + 3] = t4.w * 0.125f;
                 }
-                store_planes1(a.out_hi, a.out_lo, (size_t)b * kHidden + (kvh * 3 + h) * kHeadDim + d, num / den);
+            }
+    }
+    float m_run[3] = {-INFINITY, -INFINITY, -INFINITY}, l_run[3] = {0.f, 0.f, 0.f};
+    float acc[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+    const int dp = lane * 2;                                      // PV role: this lane's pair of head dims
+    for (int i = 0; i < n_mine; ++i) {
+        const int slot = ring(i) % ST;
+        if constexpr (BULK) {
+            bar_wait_parity(&sm.full[warp][slot], (uint32_t)(ring(i) / ST) & 1u);
+        } else {
+            cp_async_wait<ST - 1>();                              // chunk i has landed (this thread's pieces) ...
+            __syncwarp();                                         // ... and everybody else's
+        }
+        const int key0 = k_begin + kAttnChunk * (warp + 4 * i);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+        {
+            const unsigned char* rowp = sm.k[warp][slot][sj];
+#pragma unroll
+            for (int c = 0; c < NST; ++c) {
+                const int piece = 2 * ((c + rot) & (NST - 1)) + shalf;
+                if constexpr (F24) {
+                    const uint4 hv = *reinterpret_cast<const uint4*>(rowp + piece * 16);
+                    const uint2 lv = *reinterpret_cast<const uint2*>(rowp + 128 + piece * 8);
+                    const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float k0 = f24_unpack_even(hw[p], p < 2 ? lv.x : lv.y, p & 1);
+                        const float k1 = f24_unpack_odd(hw[p], p < 2 ? lv.x : lv.y, p & 1);
+                        s0 += qreg[0][c * E + 2 * p] * k0; s1 += qreg[1][c * E + 2 * p] * k0; s2 += qreg[2][c * E + 2 * p] * k0;
+                        s0 += qreg[0][c * E + 2 * p + 1] * k1; s1 += qreg[1][c * E + 2 * p + 1] * k1; s2 += qreg[2][c * E + 2 * p + 1] * k1;
+                    }
+                } else {
+                    const T* kp = reinterpret_cast<const T*>(rowp) + piece * E;
+#pragma unroll
+                    for (int e = 0; e < E; ++e) {
+                        const float kvv = kv_load(kp + e);
+                        s0 += qreg[0][c * E + e] * kvv; s1 += qreg[1][c * E + e] * kvv; s2 += qreg[2][c * E + e] * kvv;
+                    }
+                }
+            }
+        }
+        float sc[3] = {s0, s1, s2};
+        const bool ok = key0 + sj < ctx;
+        float al[3];
+#pragma unroll
+        for (int h = 0; h < 3; ++h) {
+            float s = sc[h] + __shfl_xor_sync(0xffffffffu, sc[h], 1);         // the two halves of the head dim
+            s = ok ? s : -INFINITY;
+            float mt = s;
+#pragma unroll
+            for (int o = 2; o < 32; o <<= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+            const float m_new = fmaxf(m_run[h], mt);                          // finite: the chunk holds >= 1 valid key
+            const float e = expf(s - m_new);
+            float ls = e;
+#pragma unroll
+            for (int o = 2; o < 32; o <<= 1) ls += __shfl_xor_sync(0xffffffffu, ls, o);
+            al[h] = expf(m_run[h] - m_new);
+            l_run[h] = l_run[h] * al[h] + ls;
+            m_run[h] = m_new;
+            if (shalf == 0) sm.p[warp][h][sj] = e;
+        }
+        __syncwarp();
+        {
+            float x[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+#pragma unroll
+            for (int jj = 0; jj < kAttnChunk; jj += 4) {
+                float4 p[3];
+#pragma unroll
+                for (int h = 0; h < 3; ++h) p[h] = *reinterpret_cast<const float4*>(&sm.p[warp][h][jj]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float v0, v1;
+                    const unsigned char* rowp = sm.v[warp][slot][jj + u];
+                    if constexpr (F24) {
+                        const uint32_t hw = *reinterpret_cast<const uint32_t*>(rowp + dp * 2);
+                        const uint32_t lb = *reinterpret_cast<const unsigned short*>(rowp + 128 + dp);
+                        v0 = f24_unpack_even(hw, lb, 0);
+                        v1 = f24_unpack_odd(hw, lb, 0);
+                    } else {
+                        const T* vp = reinterpret_cast<const T*>(rowp);
+                        v0 = kv_load(vp + dp); v1 = kv_load(vp + dp + 1);
+                    }
+#pragma unroll
+                    for (int h = 0; h < 3; ++h) {
+                        const float pv = u == 0 ? p[h].x : (u == 1 ? p[h].y : (u == 2 ? p[h].z : p[h].w));
+                        x[h][0] += pv * v0; x[h][1] += pv * v1;
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 3; ++h) {
+                acc[h][0] = acc[h][0] * al[h] + x[h][0];
+                acc[h][1] = acc[h][1] * al[h] + x[h][1];
+            }
+        }
+        __syncwarp();                                             // the slot and sm.p are reused
+        if (i + ST < n_mine) load_chunk(i + ST, ctx);
+        if (!BULK) cp_async_commit();
+    }
+    if (!BULK) cp_async_wait<0>();
+    if constexpr (BULK && DYN) {                                  // early requests beyond a shortened share: let them land
+        for (int i = n_mine; i < n_early; ++i) bar_wait_parity(&sm.full[warp][ring(i) % ST], (uint32_t)(ring(i) / ST) & 1u);
+    }
+    if (tid == 0 && first_cta()) trace_put(a.trace, trec, a.trace_id, 5);           // this warp's keys consumed
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+        sm.red[warp][h][dp] = acc[h][0]; sm.red[warp][h][dp + 1] = acc[h][1];
+        if (lane == 0) { sm.ml[warp][h][0] = m_run[h]; sm.ml[warp][h][1] = l_run[h]; }
+    }
+    __syncthreads();
+    for (int e = tid; e < 3 * kHeadDim; e += 128) {               // merge the four warp states (fixed order)
+        const int h = e >> 6, d = e & 63;
+        float m = sm.ml[0][h][0];
+#pragma unroll
+        for (int w = 1; w < 4; ++w) m = fmaxf(m, sm.ml[w][h][0]);
+        float num = 0.f, den = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float mw = sm.ml[w][h][0];
+            const float sc_w = mw == -INFINITY ? 0.f : expf(mw - m);          // a warp without keys contributes nothing
+            num += sc_w * sm.red[w][h][d];
+            den += sc_w * sm.ml[w][h][1];
+        }
+        if (DYN && nparts > 1) {                                  // key share of a work list: partial state of this share
+            const size_t o = ((size_t)b * kHeads + kvh * 3 + h) * kAttnDynParts + part;
+            a.part_acc[o * kHeadDim + d] = num;
+            if (d == 0) { a.part_ml[o * 2] = m; a.part_ml[o * 2 + 1] = den; }
+        } else if (a.nsplit == 1) {
+            store_planes1(a.out_hi, a.out_lo, (size_t)b * kHidden + (kvh * 3 + h) * kHeadDim + d, num / den);
+        } else {                                                  // static split: decode_combine_kernel merges
+            const size_t o = (((size_t)b * kHeads + kvh * 3 + h) * a.nsplit + split);
+            a.part_acc[o * kHeadDim + d] = num;
+            if (d == 0) { a.part_ml[o * 2] = m; a.part_ml[o * 2 + 1] = den; }
+        }
+    }
+    if constexpr (DYN) {
+        if (nparts > 1) {
+            // whichever of the nparts CTAs of this (row, kv head) finishes last merges their states, always in share order.
+            // (The same in-kernel merge for the STATIC splits of small batches instead of the combine kernel was measured
+            // 3 % slower per step -- fence + atomic + re-read cost more than a dependent launch -- and is not built:
+            // profiles/r2_decode_ab_self_merge.jsonl.)
+            __shared__ int s_last;
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                int* cnt = a.merge_count + b * kKvHeads + kvh;
+                const int old = atomicAdd(cnt, 1);
+                s_last = old == nparts - 1;
+                if (s_last) *cnt = 0;                              // ready for the next layer's launch
+            }
+            __syncthreads();
+            if (s_last) {
+                __threadfence();
+                for (int e = tid; e < 3 * kHeadDim; e += 128) {
+                    const int h = e >> 6, d = e & 63;
+                    const size_t base = ((size_t)b * kHeads + kvh * 3 + h) * kAttnDynParts;
+                    float m = -INFINITY;
+                    for (int s = 0; s < nparts; ++s) m = fmaxf(m, __ldcg(a.part_ml + (base + s) * 2));
+                    float num = 0.f, den = 0.f;
+                    for (int s = 0; s < nparts; ++s) {
+                        const float ms = __ldcg(a.part_ml + (base + s) * 2);
+                        if (ms == -INFINITY) continue;             // a share without keys
+                        const float w = expf(ms - m);
+                        num += w * __ldcg(a.part_acc + (base + s) * kHeadDim + d);
+                        den += w * __ldcg(a.part_ml + (base + s) * 2 + 1);
+                    }
+                    store_planes1(a.out_hi, a.out_lo, (size_t)b * kHidden + (kvh * 3 + h) * kHeadDim + d, num / den);
+                }
             }
         }
     }
@@ -744,34 +1010,38 @@ __global__ void __launch_bounds__(160) add_rmsnorm_row_kernel(float* __restrict_
     if (t == 0) trace_close(trace, trec, trace_id);
 }
 
-// step += 1; records the first step count at which every row has emitted eos (wrapper.py:247-249).  assign != nullptr
-// (B <= 128 = blockDim): also the work list of the next step's decode attention (DecodeAttnArgs::assign).  With n rows
-// still decoding and m = B - n finished, every live row is cut into P = min(kAttnDynParts, B / n) key shares: the row's
-// own slot keeps share 0 (its keys from 0 on: what it requests before its dependency wait stays valid), the j-th
-// finished slot takes share 1 + j / n of the (j % n)-th live row, the remaining finished slots idle.
-__global__ void __launch_bounds__(128) step_advance_kernel(int* d_step, const int* done, int B, int* d_stop_step, int* assign) {
-    __shared__ int all;
+// step += 1; records the first step count at which every row has emitted eos (wrapper.py:247-249) and, for the host's
+// sparse poll, the number of finished rows (d_stop_step[1]).  assign != nullptr (B <= 128 = blockDim): also the work
+// list of the next step's decode attention (DecodeAttnArgs::assign).  With n rows still decoding and m = B - n
+// finished, every live row is cut into P = min(kAttnDynParts, B / n) key shares (P >= 3, else none: two shares
+// measured no faster than just dropping the finished rows' streams): the row's own slot keeps share 0 (its keys from 0
+// on: what it requests before its dependency wait stays valid), the j-th finished slot takes share 1 + j / n of the
+// (j % n)-th live row, the remaining finished slots idle.  advance = 0: only (re)build the list (the decode loop does
+// this once when it switches to the work-list attention kernel).
+__global__ void __launch_bounds__(128) step_advance_kernel(int* d_step, const int* done, int B, int* d_stop_step, int* assign,
+                                                           int advance) {
     __shared__ int wcnt[4];
     __shared__ int act[128];
     pdl_trigger();
     pdl_wait();
-    if (threadIdx.x == 0) all = 1;
-    __syncthreads();
-    for (int b = threadIdx.x; b < B; b += blockDim.x)
-        if (!done[b]) all = 0;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int unfinished = 0;
+    for (int b = t; b < B; b += blockDim.x) unfinished |= !done[b];
+    const int n_live = __syncthreads_count(unfinished);         // B <= 128: the number of live rows; else only 0 / non-0 matters
     if (assign != nullptr) {
-        const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
         const bool live = t < B && !done[t];
         const unsigned bal = __ballot_sync(0xffffffffu, live);
         if (lane == 0) wcnt[warp] = __popc(bal);
         __syncthreads();
-        int pos = __popc(bal & ((1u << lane) - 1u)), n = 0;     // live rows before this one; live rows in all
-        for (int w = 0; w < 4; ++w) { if (w < warp) pos += wcnt[w]; n += wcnt[w]; }
+        int pos = __popc(bal & ((1u << lane) - 1u));             // live rows before this one
+        for (int w = 0; w < warp; ++w) pos += wcnt[w];
+        const int n = n_live;
         if (live) act[pos] = t;
         __syncthreads();
         if (t < B) {
             int P = n > 0 ? B / n : 0;
             if (P > kAttnDynParts) P = kAttnDynParts;
+            if (P < 3) P = 1;                                    // two shares do not pay for the merge (measured): plain skip
             const int j = t - pos;                               // finished rows before this one
             int v = 0;
             if (live) v = t | (P << 16);
@@ -779,11 +1049,11 @@ __global__ void __launch_bounds__(128) step_advance_kernel(int* d_step, const in
             assign[t] = v;
         }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    if (t == 0 && advance) {
         const int s = *d_step + 1;
         *d_step = s;
-        if (all && *d_stop_step < 0) *d_stop_step = s;
+        if (n_live == 0 && *d_stop_step < 0) *d_stop_step = s;
+        d_stop_step[1] = B <= 128 ? B - n_live : 0;
     }
 }
 
@@ -810,8 +1080,19 @@ cudaError_t launch_prefix(const float* rows33, const int* ids, const float* embe
     return launch_k(prefix_kernel, grid, dim3(144), 0, st, rows33, ids, embed, B, prefix);
 }
 
+template <typename T, int ST>
+cudaError_t launch_decode_attention_share(const DecodeAttnArgs& a, dim3 grid, cudaStream_t st) {
+    static bool configured[kMaxDevices] = {};
+    auto kern = decode_attention_share_kernel<T, ST, true, true>;
+    if (cudaError_t e = ensure_smem(kern, sizeof(DecodeSmemW<T, ST, true>), configured); e != cudaSuccess) return e;
+    return launch_k(kern, grid, dim3(128), sizeof(DecodeSmemW<T, ST, true>), st, a);
+}
 template <typename T, int ST, bool BULK>
 cudaError_t launch_decode_attention_warp(const DecodeAttnArgs& a, dim3 grid, cudaStream_t st) {
+    if (a.assign != nullptr) {                            // the work-list kernel exists for the product kernel (bulk copies) only
+        if constexpr (BULK) return launch_decode_attention_share<T, ST>(a, grid, st);
+        else return cudaErrorNotSupported;
+    }
     static bool configured[kMaxDevices] = {};
     auto kern = decode_attention_warp_kernel<T, ST, BULK>;
     if (cudaError_t e = ensure_smem(kern, sizeof(DecodeSmemW<T, ST, BULK>), configured); e != cudaSuccess) return e;
@@ -844,7 +1125,7 @@ cudaError_t launch_decode_attention(const DecodeAttnArgs& a, cudaStream_t st) {
         return cudaErrorNotSupported;                     // variants 0 / 1 exist in lab builds only (MB_BUILD_LAB=1)
 #endif
     }
-    if (e != cudaSuccess || a.nsplit == 1 || (a.variant != 0 && a.self_merge)) return e;   // the warp kernels can merge their splits themselves
+    if (e != cudaSuccess || a.nsplit == 1) return e;
     return launch_k(decode_combine_kernel, dim3(kHeads, a.B), dim3(64), 0, st, a);
 }
 
@@ -865,9 +1146,9 @@ cudaError_t launch_sample(const SampleArgs& a, cudaStream_t st) {
     return launch_k(sample_kernel, dim3(a.B), dim3(1024), 0, st, a);
 }
 
-cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, int* assign, cudaStream_t st) {
+cudaError_t launch_step_advance(int* d_step, const int* done, int B, int* d_stop_step, int* assign, int advance, cudaStream_t st) {
     if (assign != nullptr && B > 128) return cudaErrorInvalidValue;
-    return launch_k(step_advance_kernel, dim3(1), dim3(128), 0, st, d_step, done, B, d_stop_step, assign);
+    return launch_k(step_advance_kernel, dim3(1), dim3(128), 0, st, d_step, done, B, d_stop_step, assign, advance);
 }
 
 }  // namespace mb

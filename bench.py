@@ -337,7 +337,7 @@ def run_ours(args):
     alg_bytes = 2 * Bp * KV_HEADS * ctx * HEAD_DIM * kv_bytes + 2 * Bp * HIDDEN * 4
     achieved = alg_bytes / (ms_attn * 1e-3) / 1e9
     traffic, traffic_src = None, None
-    tname = {3: "r2_decode_attention_warp_kv24_b128_ctx539_ncu_full.json"}.get(kv_bytes)
+    tname = {3: "r2_decode_attention_final_tree_b128_ctx539_ncu_full.json"}.get(kv_bytes)
     tpath = os.path.join(ROOT, "profiles", tname) if tname else ""
     if tpath and os.path.isfile(tpath) and Bp == 128 and ctx == 539:
         with open(tpath) as f:                       # dram__bytes_read+write per launch from the committed ncu --set full capture

@@ -956,8 +956,14 @@ int mb_set_option(void* hv, const char* name, int value) {
     const std::string n = name ? name : "";
     if (n == "graph") h->use_graph = value != 0;
     else if (n == "decode_unfused") h->decode_unfused = value != 0;
-    else if (n == "skip_finished") h->skip_finished = value != 0;
-    else if (n == "share_keys") h->share_keys = value != 0;
+    else if (n == "skip_finished") {
+        if (h->skip_finished == (value != 0)) return 0;       // the wrapper sets it on every call: keep the captured graphs
+        h->skip_finished = value != 0;
+    }
+    else if (n == "share_keys") {
+        if (h->share_keys == (value != 0)) return 0;
+        h->share_keys = value != 0;
+    }
     else if (n == "kv_prefetch") h->kv_prefetch = value;
     else if (n == "wide_tiles") h->wide_tiles = value;
     else if (n == "decode_tails") h->decode_tails = value;
